@@ -1,0 +1,98 @@
+"""Pins the CPU restatement (oracle/lfm_oracle.c) AND the host-side flattening (lfm_public_b200/host/flatten.cpp)
+against the reference's own CPU solver: oracle/_ref/lfm_solve_ref is /root/reference/src/*.cpp + info/lfm_solve.cpp
+compiled unchanged (oracle/Makefile).  Same case directory in, fields after N steps and every halo message out.
+
+fp64: bit-exact (the restatement follows the reference's loops and expression trees; gcc emits no FMA).
+fp32: 1e-5 relative max-norm is the north_star bar; the restatement is also expected to be bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import common
+import oracle_lib
+from common import CASES, N_STEPS
+
+needs_ref = pytest.mark.skipif(not common.have_ref(), reason="oracle/_ref/lfm_solve_ref not built (needs /root/reference)")
+
+
+def _run_pair(name, tmp_path, sp=False, **override):
+    case_dir = str(tmp_path / name)
+    m, o = common.build_case(name, case_dir, doublePrecision=not sp, **override)
+    common.run_reference(case_dir, o, sp=sp)
+    cases = common.open_ranks(case_dir, o)
+    oracles = [oracle_lib.Oracle(c) for c in cases]
+    return case_dir, o, cases, oracles
+
+
+@needs_ref
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_fields_match_reference_fp64(name, tmp_path):
+    case_dir, o, cases, oracles = _run_pair(name, tmp_path)
+    res = oracle_lib.run(oracles, o["solver"], o["deltaT"], N_STEPS, want_res=True)
+    D = o["dimension"]
+    ref = common.read_reference_q(case_dir, o, o["deltaT"] * N_STEPS, D)
+    for r, (c, orc) in enumerate(zip(cases, oracles)):
+        q = c.to_mesh_order(orc.download(0))
+        mine = common.primitives_from_q(q, c.desc.c.gamma_m1)
+        assert ref[r]["rho"].std() > 0 and len(ref[r]["rho"]) == c.desc.n_cells      # not a vacuous comparison
+        for k in ("rho", "U", "E", "p"):
+            assert np.array_equal(mine[k], ref[r][k]), f"{name} rank {r} field {k}: rel max {common.rel_max(mine[k], ref[r][k]):.3e}"
+    assert np.isfinite(res).all() and (res > 0).all()
+
+
+@needs_ref
+@pytest.mark.parametrize("name", [n for n in sorted(CASES) if CASES[n]["blocks"]])
+def test_halo_messages_bit_exact(name, tmp_path):
+    """Every MPI_Isend payload of the reference (pre-loop warm-up + all stages) equals the restatement's pack output."""
+    case_dir, o, cases, oracles = _run_pair(name, tmp_path)
+    record = {}
+    oracle_lib.lockstep_run(oracles, cases, o["solver"], o["deltaT"], N_STEPS, record=record)
+    assert record
+    n_msgs = 0
+    for (src, dst), msgs in record.items():
+        ref = common.read_dump(case_dir, src, dst, np.float64)
+        assert len(ref) == len(msgs), f"{src}->{dst}: {len(ref)} reference messages vs {len(msgs)}"
+        for i, ((tag, a), b) in enumerate(zip(ref, msgs)):
+            assert a.shape == b.shape and a.tobytes() == b.tobytes(), f"{name} {src}->{dst} message {i} differs"
+            n_msgs += 1
+    assert n_msgs == 2 * (1 + N_STEPS * 5) * len(record)
+    # and the lockstep (per-function) driver agrees with lfmo_run
+    others = [oracle_lib.Oracle(c) for c in cases]
+    oracle_lib.run(others, o["solver"], o["deltaT"], N_STEPS)
+    for a, b in zip(oracles, others):
+        assert np.array_equal(a.download(0), b.download(0))
+
+
+@needs_ref
+@pytest.mark.skipif(not common.have_ref(sp=True), reason="single-precision reference not built")
+@pytest.mark.parametrize("name", ["quad2d_m1", "hex3d_m2_p4", "tri2d_m2"])
+def test_fields_match_reference_fp32(name, tmp_path):
+    case_dir, o, cases, oracles = _run_pair(name, tmp_path, sp=True)
+    oracle_lib.run(oracles, o["solver"], o["deltaT"], N_STEPS)
+    D = o["dimension"]
+    ref = common.read_reference_q(case_dir, o, o["deltaT"] * N_STEPS, D)
+    for r, (c, orc) in enumerate(zip(cases, oracles)):
+        q = c.to_mesh_order(orc.download(0)).astype(np.float32)
+        assert common.rel_max(q[:, 0], ref[r]["rho"]) <= 1e-5
+        assert common.rel_max(q[:, 1:D + 1] / q[:, :1], ref[r]["U"]) <= 1e-5
+        assert common.rel_max(q[:, D + 1] / q[:, 0], ref[r]["E"]) <= 1e-5
+
+
+@needs_ref
+def test_cfl_matches_reference_printout(tmp_path):
+    """compute_cfl (cfd_v0.cpp:2887) against the value the reference prints each step (10 significant digits)."""
+    name = "quad2d_m1"
+    case_dir = str(tmp_path / name)
+    m, o = common.build_case(name, case_dir)
+    out = common.run_reference(case_dir, o)
+    cfls = [float(l.split("CFL:")[1].split()[0]) for l in out.splitlines() if "CFL:" in l]
+    cases = common.open_ranks(case_dir, o)
+    orc = oracle_lib.Oracle(cases[0])
+    mine = []
+    for s in range(N_STEPS):
+        oracle_lib.run([orc], o["solver"], o["deltaT"], 1, first=(s == 0))
+        mine.append(orc.cfl(o["deltaT"]))
+    assert len(cfls) == N_STEPS
+    assert np.allclose(mine, cfls, rtol=2e-10, atol=0)
