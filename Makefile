@@ -21,7 +21,7 @@ GPU_SRC  := $(CSRC)/lfmgpu.cu
 GPU_HDR  := $(wildcard $(CSRC)/*.cuh) $(INC)/lfmgpu.h
 
 .PHONY: all host gpu driver oracle ref clean
-all: host gpu driver oracle
+all: host gpu oracle
 
 host: $(PKG)/liblfmhost.so
 $(PKG)/liblfmhost.so: $(HOST_SRC) $(HOST)/foam_io.h $(HOST)/flatten.h $(INC)/lfmhost.h $(INC)/lfmgpu.h

@@ -135,10 +135,23 @@ int lfmgpu_residual(lfmgpu_t h, double* res);                /* D+2 sums of RES^
  * prepare_for_timestep; per stage: prepare_for_RKstep, mpi_wait(0), set_bc, [gradients], vis(bnd),
  * halo(1) overlapped with vis(int), rk_stage(bnd), halo(0) overlapped with rk_stage(int); final wait. */
 int lfmgpu_step(lfmgpu_t h, int scheme, double dt, int n_steps, int minmod, int want_res);
+/* The pre-loop warm-up of Mesh::solve (mesh_solver.cpp:409-428): halo(0), set_bc, wait(0), halo(1), wait(1). */
+int lfmgpu_warmup(lfmgpu_t h);
+/* Same as lfmgpu_step for ranks that are all handles of this process (in-process transport), advanced in
+ * lockstep; first != 0 runs the warm-up before the first step. */
+int lfmgpu_step_multi(const lfmgpu_t* hs, int n_ranks, int scheme, double dt, int n_steps, int first, int want_res);
+/* The scalar reductions Mesh::solve does with MPI_Allreduce / MPI_Reduce (mesh_solver.cpp:715, 763-779,
+ * cfd_v0.cpp:3242-3243): op 0 = sum, 1 = min, 2 = max over the NCCL ranks, in place, n <= 8; blocking. */
+int lfmgpu_allreduce(lfmgpu_t h, double* values, int n, int op);
+/* Tuning knobs: "use_tiles" 1 (default) = fused shared-memory tile kernels, 0 = face kernel + gather kernels. */
+int lfmgpu_set_option(lfmgpu_t h, const char* name, int value);
 
 /* ---- data movement --------------------------------------------------------------------------------- */
 int lfmgpu_download(lfmgpu_t h, int field, void* dst, size_t dst_bytes);   /* blocking                 */
 int lfmgpu_upload_q(lfmgpu_t h, const void* q, size_t bytes);              /* [n_cells][D+2], blocking */
+/* component-major host arrays [D+2][n_cells] (what a time-directory writer wants), asynchronous on the compute stream */
+int lfmgpu_upload_q_soa_async(lfmgpu_t h, const void* q, size_t bytes);
+int lfmgpu_download_q_soa_async(lfmgpu_t h, void* q, size_t bytes);
 /* pinned host staging for the end-to-end path */
 int lfmgpu_host_alloc(void** p, size_t bytes);
 int lfmgpu_host_free(void* p);
@@ -161,6 +174,8 @@ int lfmgpu_launch_count(lfmgpu_t h, uint64_t* n);            /* kernels launched
  * with CUDA events on the launching stream when timing is enabled */
 int lfmgpu_enable_kernel_timing(lfmgpu_t h, int on);
 int lfmgpu_kernel_time(lfmgpu_t h, const char* prefix, double* total_ms, uint64_t* launches);
+/* shape of the fused-tile plan built at create time (n_tiles == 0: mesh served by the unfused kernels) */
+int lfmgpu_tile_info(lfmgpu_t h, int* n_tiles, int* tile_cells, size_t* smem_bytes, double* halo_face_ratio);
 
 #ifdef __cplusplus
 }

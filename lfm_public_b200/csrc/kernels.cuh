@@ -1,0 +1,548 @@
+// Baseline ("v1") kernels of the per-iteration solve on SoA state.
+//
+// Determinism: every accumulated cell quantity (dudx, dTdx, dq, RES) is produced by ONE thread that
+// walks the cell's faces in ascending face id.  Faces are numbered in the order the reference's stage
+// loops visit them (owner ascending, slot ascending), so ascending face id IS the reference's
+// summation order: first the faces owned by earlier cells, then the cell's own valid
+// faces in slot order.  No atomics anywhere.
+//
+// Kernels (reference function -> kernel):
+//   set_boundary_conditions  cfd_v0.cpp:1010  -> k_set_bc
+//   calc_VIS                 cfd_v0.cpp:1744  -> k_grad_cell      (cell-centric Green-Gauss gather)
+//   one_rk_step_M1/_M2       cfd_v0.cpp:2530/1897 -> k_flux_face (face-ordered) + k_update_cell (gather+sponge+RK)
+//   pack / unpack            cfd_v0.cpp:3303.. / 3608.. -> k_pack / k_unpack
+//   compute_cfl / compute_dt cfd_v0.cpp:2887 / 2913 -> k_cfl_dt
+//   postProcAverage          cfd_v0.cpp:3083  -> k_average
+//   postProcForces           cfd_v0.cpp:3169  -> k_forces_face + k_sum_sequential
+#pragma once
+#include "device_math.cuh"
+
+namespace lfm {
+
+// Device view of one rank (all pointers are device pointers).  SoA: component k of cell c lives at
+// base[k * ncs + c]; per-face arrays at base[k * nfs + f].
+template <class R> struct DevMesh {
+	int n_cells, n_faces, n_bc, n_mpi, n_tot, F;
+	size_t ncs, nfs, ngs;              // strides: cells(+ghosts), faces, mpi ghosts
+	const int *face_owner, *face_neigh;
+	const R *S, *d, *w;                // [D][nfs], [D][nfs], [nfs]
+	const R *vol_inv, *sigma;          // [n_cells]
+	const int* csr;                    // [F][n_cells] signed (face+1), ascending |face|, 0-padded
+	const int* slot;                   // [F][n_cells] signed (face+1) in the reference's slot order
+	R* dq;                             // [NQ][n_cells]
+	R* RES;                            // [NQ][n_cells]
+	R* dudx;                           // [D*D][ncs]
+	R* dTdx;                           // [D][ncs]
+	R* g_tauMC;                        // [D*D][ngs]  as received for MPI ghosts
+	R* g_sigmaU;                       // [D][ngs]
+	R* flux;                           // [NQ][nfs]   materialised face fluxes (v1 path)
+	R *pAVG, *pRMS;
+	const int *bc_cell, *bc_kind, *bc_face, *bc_patch;
+	Consts<R> k;
+};
+
+constexpr int kBlock = 256;
+
+// ---------------------------------------------------------------------------------------------------
+// set_boundary_conditions (cfd_v0.cpp:1010-1133): ghost conservatives of wall / inlet / outlet faces
+// ---------------------------------------------------------------------------------------------------
+template <class R, int D> __global__ void __launch_bounds__(kBlock) k_set_bc(DevMesh<R> m, R* __restrict__ q) {
+	const int g = blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= m.n_bc) return;
+	const int b = m.bc_cell[g];
+	const int kind = m.bc_kind[g];
+	const size_t gi = (size_t)m.n_cells + g;
+	R cq[D + 2];
+#pragma unroll
+	for (int i = 0; i < D + 2; i++) cq[i] = q[i * m.ncs + b];
+	R gq[D + 2];
+	if (kind == 1) {          // wall
+		gq[0] = cq[0];
+#pragma unroll
+		for (int i = 0; i < D; i++) gq[i + 1] = -cq[i + 1];
+		gq[D + 1] = cq[D + 1];
+	} else if (kind == 2 || kind == 3) {
+		const R rhoInt = cq[0];
+		R UvecInt[D];
+		R Umag_sqrtInt = R(0.0);
+#pragma unroll
+		for (int i = 0; i < D; i++) {
+			UvecInt[i] = cq[i + 1] / rhoInt;
+			Umag_sqrtInt += UvecInt[i] * UvecInt[i];
+		}
+		const R pInt = (cq[D + 1] - R(0.5) * Umag_sqrtInt * rhoInt) * m.k.gm1;
+		R rhoExt, pExt, UvecExt[D];
+		if (kind == 2) {      // inlet: T = Tinf, p from inside, U = Uinf
+			const R TInt = pInt * m.k.Rgas_inv / rhoInt;
+			rhoExt = rhoInt * TInt / m.k.TInf;
+			pExt = pInt;
+#pragma unroll
+			for (int i = 0; i < D; i++) UvecExt[i] = m.k.UInf[i];
+		} else {              // outlet: p = pinf, U from inside
+			pExt = m.k.pInf;
+			rhoExt = rhoInt * pExt / pInt;
+#pragma unroll
+			for (int i = 0; i < D; i++) UvecExt[i] = UvecInt[i];
+		}
+		R Umag_sqrtExt = R(0.0);
+#pragma unroll
+		for (int i = 0; i < D; i++) Umag_sqrtExt += UvecExt[i] * UvecExt[i];
+		const R EExt = pExt / (rhoExt * m.k.gm1) + R(0.5) * Umag_sqrtExt;
+		gq[0] = rhoExt;
+#pragma unroll
+		for (int i = 0; i < D; i++) gq[i + 1] = rhoExt * UvecExt[i];
+		gq[D + 1] = rhoExt * EExt;
+	} else {
+		return;               // unknown role: the reference leaves the ghost untouched
+	}
+#pragma unroll
+	for (int i = 0; i < D + 2; i++) q[i * m.ncs + gi] = gq[i];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// calc_VIS (cfd_v0.cpp:1744-1860) as a cell-centric gather: dudx, dTdx of cells [c0, c1)
+// ---------------------------------------------------------------------------------------------------
+template <class R, int D> __global__ void __launch_bounds__(kBlock) k_grad_cell(DevMesh<R> m, const R* __restrict__ q, int c0, int c1) {
+	const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= c1) return;
+	R cq[D + 2], cU[D], c_rho_inv, c_Rpsi, c_T;
+#pragma unroll
+	for (int i = 0; i < D + 2; i++) cq[i] = q[i * m.ncs + c];
+	primitives<R, D>(m.k, cq, c_rho_inv, cU, c_Rpsi, c_T);
+	const R vinv = m.vol_inv[c];
+	R dudx[D][D], dTdx[D];
+#pragma unroll
+	for (int i = 0; i < D; i++) {
+		dTdx[i] = R(0);
+#pragma unroll
+		for (int j = 0; j < D; j++) dudx[i][j] = R(0);
+	}
+	for (int s = 0; s < m.F; s++) {
+		const int e = m.csr[(size_t)s * m.n_cells + c];
+		if (e == 0) break;
+		const bool own = e > 0;
+		const int f = (own ? e : -e) - 1;
+		const int o = own ? m.face_neigh[f] : m.face_owner[f];
+		R oq[D + 2], oU[D], o_rho_inv, o_Rpsi, o_T;
+#pragma unroll
+		for (int i = 0; i < D + 2; i++) oq[i] = q[i * m.ncs + o];
+		primitives<R, D>(m.k, oq, o_rho_inv, oU, o_Rpsi, o_T);
+		const R w = m.w[f];
+		R face_U[D], face_T, sov[D];
+		if (own) {
+			grad_face_values<R, D>(m.k, w, cU, c_Rpsi, oU, o_Rpsi, face_U, face_T);
+#pragma unroll
+			for (int i = 0; i < D; i++) sov[i] = m.S[i * m.nfs + f] * vinv;
+		} else {
+			grad_face_values<R, D>(m.k, w, oU, o_Rpsi, cU, c_Rpsi, face_U, face_T);
+#pragma unroll
+			for (int i = 0; i < D; i++) sov[i] = -m.S[i * m.nfs + f] * vinv;
+		}
+#pragma unroll
+		for (int i = 0; i < D; i++) {
+#pragma unroll
+			for (int j = 0; j < D; j++) dudx[i][j] += face_U[i] * sov[j];
+			dTdx[i] += face_T * sov[i];
+		}
+	}
+#pragma unroll
+	for (int i = 0; i < D; i++) {
+#pragma unroll
+		for (int j = 0; j < D; j++) m.dudx[(size_t)(i * D + j) * m.ncs + c] = dudx[i][j];
+		m.dTdx[(size_t)i * m.ncs + c] = dTdx[i];
+	}
+}
+
+// Loads everything face_flux needs about cell x (real cell, physical ghost or MPI ghost).
+template <class R, int D> __device__ __forceinline__ void load_state(const DevMesh<R>& m, const R* __restrict__ q, int x, CellState<R, D>& s) {
+#pragma unroll
+	for (int i = 0; i < D + 2; i++) s.q[i] = q[i * m.ncs + x];
+	primitives<R, D>(m.k, s.q, s.rho_inv, s.U, s.Rpsi, s.T);
+	const bool bc_ghost = x >= m.n_cells && x < m.n_cells + m.n_bc;
+	if (bc_ghost) {
+#pragma unroll
+		for (int i = 0; i < D; i++) {
+			s.dTdx[i] = s.sigmaU[i] = R(0);
+#pragma unroll
+			for (int j = 0; j < D; j++) s.dudx[i][j] = s.tauMC[i][j] = R(0);
+		}
+		return;
+	}
+#pragma unroll
+	for (int i = 0; i < D; i++) {
+#pragma unroll
+		for (int j = 0; j < D; j++) s.dudx[i][j] = m.dudx[(size_t)(i * D + j) * m.ncs + x];
+		s.dTdx[i] = m.dTdx[(size_t)i * m.ncs + x];
+	}
+	if (x < m.n_cells) {
+		vis_cell_terms<R, D>(m.k, s.q, s.dudx, s.tauMC, s.sigmaU);
+	} else {
+		const int g = x - m.n_cells - m.n_bc;
+#pragma unroll
+		for (int i = 0; i < D; i++) {
+#pragma unroll
+			for (int j = 0; j < D; j++) s.tauMC[i][j] = m.g_tauMC[(size_t)(i * D + j) * m.ngs + g];
+			s.sigmaU[i] = m.g_sigmaU[(size_t)i * m.ngs + g];
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// face-ordered flux kernel: rhs of faces [f0, f1) -> m.flux   (one_rk_step_M1/_M2 face body)
+// ---------------------------------------------------------------------------------------------------
+template <class R, int D, int SCHEME> __global__ void __launch_bounds__(kBlock) k_flux_face(DevMesh<R> m, const R* __restrict__ q, int f0, int f1) {
+	const int f = f0 + blockIdx.x * blockDim.x + threadIdx.x;
+	if (f >= f1) return;
+	const int o = m.face_owner[f], n = m.face_neigh[f];
+	CellState<R, D> c, a;
+	load_state<R, D>(m, q, o, c);
+	load_state<R, D>(m, q, n, a);
+	R S[D], dv[D], rhs[D + 2];
+#pragma unroll
+	for (int i = 0; i < D; i++) {
+		S[i] = m.S[i * m.nfs + f];
+		dv[i] = m.d[i * m.nfs + f];
+	}
+	const bool ghost = n >= m.n_cells && n < m.n_cells + m.n_bc;
+	face_flux<R, D, SCHEME>(m.k, c, a, S, dv, m.w[f], ghost, rhs);
+#pragma unroll
+	for (int i = 0; i < D + 2; i++) m.flux[i * m.nfs + f] = rhs[i];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fused RK-stage cell kernel: dq = A_k dq + sum_faces(+-dt rhs / V) + sponge ; q_new = q + B_k dq
+// (prepare_for_RKstep's dq *= A_k, the scatter of cfd_v0.cpp:2792-2804 as a gather, sponge 2810-2814,
+//  update 2819-2822).  first: dq starts from zero (prepare_for_timestep).  res: also gather RES.
+// ---------------------------------------------------------------------------------------------------
+template <class R, int D> __global__ void __launch_bounds__(kBlock) k_update_cell(DevMesh<R> m, const R* __restrict__ q, R* __restrict__ qn, int c0, int c1, R dt, R Ak, R Bk, int first, int res) {
+	const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= c1) return;
+	constexpr int NQ = D + 2;
+	R dq[NQ], RES[NQ];
+#pragma unroll
+	for (int i = 0; i < NQ; i++) {
+		dq[i] = first ? R(0) : m.dq[(size_t)i * m.n_cells + c] * Ak;
+		RES[i] = R(0);
+	}
+	const R vinv = m.vol_inv[c];
+	for (int s = 0; s < m.F; s++) {
+		const int e = m.csr[(size_t)s * m.n_cells + c];
+		if (e == 0) break;
+		const int f = (e > 0 ? e : -e) - 1;
+		if (e > 0) {
+#pragma unroll
+			for (int i = 0; i < NQ; i++) {
+				const R r = m.flux[i * m.nfs + f];
+				if (res) RES[i] += r;
+				dq[i] += dt * r * vinv;
+			}
+		} else {
+#pragma unroll
+			for (int i = 0; i < NQ; i++) {
+				const R r = m.flux[i * m.nfs + f];
+				if (res) RES[i] -= r;
+				dq[i] -= dt * r * vinv;
+			}
+		}
+	}
+	R cq[NQ];
+#pragma unroll
+	for (int i = 0; i < NQ; i++) cq[i] = q[i * m.ncs + c];
+	const R sg = m.sigma[c];
+	dq[0] += dt * sg * (m.k.rhoInf - cq[0]);
+#pragma unroll
+	for (int i = 0; i < D; i++) dq[i + 1] += dt * sg * (m.k.rhoUInf[i] - cq[i + 1]);
+	dq[D + 1] += dt * sg * (m.k.rhoEInf - cq[D + 1]);
+#pragma unroll
+	for (int i = 0; i < NQ; i++) {
+		m.dq[(size_t)i * m.n_cells + c] = dq[i];
+		qn[i * m.ncs + c] = cq[i] + Bk * dq[i];
+		if (res) m.RES[(size_t)i * m.n_cells + c] = RES[i];
+	}
+}
+
+// copies q of cells [c0,c1) between the two buffers (used when only part of the submeshes is advanced)
+template <class R> __global__ void __launch_bounds__(kBlock) k_copy_q(const R* __restrict__ src, R* __restrict__ dst, size_t ncs, int NQ, int c0, int c1) {
+	const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= c1) return;
+	for (int i = 0; i < NQ; i++) dst[i * ncs + c] = src[i * ncs + c];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// halo pack (cfd_v0.cpp:3303-3331 / 3398-3408 / 3475-3499) and unpack (3608-3692)
+// mode bit 0: q payload, bit 1: viscous payload.  Wire order per cell: q | dudx | dTdx | tauMC | sigmaU
+// ---------------------------------------------------------------------------------------------------
+template <class R, int D> __global__ void __launch_bounds__(kBlock) k_pack(DevMesh<R> m, const R* __restrict__ q, const int* __restrict__ send_cell, int n_send, int mode, R* __restrict__ buf) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_send) return;
+	constexpr int NQ = D + 2, NV = 2 * D * D + 2 * D;
+	const int spc = ((mode & 1) ? NQ : 0) + ((mode & 2) ? NV : 0);
+	const int c = send_cell[i];
+	R* o = buf + (size_t)i * spc;
+	R cq[NQ];
+#pragma unroll
+	for (int k = 0; k < NQ; k++) cq[k] = q[k * m.ncs + c];
+	if (mode & 1) {
+#pragma unroll
+		for (int k = 0; k < NQ; k++) *o++ = cq[k];
+	}
+	if (mode & 2) {
+		R dudx[D][D], dTdx[D], tauMC[D][D], sigmaU[D];
+#pragma unroll
+		for (int a = 0; a < D; a++) {
+#pragma unroll
+			for (int b = 0; b < D; b++) dudx[a][b] = m.dudx[(size_t)(a * D + b) * m.ncs + c];
+			dTdx[a] = m.dTdx[(size_t)a * m.ncs + c];
+		}
+		vis_cell_terms<R, D>(m.k, cq, dudx, tauMC, sigmaU);
+#pragma unroll
+		for (int a = 0; a < D; a++)
+#pragma unroll
+			for (int b = 0; b < D; b++) *o++ = dudx[a][b];
+#pragma unroll
+		for (int a = 0; a < D; a++) *o++ = dTdx[a];
+#pragma unroll
+		for (int a = 0; a < D; a++)
+#pragma unroll
+			for (int b = 0; b < D; b++) *o++ = tauMC[a][b];
+#pragma unroll
+		for (int a = 0; a < D; a++) *o++ = sigmaU[a];
+	}
+}
+
+template <class R, int D> __global__ void __launch_bounds__(kBlock) k_unpack(DevMesh<R> m, R* __restrict__ q, int n_recv, int mode, const R* __restrict__ buf) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_recv) return;
+	constexpr int NQ = D + 2, NV = 2 * D * D + 2 * D;
+	const int spc = ((mode & 1) ? NQ : 0) + ((mode & 2) ? NV : 0);
+	const size_t g = (size_t)m.n_cells + m.n_bc + i;
+	const R* o = buf + (size_t)i * spc;
+	if (mode & 1) {
+#pragma unroll
+		for (int k = 0; k < NQ; k++) q[k * m.ncs + g] = *o++;
+	}
+	if (mode & 2) {
+#pragma unroll
+		for (int a = 0; a < D * D; a++) m.dudx[(size_t)a * m.ncs + g] = *o++;
+#pragma unroll
+		for (int a = 0; a < D; a++) m.dTdx[(size_t)a * m.ncs + g] = *o++;
+#pragma unroll
+		for (int a = 0; a < D * D; a++) m.g_tauMC[(size_t)a * m.ngs + i] = *o++;
+#pragma unroll
+		for (int a = 0; a < D; a++) m.g_sigmaU[(size_t)a * m.ngs + i] = *o++;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// compute_cfl (cfd_v0.cpp:2887-2909) / compute_dt (2913-2942): block max / min -> partial[blockIdx]
+// what = 0: cfl (max), 1: dt (min)
+// ---------------------------------------------------------------------------------------------------
+template <class R, int D> __global__ void __launch_bounds__(kBlock) k_cfl_dt(DevMesh<R> m, const R* __restrict__ q, R arg, int what, R* __restrict__ partial) {
+	__shared__ R sh[kBlock];
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	R v = what == 0 ? R(0) : R(100.0);
+	if (c < m.n_cells) {
+		R cq[D + 1];
+#pragma unroll
+		for (int i = 0; i < D + 1; i++) cq[i] = q[i * m.ncs + c];
+		R acc = R(0);
+		for (int s = 0; s < m.F; s++) {
+			const int e = m.slot[(size_t)s * m.n_cells + c];
+			if (e == 0) continue;
+			const int f = (e > 0 ? e : -e) - 1;
+			R S[D];
+#pragma unroll
+			for (int i = 0; i < D; i++) S[i] = e > 0 ? m.S[i * m.nfs + f] : -m.S[i * m.nfs + f];
+			R flux = R(0);
+			if (what == 0) {
+#pragma unroll
+				for (int i = 0; i < D; i++) flux += cq[i + 1] * S[i];
+			} else {
+				R sMag = R(0);
+#pragma unroll
+				for (int i = 0; i < D; i++) sMag += S[i] * S[i];
+				sMag = LFM_SQRT(sMag);
+#pragma unroll
+				for (int i = 0; i < D; i++) flux += cq[i + 1] * S[i] / sMag;
+			}
+			acc += flux < R(0) ? -flux : flux;
+		}
+		if (what == 0) {
+			const R rho_inv = R(1.0) / cq[0];
+			v = acc;
+			v *= rho_inv * m.vol_inv[c] * arg;
+		} else {
+			const R vol = R(1.0) / m.vol_inv[c];
+			v = arg * cq[0] * R(2.0) * vol / acc;
+		}
+	}
+	sh[threadIdx.x] = v;
+	__syncthreads();
+	for (int s = kBlock / 2; s > 0; s >>= 1) {
+		if (threadIdx.x < s) {
+			const R o = sh[threadIdx.x + s];
+			if (what == 0 ? (sh[threadIdx.x] < o) : (o < sh[threadIdx.x])) sh[threadIdx.x] = o;
+		}
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+template <class R> __global__ void k_reduce_minmax(const R* __restrict__ partial, int n, int what, R* __restrict__ out) {
+	__shared__ R sh[kBlock];
+	R v = what == 0 ? R(0) : R(100.0);
+	for (int i = threadIdx.x; i < n; i += kBlock) {
+		const R o = partial[i];
+		if (what == 0 ? (v < o) : (o < v)) v = o;
+	}
+	sh[threadIdx.x] = v;
+	__syncthreads();
+	for (int s = kBlock / 2; s > 0; s >>= 1) {
+		if (threadIdx.x < s) {
+			const R o = sh[threadIdx.x + s];
+			if (what == 0 ? (sh[threadIdx.x] < o) : (o < sh[threadIdx.x])) sh[threadIdx.x] = o;
+		}
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) out[0] = sh[0];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// postProcAverage (cfd_v0.cpp:3083-3103)
+// ---------------------------------------------------------------------------------------------------
+template <class R, int D> __global__ void __launch_bounds__(kBlock) k_average(DevMesh<R> m, const R* __restrict__ q, int time_step) {
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= m.n_cells) return;
+	const R r = q[c];
+	R velMag = R(0);
+#pragma unroll
+	for (int nD = 1; nD <= D; nD++) {
+		const R vel = q[nD * m.ncs + c] / r;
+		velMag += vel * vel;
+	}
+	const R E = q[(D + 1) * m.ncs + c] / r;
+	const R p = (r * m.k.gm1) * (E - R(0.5) * velMag);
+	const R avg = m.pAVG[c] + p;
+	m.pAVG[c] = avg;
+	const R dev = p - avg / R(time_step);
+	m.pRMS[c] += dev * dev;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stage-0 residual norm (cfd_v0.cpp:2825-2831): sum over cells [c0,c1) of RES^2, fixed-shape tree
+// ---------------------------------------------------------------------------------------------------
+template <class R> __global__ void __launch_bounds__(kBlock) k_res_partial(const R* __restrict__ RES, int n_cells, int NQ, int c0, int c1, double* __restrict__ partial) {
+	__shared__ double sh[kBlock];
+	for (int i = 0; i < NQ; i++) {
+		const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+		double v = 0.0;
+		if (c < c1) {
+			const R r = RES[(size_t)i * n_cells + c];
+			v = (double)(r * r);
+		}
+		sh[threadIdx.x] = v;
+		__syncthreads();
+		for (int s = kBlock / 2; s > 0; s >>= 1) {
+			if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+			__syncthreads();
+		}
+		if (threadIdx.x == 0) partial[(size_t)i * gridDim.x + blockIdx.x] = sh[0];
+		__syncthreads();
+	}
+}
+// out[i] += sum(partial[i][:]) with a fixed-shape tree (one block per component)
+__global__ void __launch_bounds__(kBlock) k_res_final(const double* __restrict__ partial, int n, double* __restrict__ out) {
+	__shared__ double sh[kBlock];
+	double v = 0.0;
+	for (int i = threadIdx.x; i < n; i += kBlock) v += partial[(size_t)blockIdx.x * n + i];
+	sh[threadIdx.x] = v;
+	__syncthreads();
+	for (int s = kBlock / 2; s > 0; s >>= 1) {
+		if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) out[blockIdx.x] += sh[0];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// postProcForces (cfd_v0.cpp:3173-3240): per wall face contributions, then a sequential sum in the
+// reference's face order (bit-exact with the CPU loop)
+// ---------------------------------------------------------------------------------------------------
+template <class R, int D> __global__ void __launch_bounds__(kBlock) k_forces_face(DevMesh<R> m, const R* __restrict__ q, int patch, R* __restrict__ contrib /*[n_bc][2*D]*/, int* __restrict__ used) {
+	const int g = blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= m.n_bc) return;
+	if (m.bc_patch[g] != patch) {
+		used[g] = 0;
+		return;
+	}
+	used[g] = 1;
+	const int t = m.bc_cell[g], f = m.bc_face[g];
+	const size_t n = (size_t)m.n_cells + g;
+	R S[D], dv[D], cq[D + 2], nq[D + 2];
+#pragma unroll
+	for (int i = 0; i < D; i++) {
+		S[i] = m.S[i * m.nfs + f];
+		dv[i] = m.d[i * m.nfs + f];
+	}
+#pragma unroll
+	for (int i = 0; i < D + 2; i++) {
+		cq[i] = q[i * m.ncs + t];
+		nq[i] = q[i * m.ncs + n];
+	}
+	const R r = cq[0], rE = cq[D + 1];
+	R Umag = R(0);
+#pragma unroll
+	for (int i = 0; i < D; i++) {
+		const R u = cq[i + 1] / r;
+		Umag += u * u;
+	}
+	Umag = LFM_SQRT(Umag);
+	const R E = rE / r;
+	const R p = (r * m.k.gm1) * (E - R(0.5) * Umag * Umag);
+	R* o = contrib + (size_t)g * 2 * D;
+#pragma unroll
+	for (int nD = 0; nD < D; nD++) o[nD] = S[nD] * (p - m.k.pInf);
+	R d_mag = dv[0] * dv[0];
+#pragma unroll
+	for (int i = 1; i < D; i++) d_mag += dv[i] * dv[i];
+	d_mag = LFM_SQRT(d_mag);
+	const R dmag_inv = R(1.0) / d_mag;
+	R d_norm[D], dudx[D][D], tau[D][D];
+#pragma unroll
+	for (int i = 0; i < D; i++) d_norm[i] = dv[i] * dmag_inv;
+#pragma unroll
+	for (int i = 0; i < D; i++) {
+		const R cell_U = cq[i + 1] / cq[0];
+		const R adjc_U = nq[i + 1] / nq[0];
+#pragma unroll
+		for (int j = 0; j < D; j++) dudx[i][j] = (adjc_U - cell_U) * d_norm[j] * dmag_inv;
+	}
+	stress<R, D>(m.k, dudx, tau);
+	// Fvis[a] -= tau[a][b]*S[b] for b ascending: keep the products separate so the serial sum can replay the order
+#pragma unroll
+	for (int a = 0; a < D; a++) {
+		// the reference subtracts term by term from the running total; store the D products per row
+		o[D + a] = R(0);
+	}
+	R* prod = contrib + (size_t)m.n_bc * 2 * D + (size_t)g * D * D;
+#pragma unroll
+	for (int a = 0; a < D; a++)
+#pragma unroll
+		for (int b = 0; b < D; b++) prod[a * D + b] = tau[a][b] * S[b];
+}
+
+template <class R, int D> __global__ void k_forces_sum(int n_bc, const R* __restrict__ contrib, const int* __restrict__ used, R* __restrict__ out /*[2*D]*/) {
+	const int a = threadIdx.x;
+	if (a >= D) return;
+	R fp = R(0), fv = R(0);
+	const R* prod = contrib + (size_t)n_bc * 2 * D;
+	for (int g = 0; g < n_bc; g++) {
+		if (!used[g]) continue;
+		fp += contrib[(size_t)g * 2 * D + a];
+		for (int b = 0; b < D; b++) fv -= prod[(size_t)g * D * D + a * D + b];
+	}
+	out[a] = fp;
+	out[D + a] = fv;
+}
+
+}  // namespace lfm

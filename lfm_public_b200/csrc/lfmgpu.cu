@@ -1,0 +1,1057 @@
+// liblfmgpu.so -- the C ABI of include/lfmgpu.h over the sm_100a kernels.
+//
+// Host-side bookkeeping only: uploads the flattened rank (lfmgpu_desc) into SoA device arrays, orders
+// the kernels on a compute stream and a high-priority halo stream exactly as Mesh::solve orders the
+// ISolver virtuals (reference: src/mesh_solver.cpp:474-691), and moves halo buffers either between
+// handles of the same process or over NCCL (dlopen'ed, so the library loads on a box without NCCL).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "lfmgpu.h"
+#include "tile_kernels.cuh"
+
+using namespace lfm;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(const char* fmt, ...) {
+	char buf[1024];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof buf, fmt, ap);
+	va_end(ap);
+	g_err = buf;
+	return 1;
+}
+#define CU(call) \
+	do { \
+		cudaError_t e_ = (call); \
+		if (e_ != cudaSuccess) return fail("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+	} while (0)
+#define TRY(call) \
+	do { \
+		int r_ = (call); \
+		if (r_) return r_; \
+	} while (0)
+
+// ---- NCCL through dlopen ---------------------------------------------------------------------------
+struct NcclApi {
+	void* lib = nullptr;
+	ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+	ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*GroupStart)() = nullptr;
+	ncclResult_t (*GroupEnd)() = nullptr;
+	const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+int load_nccl() {
+	if (g_nccl.lib) return 0;
+	const char* names[] = {"libnccl.so.2", "libnccl.so"};
+	void* lib = nullptr;
+	for (const char* n : names) {
+		lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+		if (lib) break;
+	}
+	if (!lib) return fail("cannot dlopen libnccl.so.2: %s", dlerror());
+#define SYM(field, name) \
+	*(void**)(&g_nccl.field) = dlsym(lib, name); \
+	if (!g_nccl.field) return fail("libnccl lacks %s", name);
+	SYM(GetUniqueId, "ncclGetUniqueId")
+	SYM(CommInitRank, "ncclCommInitRank")
+	SYM(CommDestroy, "ncclCommDestroy")
+	SYM(Send, "ncclSend")
+	SYM(Recv, "ncclRecv")
+	SYM(AllReduce, "ncclAllReduce")
+	SYM(GroupStart, "ncclGroupStart")
+	SYM(GroupEnd, "ncclGroupEnd")
+	SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+	g_nccl.lib = lib;
+	return 0;
+}
+#define NC(call) \
+	do { \
+		ncclResult_t r_ = (call); \
+		if (r_ != ncclSuccess) return fail("%s:%d %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r_)); \
+	} while (0)
+
+struct TimedLaunch {
+	const char* name;
+	cudaEvent_t a, b;
+};
+
+}  // namespace
+
+struct lfmgpu_ctx {
+	int device = 0, prec = 8, D = 3, NQ = 5, F = 0;
+	int n_cells = 0, n_faces = 0, n_bc = 0, n_mpi = 0, n_tot = 0, n_sub = 1;
+	size_t ncs = 0, nfs = 0, ngs = 0;
+	int sub_cell_start[LFMGPU_MAX_SUBMESH + 1] = {0};
+	int sub_face_start[LFMGPU_MAX_SUBMESH + 1] = {0};
+	lfmgpu_consts c{};
+	std::vector<void*> allocs;
+	DevMesh<double> md{};
+	DevMesh<float> mf{};
+	void* q[2] = {nullptr, nullptr};
+	int cur = 0;
+	unsigned updated_mask = 0;         // submeshes already advanced in the running stage
+	bool dq_zero = true;               // prepare_for_timestep seen, no stage yet
+	int rk_pending = 0;
+	bool stage_done = false;           // at least one stage completed (q[1-cur] holds the pre-stage state)
+	double* d_res = nullptr;           // [NQ] sum of RES^2
+	double* d_res_partial = nullptr;
+	void* d_partial = nullptr;         // block partials for cfl/dt
+	void* d_scalar = nullptr;
+	void* d_force_contrib = nullptr;
+	int* d_force_used = nullptr;
+	void* d_force_out = nullptr;
+	cudaStream_t s_main = nullptr, s_comm = nullptr;
+	cudaEvent_t ev_ready = nullptr;
+	cudaEvent_t ev_packed[2] = {nullptr, nullptr}, ev_arrived[2] = {nullptr, nullptr};
+	bool pending[2] = {false, false};
+	// halo
+	int n_nbr = 0, rank = 0, n_ranks = 1;
+	std::vector<int> nbr_rank, send_start, recv_start;
+	int* d_send_cell = nullptr;
+	void* send_buf[2] = {nullptr, nullptr};
+	void* recv_buf[2] = {nullptr, nullptr};
+	size_t last_send_count[2] = {0, 0};
+	int transport = 0;                 // 0 none, 1 local, 2 nccl
+	std::vector<lfmgpu_ctx*> peers;
+	ncclComm_t comm = nullptr;
+	// tiles (fused path)
+	TilePlan tiles;
+	int use_tiles = 1;
+	// introspection
+	uint64_t launches = 0;
+	bool timing = false;
+	std::vector<TimedLaunch> timed;
+
+	template <class R> DevMesh<R>& mesh();
+};
+template <> DevMesh<double>& lfmgpu_ctx::mesh<double>() { return md; }
+template <> DevMesh<float>& lfmgpu_ctx::mesh<float>() { return mf; }
+
+namespace {
+
+int tile_plan_build(lfmgpu_ctx* h, const lfmgpu_desc* ds);
+template <class R, int D> int tile_grad(lfmgpu_ctx* h, int sub);
+template <class R, int D> int tile_stage(lfmgpu_ctx* h, int sub, int scheme, R dt, R Ak, R Bk, int first, int res);
+
+struct LaunchScope {
+	lfmgpu_ctx* h;
+	cudaStream_t s;
+	TimedLaunch t{};
+	LaunchScope(lfmgpu_ctx* h_, const char* name, cudaStream_t s_) : h(h_), s(s_) {
+		h->launches++;
+		if (h->timing) {
+			t.name = name;
+			cudaEventCreate(&t.a);
+			cudaEventCreate(&t.b);
+			cudaEventRecord(t.a, s);
+		}
+	}
+	~LaunchScope() {
+		if (h->timing) {
+			cudaEventRecord(t.b, s);
+			h->timed.push_back(t);
+		}
+	}
+};
+#define LAUNCH(h, name, stream, ...) \
+	do { \
+		LaunchScope ls_(h, name, stream); \
+		__VA_ARGS__; \
+	} while (0)
+#define CHECK_LAUNCH() CU(cudaGetLastError())
+
+inline int blocks_for(int n) { return (n + kBlock - 1) / kBlock; }
+
+int dev_alloc(lfmgpu_ctx* h, void** p, size_t bytes, bool zero = true) {
+	if (bytes == 0) bytes = 16;
+	CU(cudaMalloc(p, bytes));
+	h->allocs.push_back(*p);
+	if (zero) CU(cudaMemset(*p, 0, bytes));
+	return 0;
+}
+
+template <class T> int upload(lfmgpu_ctx* h, T** dst, const T* src, size_t n) {
+	TRY(dev_alloc(h, (void**)dst, n * sizeof(T), n == 0));
+	if (n) CU(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+	return 0;
+}
+
+// AoS [n][k] host -> SoA [k][stride] device
+template <class R> int upload_soa(lfmgpu_ctx* h, R** dst, const R* src, size_t n, int k, size_t stride) {
+	std::vector<R> tmp((size_t)k * stride, R(0));
+	for (size_t i = 0; i < n; i++)
+		for (int j = 0; j < k; j++) tmp[(size_t)j * stride + i] = src[i * k + j];
+	return upload<R>(h, dst, tmp.data(), tmp.size());
+}
+
+inline size_t pad32(size_t n) { return (n + 31) / 32 * 32; }
+
+template <class R> int build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
+	const int D = h->D, NQ = h->NQ, F = h->F;
+	DevMesh<R>& m = h->mesh<R>();
+	m.n_cells = h->n_cells;
+	m.n_faces = h->n_faces;
+	m.n_bc = h->n_bc;
+	m.n_mpi = h->n_mpi;
+	m.n_tot = h->n_tot;
+	m.F = F;
+	m.ncs = h->ncs;
+	m.nfs = h->nfs;
+	m.ngs = h->ngs;
+	int* p = nullptr;
+	TRY(upload<int>(h, &p, ds->face_owner, (size_t)h->n_faces));
+	m.face_owner = p;
+	TRY(upload<int>(h, &p, ds->face_neigh, (size_t)h->n_faces));
+	m.face_neigh = p;
+	R* r = nullptr;
+	TRY(upload_soa<R>(h, &r, (const R*)ds->face_S, (size_t)h->n_faces, D, h->nfs));
+	m.S = r;
+	TRY(upload_soa<R>(h, &r, (const R*)ds->face_d, (size_t)h->n_faces, D, h->nfs));
+	m.d = r;
+	TRY(upload<R>(h, &r, (const R*)ds->face_w, (size_t)h->n_faces));
+	m.w = r;
+	TRY(upload<R>(h, &r, (const R*)ds->vol_inv, (size_t)h->n_cells));
+	m.vol_inv = r;
+	TRY(upload<R>(h, &r, (const R*)ds->sponge_sigma, (size_t)h->n_cells));
+	m.sigma = r;
+	// cell -> faces: reference slot order and ascending-face order, both transposed to [F][n_cells]
+	{
+		std::vector<int> slot((size_t)F * h->n_cells, 0), csr((size_t)F * h->n_cells, 0);
+		std::vector<int> tmp((size_t)F);
+		for (int c = 0; c < h->n_cells; c++) {
+			int n = 0;
+			for (int s = 0; s < F; s++) {
+				const int e = ds->cell_slot_face[(size_t)c * F + s];
+				slot[(size_t)s * h->n_cells + c] = e;
+				if (e) tmp[(size_t)n++] = e;
+			}
+			std::sort(tmp.begin(), tmp.begin() + n, [](int a, int b) { return std::abs(a) < std::abs(b); });
+			for (int s = 0; s < n; s++) csr[(size_t)s * h->n_cells + c] = tmp[(size_t)s];
+		}
+		TRY(upload<int>(h, &p, slot.data(), slot.size()));
+		m.slot = p;
+		TRY(upload<int>(h, &p, csr.data(), csr.size()));
+		m.csr = p;
+	}
+	for (int b = 0; b < 2; b++) TRY(dev_alloc(h, &h->q[b], (size_t)NQ * h->ncs * sizeof(R)));
+	{
+		std::vector<R> tmp((size_t)NQ * h->ncs, R(0));
+		const R* q0 = (const R*)ds->q0;
+		for (int c = 0; c < h->n_cells; c++)
+			for (int i = 0; i < NQ; i++) tmp[(size_t)i * h->ncs + c] = q0[(size_t)c * NQ + i];
+		CU(cudaMemcpy(h->q[0], tmp.data(), tmp.size() * sizeof(R), cudaMemcpyHostToDevice));
+		CU(cudaMemcpy(h->q[1], tmp.data(), tmp.size() * sizeof(R), cudaMemcpyHostToDevice));
+	}
+	TRY(dev_alloc(h, (void**)&m.dq, (size_t)NQ * h->n_cells * sizeof(R)));
+	TRY(dev_alloc(h, (void**)&m.RES, (size_t)NQ * h->n_cells * sizeof(R)));
+	TRY(dev_alloc(h, (void**)&m.dudx, (size_t)D * D * h->ncs * sizeof(R)));
+	TRY(dev_alloc(h, (void**)&m.dTdx, (size_t)D * h->ncs * sizeof(R)));
+	TRY(dev_alloc(h, (void**)&m.g_tauMC, (size_t)D * D * h->ngs * sizeof(R)));
+	TRY(dev_alloc(h, (void**)&m.g_sigmaU, (size_t)D * h->ngs * sizeof(R)));
+	m.flux = nullptr;   // allocated on first use of the materialised path
+	TRY(dev_alloc(h, (void**)&m.pAVG, (size_t)h->n_cells * sizeof(R)));
+	TRY(dev_alloc(h, (void**)&m.pRMS, (size_t)h->n_cells * sizeof(R)));
+	TRY(upload<int>(h, &p, ds->bc_cell, (size_t)h->n_bc));
+	m.bc_cell = p;
+	TRY(upload<int>(h, &p, ds->bc_kind, (size_t)h->n_bc));
+	m.bc_kind = p;
+	TRY(upload<int>(h, &p, ds->bc_face, (size_t)h->n_bc));
+	m.bc_face = p;
+	TRY(upload<int>(h, &p, ds->bc_patch, (size_t)h->n_bc));
+	m.bc_patch = p;
+	// constants, narrowed exactly as the CPU restatement narrows them
+	const lfmgpu_consts& c = ds->c;
+	Consts<R>& k = m.k;
+	k.gamma = (R)c.gamma;
+	k.gm1 = (R)c.gamma_m1;
+	k.Rgas_inv = (R)c.Rgas_inv;
+	k.mu = (R)c.mu;
+	k.Cp = (R)c.Cp;
+	k.Pr_inv = (R)c.Pr_inv;
+	{
+		volatile R t = k.Cp * k.mu;
+		k.kappa = t * k.Pr_inv;
+	}
+	k.c_tau = (R)(2.0 / 3.0 * (double)k.mu);
+	k.c_diag = (R)((double)k.mu * 2.0 / 3.0);
+	k.rhoInf = (R)c.rhoInf;
+	for (int i = 0; i < 3; i++) k.UInf[i] = (R)c.UInf[i];
+	k.EInf = (R)c.EInf;
+	k.pInf = (R)c.pInf;
+	k.TInf = (R)c.TInf;
+	for (int i = 0; i < 3; i++) {
+		volatile R t = k.rhoInf * k.UInf[i];
+		k.rhoUInf[i] = t;
+	}
+	{
+		volatile R t = k.rhoInf * k.EInf;
+		k.rhoEInf = t;
+	}
+	// scratch
+	TRY(dev_alloc(h, &h->d_partial, (size_t)(blocks_for(h->n_cells) + 1) * sizeof(R)));
+	TRY(dev_alloc(h, &h->d_scalar, 64));
+	TRY(dev_alloc(h, (void**)&h->d_res, 8 * sizeof(double)));
+	TRY(dev_alloc(h, (void**)&h->d_res_partial, (size_t)NQ * (blocks_for(h->n_cells) + 1) * sizeof(double)));
+	TRY(dev_alloc(h, &h->d_force_contrib, (size_t)h->n_bc * (2 * D + D * D) * sizeof(R)));
+	TRY(dev_alloc(h, (void**)&h->d_force_used, (size_t)h->n_bc * sizeof(int)));
+	TRY(dev_alloc(h, &h->d_force_out, 16 * sizeof(R)));
+	// halo
+	if (h->n_nbr) {
+		const size_t ns = (size_t)h->send_start[(size_t)h->n_nbr], nr = (size_t)h->recv_start[(size_t)h->n_nbr];
+		TRY(upload<int>(h, &h->d_send_cell, ds->send_cell, ns));
+		const size_t per = (size_t)(NQ + 2 * D * D + 2 * D) * sizeof(R);
+		for (int s = 0; s < 2; s++) {
+			TRY(dev_alloc(h, &h->send_buf[s], ns * per));
+			TRY(dev_alloc(h, &h->recv_buf[s], nr * per));
+		}
+	}
+	return 0;
+}
+
+int halo_mode(const lfmgpu_ctx* h, int step) { return h->c.comm_type == LFMGPU_COMM_SPLIT ? (step == 0 ? 1 : 2) : 3; }
+int halo_spc(const lfmgpu_ctx* h, int step) {
+	const int mode = halo_mode(h, step), D = h->D;
+	return ((mode & 1) ? D + 2 : 0) + ((mode & 2) ? 2 * D * D + 2 * D : 0);
+}
+
+// buffer that holds the latest conservatives of cell range of submesh 0 (for packing)
+void* q_for_pack(lfmgpu_ctx* h) { return (h->updated_mask & 1u) ? h->q[1 - h->cur] : h->q[h->cur]; }
+
+template <class R, int D> int t_set_bc(lfmgpu_ctx* h) {
+	if (!h->n_bc) return 0;
+	LAUNCH(h, "k_set_bc", h->s_main, (k_set_bc<R, D><<<blocks_for(h->n_bc), kBlock, 0, h->s_main>>>(h->mesh<R>(), (R*)h->q[h->cur])));
+	CHECK_LAUNCH();
+	return 0;
+}
+
+void sub_range(const lfmgpu_ctx* h, int sub, int& c0, int& c1, int& f0, int& f1) {
+	if (sub < 0) {
+		c0 = 0;
+		c1 = h->n_cells;
+		f0 = 0;
+		f1 = h->n_faces;
+	} else {
+		c0 = h->sub_cell_start[sub];
+		c1 = h->sub_cell_start[sub + 1];
+		f0 = h->sub_face_start[sub];
+		f1 = h->sub_face_start[sub + 1];
+	}
+}
+
+template <class R, int D> int t_vis(lfmgpu_ctx* h, int sub) {
+	int c0, c1, f0, f1;
+	sub_range(h, sub, c0, c1, f0, f1);
+	if (c1 <= c0) return 0;
+	if (h->use_tiles && h->tiles.ready) return tile_grad<R, D>(h, sub);
+	LAUNCH(h, "k_grad_cell", h->s_main, (k_grad_cell<R, D><<<blocks_for(c1 - c0), kBlock, 0, h->s_main>>>(h->mesh<R>(), (const R*)h->q[h->cur], c0, c1)));
+	CHECK_LAUNCH();
+	return 0;
+}
+
+template <class R, int D> int t_rk_stage(lfmgpu_ctx* h, int sub, int scheme, int rk, double dt, int want_res) {
+	int c0, c1, f0, f1;
+	sub_range(h, sub, c0, c1, f0, f1);
+	DevMesh<R>& m = h->mesh<R>();
+	const R* q = (const R*)h->q[h->cur];
+	R* qn = (R*)h->q[1 - h->cur];
+	const int res = (want_res && rk == 0) ? 1 : 0;
+	const int first = h->dq_zero ? 1 : 0;
+	const R Ak = (R)h->c.Ak[rk], Bk = (R)h->c.Bk[rk];
+	if (c1 > c0) {
+		if (h->use_tiles && h->tiles.ready) {
+			TRY((tile_stage<R, D>(h, sub, scheme, (R)dt, Ak, Bk, first, res)));
+		} else {
+			if (!m.flux) TRY(dev_alloc(h, (void**)&m.flux, (size_t)h->NQ * h->nfs * sizeof(R)));
+			if (f1 > f0) {
+				if (scheme == LFMGPU_SCHEME_M1)
+					LAUNCH(h, "k_flux_face", h->s_main, (k_flux_face<R, D, 0><<<blocks_for(f1 - f0), kBlock, 0, h->s_main>>>(m, q, f0, f1)));
+				else
+					LAUNCH(h, "k_flux_face", h->s_main, (k_flux_face<R, D, 1><<<blocks_for(f1 - f0), kBlock, 0, h->s_main>>>(m, q, f0, f1)));
+				CHECK_LAUNCH();
+			}
+			LAUNCH(h, "k_update_cell", h->s_main, (k_update_cell<R, D><<<blocks_for(c1 - c0), kBlock, 0, h->s_main>>>(m, q, qn, c0, c1, (R)dt, Ak, Bk, first, res)));
+			CHECK_LAUNCH();
+		}
+		if (res) {
+			const int nb = blocks_for(c1 - c0);
+			LAUNCH(h, "k_res_partial", h->s_main, (k_res_partial<R><<<nb, kBlock, 0, h->s_main>>>(m.RES, h->n_cells, h->NQ, c0, c1, h->d_res_partial)));
+			LAUNCH(h, "k_res_final", h->s_main, (k_res_final<<<h->NQ, kBlock, 0, h->s_main>>>(h->d_res_partial, nb, h->d_res)));
+			CHECK_LAUNCH();
+		}
+	}
+	// bookkeeping: flip the conservatives once every submesh has been advanced
+	const unsigned all = (1u << h->n_sub) - 1u;
+	h->updated_mask |= (sub < 0) ? all : (1u << sub);
+	if (h->updated_mask == all) {
+		h->cur = 1 - h->cur;
+		h->updated_mask = 0;
+		h->dq_zero = false;
+		h->stage_done = true;
+	}
+	return 0;
+}
+
+template <class R, int D> int t_pack(lfmgpu_ctx* h, int step, cudaStream_t s) {
+	const int ns = h->send_start[(size_t)h->n_nbr];
+	const int mode = halo_mode(h, step);
+	h->last_send_count[step] = (size_t)ns * halo_spc(h, step);
+	if (!ns) return 0;
+	LAUNCH(h, "k_pack", s, (k_pack<R, D><<<blocks_for(ns), kBlock, 0, s>>>(h->mesh<R>(), (const R*)q_for_pack(h), h->d_send_cell, ns, mode, (R*)h->send_buf[step])));
+	CHECK_LAUNCH();
+	return 0;
+}
+
+template <class R, int D> int t_unpack(lfmgpu_ctx* h, int step) {
+	const int nr = h->recv_start[(size_t)h->n_nbr];
+	if (!nr) return 0;
+	LAUNCH(h, "k_unpack", h->s_main, (k_unpack<R, D><<<blocks_for(nr), kBlock, 0, h->s_main>>>(h->mesh<R>(), (R*)h->q[h->cur], nr, halo_mode(h, step), (const R*)h->recv_buf[step])));
+	CHECK_LAUNCH();
+	return 0;
+}
+
+template <class R, int D> int t_cfl_dt(lfmgpu_ctx* h, double arg, int what, double* out) {
+	const int nb = blocks_for(h->n_cells);
+	LAUNCH(h, "k_cfl_dt", h->s_main, (k_cfl_dt<R, D><<<nb, kBlock, 0, h->s_main>>>(h->mesh<R>(), (const R*)h->q[h->cur], (R)arg, what, (R*)h->d_partial)));
+	LAUNCH(h, "k_reduce_minmax", h->s_main, (k_reduce_minmax<R><<<1, kBlock, 0, h->s_main>>>((const R*)h->d_partial, nb, what, (R*)h->d_scalar)));
+	CHECK_LAUNCH();
+	R v;
+	CU(cudaMemcpyAsync(&v, h->d_scalar, sizeof(R), cudaMemcpyDeviceToHost, h->s_main));
+	CU(cudaStreamSynchronize(h->s_main));
+	*out = (double)v;
+	return 0;
+}
+
+template <class R, int D> int t_average(lfmgpu_ctx* h, int time_step) {
+	if (time_step <= 0) return 0;
+	LAUNCH(h, "k_average", h->s_main, (k_average<R, D><<<blocks_for(h->n_cells), kBlock, 0, h->s_main>>>(h->mesh<R>(), (const R*)h->q[h->cur], time_step)));
+	CHECK_LAUNCH();
+	return 0;
+}
+
+template <class R, int D> int t_forces(lfmgpu_ctx* h, int patch, double* Fpre, double* Fvis) {
+	for (int i = 0; i < D; i++) Fpre[i] = Fvis[i] = 0.0;
+	if (!h->n_bc) return 0;
+	LAUNCH(h, "k_forces_face", h->s_main, (k_forces_face<R, D><<<blocks_for(h->n_bc), kBlock, 0, h->s_main>>>(h->mesh<R>(), (const R*)h->q[h->cur], patch, (R*)h->d_force_contrib, h->d_force_used)));
+	LAUNCH(h, "k_forces_sum", h->s_main, (k_forces_sum<R, D><<<1, 32, 0, h->s_main>>>(h->n_bc, (const R*)h->d_force_contrib, h->d_force_used, (R*)h->d_force_out)));
+	CHECK_LAUNCH();
+	R out[6];
+	CU(cudaMemcpyAsync(out, h->d_force_out, 2 * D * sizeof(R), cudaMemcpyDeviceToHost, h->s_main));
+	CU(cudaStreamSynchronize(h->s_main));
+	for (int i = 0; i < D; i++) {
+		Fpre[i] = (double)out[i];
+		Fvis[i] = (double)out[D + i];
+	}
+	return 0;
+}
+
+int tile_plan_build(lfmgpu_ctx*, const lfmgpu_desc*) { return 0; }
+template <class R, int D> int tile_grad(lfmgpu_ctx*, int) { return fail("tiled path not built"); }
+template <class R, int D> int tile_stage(lfmgpu_ctx*, int, int, R, R, R, int, int) { return fail("tiled path not built"); }
+
+#define DISPATCH(h, fn, ...) \
+	((h)->prec == 8 ? ((h)->D == 3 ? fn<double, 3>(__VA_ARGS__) : fn<double, 2>(__VA_ARGS__)) \
+	                : ((h)->D == 3 ? fn<float, 3>(__VA_ARGS__) : fn<float, 2>(__VA_ARGS__)))
+
+int halo_start_impl(lfmgpu_ctx* h, int step) {
+	if (h->n_nbr == 0 || h->transport == 0) return 0;
+	// the pack reads what the compute stream has produced up to here
+	CU(cudaEventRecord(h->ev_ready, h->s_main));
+	CU(cudaStreamWaitEvent(h->s_comm, h->ev_ready, 0));
+	if (h->transport == 1) {
+		// consumers of my previous send buffer must have copied it
+		for (int i = 0; i < h->n_nbr; i++) {
+			lfmgpu_ctx* p = h->peers[(size_t)h->nbr_rank[(size_t)i]];
+			CU(cudaStreamWaitEvent(h->s_comm, p->ev_arrived[step], 0));
+		}
+	}
+	TRY(DISPATCH(h, t_pack, h, step, h->s_comm));
+	CU(cudaEventRecord(h->ev_packed[step], h->s_comm));
+	if (h->transport == 2) {
+		const int spc = halo_spc(h, step);
+		const ncclDataType_t ty = h->prec == 8 ? ncclDouble : ncclFloat;
+		NC(g_nccl.GroupStart());
+		for (int i = 0; i < h->n_nbr; i++) {
+			const size_t so = (size_t)h->send_start[(size_t)i] * spc, sn = (size_t)(h->send_start[(size_t)i + 1] - h->send_start[(size_t)i]) * spc;
+			const size_t ro = (size_t)h->recv_start[(size_t)i] * spc, rn = (size_t)(h->recv_start[(size_t)i + 1] - h->recv_start[(size_t)i]) * spc;
+			NC(g_nccl.Send((const char*)h->send_buf[step] + so * h->prec, sn, ty, h->nbr_rank[(size_t)i], h->comm, h->s_comm));
+			NC(g_nccl.Recv((char*)h->recv_buf[step] + ro * h->prec, rn, ty, h->nbr_rank[(size_t)i], h->comm, h->s_comm));
+		}
+		NC(g_nccl.GroupEnd());
+		h->launches++;
+		CU(cudaEventRecord(h->ev_arrived[step], h->s_comm));
+	}
+	h->pending[step] = true;
+	return 0;
+}
+
+int halo_wait_impl(lfmgpu_ctx* h, int step) {
+	if (h->n_nbr == 0 || h->transport == 0 || !h->pending[step]) return 0;
+	if (h->transport == 1) {
+		const int spc = halo_spc(h, step);
+		for (int i = 0; i < h->n_nbr; i++) {
+			lfmgpu_ctx* p = h->peers[(size_t)h->nbr_rank[(size_t)i]];
+			int j = -1;
+			for (int k = 0; k < p->n_nbr; k++)
+				if (p->nbr_rank[(size_t)k] == h->rank) j = k;
+			if (j < 0) return fail("rank %d: neighbour %d does not list me", h->rank, h->nbr_rank[(size_t)i]);
+			if (!p->pending[step] && p->last_send_count[step] == 0) return fail("rank %d: neighbour %d has not started halo step %d", h->rank, p->rank, step);
+			const size_t rn = (size_t)(h->recv_start[(size_t)i + 1] - h->recv_start[(size_t)i]) * spc;
+			const size_t sn = (size_t)(p->send_start[(size_t)j + 1] - p->send_start[(size_t)j]) * spc;
+			if (rn != sn) return fail("halo size mismatch between ranks %d and %d (%zu vs %zu)", h->rank, p->rank, rn, sn);
+			CU(cudaStreamWaitEvent(h->s_comm, p->ev_packed[step], 0));
+			const char* src = (const char*)p->send_buf[step] + (size_t)p->send_start[(size_t)j] * spc * h->prec;
+			char* dst = (char*)h->recv_buf[step] + (size_t)h->recv_start[(size_t)i] * spc * h->prec;
+			if (p->device == h->device)
+				CU(cudaMemcpyAsync(dst, src, rn * h->prec, cudaMemcpyDeviceToDevice, h->s_comm));
+			else
+				CU(cudaMemcpyPeerAsync(dst, h->device, src, p->device, rn * h->prec, h->s_comm));
+		}
+		CU(cudaEventRecord(h->ev_arrived[step], h->s_comm));
+	}
+	CU(cudaStreamWaitEvent(h->s_main, h->ev_arrived[step], 0));
+	TRY(DISPATCH(h, t_unpack, h, step));
+	h->pending[step] = false;
+	return 0;
+}
+
+int use(lfmgpu_ctx* h) {
+	if (!h) return fail("null handle");
+	CU(cudaSetDevice(h->device));
+	return 0;
+}
+
+// one RK stage of every listed rank, in the call order of Mesh::solve (mesh_solver.cpp:500-679)
+int stage_all(lfmgpu_ctx** hs, int n, int scheme, int rk, double dt, int want_res) {
+	for (int r = 0; r < n; r++) {
+		lfmgpu_ctx* h = hs[r];
+		TRY(use(h));
+		h->rk_pending = rk;
+		TRY(halo_wait_impl(h, 0));
+		TRY(DISPATCH(h, t_set_bc, h));
+		TRY(DISPATCH(h, t_vis, h, h->n_nbr ? 0 : -1));
+		TRY(halo_start_impl(h, 1));
+	}
+	for (int r = 0; r < n; r++) {
+		lfmgpu_ctx* h = hs[r];
+		TRY(use(h));
+		if (h->n_nbr)
+			for (int s = 1; s < h->n_sub; s++) TRY(DISPATCH(h, t_vis, h, s));
+	}
+	for (int r = 0; r < n; r++) {
+		lfmgpu_ctx* h = hs[r];
+		TRY(use(h));
+		TRY(halo_wait_impl(h, 1));
+		TRY(DISPATCH(h, t_rk_stage, h, h->n_nbr ? 0 : -1, scheme, rk, dt, want_res));
+		TRY(halo_start_impl(h, 0));
+	}
+	for (int r = 0; r < n; r++) {
+		lfmgpu_ctx* h = hs[r];
+		TRY(use(h));
+		if (h->n_nbr)
+			for (int s = 1; s < h->n_sub; s++) TRY(DISPATCH(h, t_rk_stage, h, s, scheme, rk, dt, want_res));
+	}
+	return 0;
+}
+
+int steps_all(lfmgpu_ctx** hs, int n, int scheme, double dt, int n_steps, int first, int want_res) {
+	if (first) {
+		// pre-loop warm-up (mesh_solver.cpp:409-428)
+		for (int r = 0; r < n; r++) {
+			TRY(use(hs[r]));
+			TRY(halo_start_impl(hs[r], 0));
+		}
+		for (int r = 0; r < n; r++) {
+			TRY(use(hs[r]));
+			TRY(DISPATCH(hs[r], t_set_bc, hs[r]));
+			TRY(halo_wait_impl(hs[r], 0));
+		}
+		for (int r = 0; r < n; r++) {
+			TRY(use(hs[r]));
+			TRY(halo_start_impl(hs[r], 1));
+		}
+		for (int r = 0; r < n; r++) {
+			TRY(use(hs[r]));
+			TRY(halo_wait_impl(hs[r], 1));
+		}
+	}
+	for (int s = 0; s < n_steps; s++) {
+		for (int r = 0; r < n; r++) hs[r]->dq_zero = true;
+		const int order = hs[0]->c.rk_order;
+		for (int rk = 0; rk < order; rk++) TRY(stage_all(hs, n, scheme, rk, dt, want_res));
+		for (int r = 0; r < n; r++) {
+			TRY(use(hs[r]));
+			TRY(halo_wait_impl(hs[r], 0));
+		}
+	}
+	return 0;
+}
+
+}  // namespace
+
+// ======================================================================================================
+// C ABI
+// ======================================================================================================
+extern "C" {
+
+const char* lfmgpu_last_error(void) { return g_err.c_str(); }
+
+int lfmgpu_device_count(int* n) {
+	CU(cudaGetDeviceCount(n));
+	return 0;
+}
+
+int lfmgpu_create(const lfmgpu_desc* ds, int device, lfmgpu_t* out) {
+	if (!ds || !out) return fail("lfmgpu_create: null argument");
+	if (ds->precision != 4 && ds->precision != 8) return fail("lfmgpu_create: precision must be 4 or 8");
+	if (ds->dim != 2 && ds->dim != 3) return fail("lfmgpu_create: dim must be 2 or 3");
+	if (ds->n_sub < 1 || ds->n_sub > LFMGPU_MAX_SUBMESH) return fail("lfmgpu_create: bad submesh count");
+	CU(cudaSetDevice(device));
+	lfmgpu_ctx* h = new lfmgpu_ctx();
+	h->device = device;
+	h->prec = ds->precision;
+	h->D = ds->dim;
+	h->NQ = ds->dim + 2;
+	h->F = ds->max_slots;
+	h->n_cells = ds->n_cells;
+	h->n_faces = ds->n_faces;
+	h->n_bc = ds->n_bc_ghosts;
+	h->n_mpi = ds->n_mpi_ghosts;
+	h->n_tot = ds->n_cells + ds->n_bc_ghosts + ds->n_mpi_ghosts;
+	h->n_sub = ds->n_sub;
+	h->ncs = pad32((size_t)h->n_tot);
+	h->nfs = pad32((size_t)h->n_faces);
+	h->ngs = pad32((size_t)std::max(1, h->n_mpi));
+	memcpy(h->sub_cell_start, ds->sub_cell_start, sizeof h->sub_cell_start);
+	memcpy(h->sub_face_start, ds->sub_face_start, sizeof h->sub_face_start);
+	h->c = ds->c;
+	h->n_nbr = ds->n_nbr;
+	h->nbr_rank.assign(ds->nbr_rank, ds->nbr_rank + ds->n_nbr);
+	h->send_start.assign(1, 0);
+	h->recv_start.assign(1, 0);
+	if (ds->n_nbr) {
+		h->send_start.assign(ds->send_start, ds->send_start + ds->n_nbr + 1);
+		h->recv_start.assign(ds->recv_start, ds->recv_start + ds->n_nbr + 1);
+		if (h->recv_start[(size_t)ds->n_nbr] != ds->n_mpi_ghosts) {
+			delete h;
+			return fail("lfmgpu_create: recv_start does not cover n_mpi_ghosts");
+		}
+	}
+	int lo, hi;
+	cudaDeviceGetStreamPriorityRange(&lo, &hi);
+	int rc = 0;
+	if (cudaStreamCreateWithPriority(&h->s_main, cudaStreamNonBlocking, lo) != cudaSuccess ||
+	    cudaStreamCreateWithPriority(&h->s_comm, cudaStreamNonBlocking, hi) != cudaSuccess)
+		rc = fail("stream creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+	if (!rc) {
+		cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming);
+		for (int s = 0; s < 2; s++) {
+			cudaEventCreateWithFlags(&h->ev_packed[s], cudaEventDisableTiming);
+			cudaEventCreateWithFlags(&h->ev_arrived[s], cudaEventDisableTiming);
+		}
+		rc = h->prec == 8 ? build<double>(h, ds) : build<float>(h, ds);
+	}
+	if (!rc) rc = tile_plan_build(h, ds);
+	if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = fail("upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+	if (rc) {
+		lfmgpu_destroy(h);
+		return rc;
+	}
+	*out = h;
+	return 0;
+}
+
+int lfmgpu_destroy(lfmgpu_t h) {
+	if (!h) return 0;
+	cudaSetDevice(h->device);
+	cudaDeviceSynchronize();
+	if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+	for (auto& t : h->timed) {
+		cudaEventDestroy(t.a);
+		cudaEventDestroy(t.b);
+	}
+	for (void* p : h->allocs) cudaFree(p);
+	if (h->ev_ready) cudaEventDestroy(h->ev_ready);
+	for (int s = 0; s < 2; s++) {
+		if (h->ev_packed[s]) cudaEventDestroy(h->ev_packed[s]);
+		if (h->ev_arrived[s]) cudaEventDestroy(h->ev_arrived[s]);
+	}
+	if (h->s_main) cudaStreamDestroy(h->s_main);
+	if (h->s_comm) cudaStreamDestroy(h->s_comm);
+	delete h;
+	return 0;
+}
+
+int lfmgpu_sync(lfmgpu_t h) {
+	TRY(use(h));
+	CU(cudaStreamSynchronize(h->s_comm));
+	CU(cudaStreamSynchronize(h->s_main));
+	return 0;
+}
+
+int lfmgpu_set_option(lfmgpu_t h, const char* name, int value) {
+	TRY(use(h));
+	if (!strcmp(name, "use_tiles")) {
+		h->use_tiles = value;
+		return 0;
+	}
+	return fail("unknown option %s", name);
+}
+
+int lfmgpu_prepare_timestep(lfmgpu_t h) {
+	TRY(use(h));
+	h->dq_zero = true;
+	return 0;
+}
+int lfmgpu_prepare_rkstep(lfmgpu_t h, int rk_step) {
+	TRY(use(h));
+	if (rk_step < 0 || rk_step >= LFMGPU_MAX_RK) return fail("rk_step out of range");
+	h->rk_pending = rk_step;
+	return 0;
+}
+int lfmgpu_set_bc(lfmgpu_t h) {
+	TRY(use(h));
+	return DISPATCH(h, t_set_bc, h);
+}
+int lfmgpu_gradients(lfmgpu_t h, int submesh) {
+	// calc_gradients feeds only one_rk_step_M2AUSM: for the M1/M2 schemes served here its
+	// outputs are never read, so the call is accepted and does no work.
+	TRY(use(h));
+	(void)submesh;
+	return 0;
+}
+int lfmgpu_vis(lfmgpu_t h, int submesh) {
+	TRY(use(h));
+	if (submesh >= h->n_sub) return fail("submesh out of range");
+	return DISPATCH(h, t_vis, h, submesh);
+}
+int lfmgpu_rk_stage(lfmgpu_t h, int submesh, int scheme, int rk_step, double dt, int want_res) {
+	TRY(use(h));
+	if (submesh >= h->n_sub) return fail("submesh out of range");
+	if (scheme != LFMGPU_SCHEME_M1 && scheme != LFMGPU_SCHEME_M2) return fail("scheme %d is not served by the GPU path", scheme);
+	if (rk_step < 0 || rk_step >= LFMGPU_MAX_RK) return fail("rk_step out of range");
+	return DISPATCH(h, t_rk_stage, h, submesh, scheme, rk_step, dt, want_res);
+}
+int lfmgpu_halo_start(lfmgpu_t h, int comm_step) {
+	TRY(use(h));
+	if (comm_step != 0 && comm_step != 1) return fail("comm_step must be 0 or 1");
+	return halo_start_impl(h, comm_step);
+}
+int lfmgpu_halo_wait(lfmgpu_t h, int comm_step) {
+	TRY(use(h));
+	if (comm_step != 0 && comm_step != 1) return fail("comm_step must be 0 or 1");
+	return halo_wait_impl(h, comm_step);
+}
+int lfmgpu_cfl(lfmgpu_t h, double dt, double* cfl_max) {
+	TRY(use(h));
+	return DISPATCH(h, t_cfl_dt, h, dt, 0, cfl_max);
+}
+int lfmgpu_dt(lfmgpu_t h, double cfl_max, double* dt_min) {
+	TRY(use(h));
+	return DISPATCH(h, t_cfl_dt, h, cfl_max, 1, dt_min);
+}
+int lfmgpu_average(lfmgpu_t h, int time_step) {
+	TRY(use(h));
+	return DISPATCH(h, t_average, h, time_step);
+}
+int lfmgpu_forces(lfmgpu_t h, int patch, double* Fpre, double* Fvis) {
+	TRY(use(h));
+	return DISPATCH(h, t_forces, h, patch, Fpre, Fvis);
+}
+int lfmgpu_residual(lfmgpu_t h, double* res) {
+	TRY(use(h));
+	CU(cudaMemcpyAsync(res, h->d_res, (size_t)h->NQ * sizeof(double), cudaMemcpyDeviceToHost, h->s_main));
+	CU(cudaMemsetAsync(h->d_res, 0, 8 * sizeof(double), h->s_main));
+	CU(cudaStreamSynchronize(h->s_main));
+	return 0;
+}
+
+int lfmgpu_warmup(lfmgpu_t h) {
+	TRY(use(h));
+	if (h->transport == 1 && h->n_ranks > 1) return fail("lfmgpu_warmup: in-process ranks must be driven together (lfmgpu_step_multi)");
+	lfmgpu_ctx* hs[1] = {h};
+	return steps_all(hs, 1, 0, 0.0, 0, 1, 0);
+}
+
+int lfmgpu_step(lfmgpu_t h, int scheme, double dt, int n_steps, int minmod, int want_res) {
+	(void)minmod;
+	TRY(use(h));
+	if (scheme != LFMGPU_SCHEME_M1 && scheme != LFMGPU_SCHEME_M2) return fail("scheme %d is not served by the GPU path", scheme);
+	if (h->transport == 1 && h->n_ranks > 1) return fail("lfmgpu_step: in-process ranks must be driven together (lfmgpu_step_multi)");
+	if (h->n_nbr && h->transport == 0) return fail("lfmgpu_step: rank has neighbours but no halo transport was initialised");
+	lfmgpu_ctx* hs[1] = {h};
+	return steps_all(hs, 1, scheme, dt, n_steps, 0, want_res);
+}
+
+int lfmgpu_step_multi(const lfmgpu_t* hs, int n_ranks, int scheme, double dt, int n_steps, int first, int want_res) {
+	if (!hs || n_ranks < 1) return fail("lfmgpu_step_multi: bad arguments");
+	if (scheme != LFMGPU_SCHEME_M1 && scheme != LFMGPU_SCHEME_M2) return fail("scheme %d is not served by the GPU path", scheme);
+	std::vector<lfmgpu_ctx*> v(hs, hs + n_ranks);
+	for (auto* h : v)
+		if (h->n_nbr && h->transport == 0) return fail("lfmgpu_step_multi: rank has neighbours but no halo transport");
+	return steps_all(v.data(), n_ranks, scheme, dt, n_steps, first, want_res);
+}
+
+// ---- data movement ---------------------------------------------------------------------------------
+int lfmgpu_download(lfmgpu_t h, int field, void* dst, size_t dst_bytes) {
+	TRY(use(h));
+	TRY(lfmgpu_sync(h));
+	const int D = h->D, NQ = h->NQ, nc = h->n_cells;
+	const size_t es = (size_t)h->prec;
+	const char* base = nullptr;
+	size_t stride = 0, n = (size_t)nc, off = 0;
+	int comps = 1;
+	bool derived = false;
+	const char *dudx = h->prec == 8 ? (const char*)h->md.dudx : (const char*)h->mf.dudx;
+	switch (field) {
+		case LFMGPU_FIELD_Q: base = (const char*)h->q[h->cur]; stride = h->ncs; comps = NQ; break;
+		case LFMGPU_FIELD_DQ: base = h->prec == 8 ? (const char*)h->md.dq : (const char*)h->mf.dq; stride = (size_t)nc; comps = NQ; break;
+		case LFMGPU_FIELD_RES: base = h->prec == 8 ? (const char*)h->md.RES : (const char*)h->mf.RES; stride = (size_t)nc; comps = NQ; break;
+		case LFMGPU_FIELD_DUDX: base = dudx; stride = h->ncs; comps = D * D; break;
+		case LFMGPU_FIELD_DTDX: base = h->prec == 8 ? (const char*)h->md.dTdx : (const char*)h->mf.dTdx; stride = h->ncs; comps = D; break;
+		case LFMGPU_FIELD_PAVG: base = h->prec == 8 ? (const char*)h->md.pAVG : (const char*)h->mf.pAVG; stride = (size_t)nc; break;
+		case LFMGPU_FIELD_PRMS: base = h->prec == 8 ? (const char*)h->md.pRMS : (const char*)h->mf.pRMS; stride = (size_t)nc; break;
+		case LFMGPU_FIELD_QGHOST: base = (const char*)h->q[h->cur]; stride = h->ncs; comps = NQ; off = (size_t)nc; n = (size_t)(h->n_bc + h->n_mpi); break;
+		case LFMGPU_FIELD_TAUMC: comps = D * D; derived = true; break;
+		case LFMGPU_FIELD_SIGMAU: comps = D; derived = true; break;
+		default: return fail("unknown field %d", field);
+	}
+	if (dst_bytes < n * comps * es) return fail("lfmgpu_download: destination too small (%zu < %zu)", dst_bytes, n * comps * es);
+	if (n == 0) return 0;
+	if (derived) {
+		// tauMC / sigmaU are not stored: rebuild them from q and dudx with the calc_VIS expressions on the host
+		std::vector<char> qh((size_t)NQ * n * es), gh((size_t)D * D * n * es);
+		// calc_VIS saw the conservatives of the stage it ran in: after a completed stage those are in the other buffer
+		const char* qsrc = (const char*)h->q[h->stage_done ? 1 - h->cur : h->cur];
+		for (int i = 0; i < NQ; i++) CU(cudaMemcpy(qh.data() + (size_t)i * n * es, qsrc + (size_t)i * h->ncs * es, n * es, cudaMemcpyDeviceToHost));
+		for (int i = 0; i < D * D; i++) CU(cudaMemcpy(gh.data() + (size_t)i * n * es, dudx + (size_t)i * h->ncs * es, n * es, cudaMemcpyDeviceToHost));
+		auto run = [&](auto zero) {
+			using R = decltype(zero);
+			const R* q = (const R*)qh.data();
+			const R* g = (const R*)gh.data();
+			const R mu = (R)h->c.mu;
+			const R c_tau = (R)(2.0 / 3.0 * (double)mu), c_diag = (R)((double)mu * 2.0 / 3.0);
+			R* o = (R*)dst;
+			for (size_t c = 0; c < n; c++) {
+				R du[3][3], tau[3][3], U[3];
+				for (int i = 0; i < D; i++) {
+					U[i] = q[(size_t)(i + 1) * n + c] / q[c];
+					for (int j = 0; j < D; j++) du[i][j] = g[(size_t)(i * D + j) * n + c];
+				}
+				for (int nD = 0; nD < D; nD++) {
+					tau[nD][nD] = R(2.0) * du[nD][nD];
+					for (int nD1 = nD + 1; nD1 < D + nD; nD1++) {
+						const int nD2 = nD1 % D;
+						tau[nD][nD2] = mu * (du[nD][nD2] + du[nD2][nD]);
+						tau[nD][nD] -= du[nD2][nD2];
+					}
+					tau[nD][nD] *= c_tau;
+				}
+				R diag = 0;
+				for (int nD = 0; nD < D; nD++) diag -= du[nD][nD];
+				diag *= c_diag;
+				for (int i = 0; i < D; i++) {
+					if (field == LFMGPU_FIELD_SIGMAU) {
+						volatile R s = U[0] * tau[i][0];
+						for (int j = 1; j < D; j++) {
+							volatile R t = U[j] * tau[i][j];
+							s = s + t;
+						}
+						o[c * D + i] = s;
+					} else {
+						for (int j = 0; j < D; j++) {
+							volatile R t = mu * du[j][i];
+							o[(c * D + i) * D + j] = t;
+						}
+						o[(c * D + i) * D + i] += diag;
+					}
+				}
+			}
+		};
+		if (h->prec == 8) run(double(0)); else run(float(0));
+		return 0;
+	}
+	std::vector<char> tmp((size_t)comps * n * es);
+	for (int i = 0; i < comps; i++) CU(cudaMemcpy(tmp.data() + (size_t)i * n * es, base + ((size_t)i * stride + off) * es, n * es, cudaMemcpyDeviceToHost));
+	if (field == LFMGPU_FIELD_QGHOST && h->n_bc && h->stage_done) {
+		// physical ghosts were last written by set_boundary_conditions of the latest stage, i.e. into the other buffer
+		const char* old = (const char*)h->q[1 - h->cur];
+		for (int i = 0; i < comps; i++) CU(cudaMemcpy(tmp.data() + (size_t)i * n * es, old + ((size_t)i * stride + off) * es, (size_t)h->n_bc * es, cudaMemcpyDeviceToHost));
+	}
+	// SoA -> AoS
+	char* o = (char*)dst;
+	for (size_t c = 0; c < n; c++)
+		for (int i = 0; i < comps; i++) memcpy(o + (c * comps + i) * es, tmp.data() + ((size_t)i * n + c) * es, es);
+	return 0;
+}
+
+int lfmgpu_upload_q(lfmgpu_t h, const void* q, size_t bytes) {
+	TRY(use(h));
+	TRY(lfmgpu_sync(h));
+	const size_t es = (size_t)h->prec, n = (size_t)h->n_cells;
+	if (bytes != n * h->NQ * es) return fail("lfmgpu_upload_q: expected %zu bytes", n * h->NQ * es);
+	std::vector<char> tmp(bytes);
+	for (size_t c = 0; c < n; c++)
+		for (int i = 0; i < h->NQ; i++) memcpy(tmp.data() + ((size_t)i * n + c) * es, (const char*)q + (c * h->NQ + i) * es, es);
+	for (int i = 0; i < h->NQ; i++) CU(cudaMemcpy((char*)h->q[h->cur] + (size_t)i * h->ncs * es, tmp.data() + (size_t)i * n * es, n * es, cudaMemcpyHostToDevice));
+	h->stage_done = false;
+	return 0;
+}
+
+// SoA variants for the end-to-end path: host arrays are [NQ][n_cells] (component-major), pinned or not;
+// asynchronous on the compute stream.
+int lfmgpu_upload_q_soa_async(lfmgpu_t h, const void* q, size_t bytes) {
+	TRY(use(h));
+	const size_t es = (size_t)h->prec, n = (size_t)h->n_cells;
+	if (bytes != n * h->NQ * es) return fail("lfmgpu_upload_q_soa_async: expected %zu bytes", n * h->NQ * es);
+	CU(cudaMemcpy2DAsync(h->q[h->cur], h->ncs * es, q, n * es, n * es, (size_t)h->NQ, cudaMemcpyHostToDevice, h->s_main));
+	return 0;
+}
+int lfmgpu_download_q_soa_async(lfmgpu_t h, void* q, size_t bytes) {
+	TRY(use(h));
+	const size_t es = (size_t)h->prec, n = (size_t)h->n_cells;
+	if (bytes != n * h->NQ * es) return fail("lfmgpu_download_q_soa_async: expected %zu bytes", n * h->NQ * es);
+	CU(cudaMemcpy2DAsync(q, n * es, h->q[h->cur], h->ncs * es, n * es, (size_t)h->NQ, cudaMemcpyDeviceToHost, h->s_main));
+	return 0;
+}
+
+int lfmgpu_host_alloc(void** p, size_t bytes) {
+	CU(cudaMallocHost(p, bytes));
+	return 0;
+}
+int lfmgpu_host_free(void* p) {
+	CU(cudaFreeHost(p));
+	return 0;
+}
+
+// ---- halo transport --------------------------------------------------------------------------------
+int lfmgpu_nccl_unique_id(void* id128) {
+	TRY(load_nccl());
+	ncclUniqueId id;
+	NC(g_nccl.GetUniqueId(&id));
+	static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+	memcpy(id128, &id, 128);
+	return 0;
+}
+int lfmgpu_comm_init_nccl(lfmgpu_t h, const void* id128, int rank, int n_ranks) {
+	TRY(use(h));
+	TRY(load_nccl());
+	ncclUniqueId id;
+	memcpy(&id, id128, 128);
+	NC(g_nccl.CommInitRank(&h->comm, n_ranks, id, rank));
+	h->rank = rank;
+	h->n_ranks = n_ranks;
+	h->transport = 2;
+	return 0;
+}
+int lfmgpu_comm_init_local(lfmgpu_t h, int rank, int n_ranks, const lfmgpu_t* peers) {
+	TRY(use(h));
+	if (rank < 0 || rank >= n_ranks) return fail("bad rank");
+	h->rank = rank;
+	h->n_ranks = n_ranks;
+	h->peers.assign(peers, peers + n_ranks);
+	for (int i = 0; i < h->n_nbr; i++) {
+		const int r = h->nbr_rank[(size_t)i];
+		if (r < 0 || r >= n_ranks || !h->peers[(size_t)r]) return fail("neighbour rank %d has no handle", r);
+		lfmgpu_ctx* p = h->peers[(size_t)r];
+		if (p->device != h->device) {
+			int can = 0;
+			CU(cudaDeviceCanAccessPeer(&can, h->device, p->device));
+			if (can) {
+				cudaError_t e = cudaDeviceEnablePeerAccess(p->device, 0);
+				if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail("cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+				cudaGetLastError();
+			}
+		}
+	}
+	h->transport = 1;
+	return 0;
+}
+int lfmgpu_allreduce(lfmgpu_t h, double* values, int n, int op) {
+	// op: 0 sum, 1 min, 2 max -- the per-step scalar reductions of Mesh::solve (mesh_solver.cpp:715, 763-779)
+	TRY(use(h));
+	if (h->transport != 2) return 0;   // single rank, or in-process ranks reduced by the caller
+	if (n > 8) return fail("lfmgpu_allreduce: at most 8 values");
+	CU(cudaMemcpyAsync(h->d_scalar, values, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->s_main));
+	NC(g_nccl.AllReduce(h->d_scalar, h->d_scalar, (size_t)n, ncclDouble, op == 0 ? ncclSum : (op == 1 ? ncclMin : ncclMax), h->comm, h->s_main));
+	CU(cudaMemcpyAsync(values, h->d_scalar, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->s_main));
+	CU(cudaStreamSynchronize(h->s_main));
+	return 0;
+}
+int lfmgpu_halo_send_count(lfmgpu_t h, int comm_step, size_t* n_scalars) {
+	if (!h || comm_step < 0 || comm_step > 1) return fail("bad argument");
+	*n_scalars = h->last_send_count[comm_step];
+	return 0;
+}
+int lfmgpu_download_send_buffer(lfmgpu_t h, int comm_step, void* dst, size_t dst_bytes) {
+	TRY(use(h));
+	if (comm_step < 0 || comm_step > 1) return fail("bad argument");
+	const size_t bytes = h->last_send_count[comm_step] * (size_t)h->prec;
+	if (dst_bytes < bytes) return fail("destination too small");
+	CU(cudaStreamSynchronize(h->s_comm));
+	if (bytes) CU(cudaMemcpy(dst, h->send_buf[comm_step], bytes, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+// ---- introspection ---------------------------------------------------------------------------------
+int lfmgpu_launch_count(lfmgpu_t h, uint64_t* n) {
+	if (!h) return fail("null handle");
+	*n = h->launches;
+	return 0;
+}
+int lfmgpu_enable_kernel_timing(lfmgpu_t h, int on) {
+	TRY(use(h));
+	TRY(lfmgpu_sync(h));
+	for (auto& t : h->timed) {
+		cudaEventDestroy(t.a);
+		cudaEventDestroy(t.b);
+	}
+	h->timed.clear();
+	h->timing = on != 0;
+	return 0;
+}
+int lfmgpu_kernel_time(lfmgpu_t h, const char* prefix, double* total_ms, uint64_t* launches) {
+	TRY(use(h));
+	TRY(lfmgpu_sync(h));
+	double tot = 0;
+	uint64_t n = 0;
+	const size_t pl = strlen(prefix);
+	for (auto& t : h->timed) {
+		if (strncmp(t.name, prefix, pl)) continue;
+		float ms = 0;
+		CU(cudaEventElapsedTime(&ms, t.a, t.b));
+		tot += ms;
+		n++;
+	}
+	*total_ms = tot;
+	*launches = n;
+	return 0;
+}
+int lfmgpu_tile_info(lfmgpu_t h, int* n_tiles, int* tile_cells, size_t* smem_bytes, double* halo_face_ratio) {
+	if (!h) return fail("null handle");
+	*n_tiles = h->tiles.ready ? h->tiles.n_tiles : 0;
+	*tile_cells = h->tiles.tile_cells;
+	*smem_bytes = h->tiles.smem_bytes;
+	*halo_face_ratio = h->tiles.halo_face_ratio;
+	return 0;
+}
+
+}  // extern "C"
