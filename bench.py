@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py -- cell-updates/s per RK stage of the per-iteration solve on B200, and the reference CPU arm.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                 the CUDA path (one rank per GPU)
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W] the reference's own CPU solver (oracle/_ref)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...               multi-GPU (weak scaling, NCCL halo exchange)
+
+Workload (BASELINE.json configs[4], the one the metric is quoted on): synthetic 3D hex polyMesh, 256^3 = 16.8 M
+cells PER GPU (blocks 1x1x1, 2x1x1, 2x2x1, 2x2x2 for N = 1,2,4,8), M2 scheme + laminar viscous terms + sponge,
+RK5, fp64.  One "step" is one time step = 5 RK stages over every cell of the job; value = cells * 5 * K / time.
+The working set (about 7 GB per GPU) is far larger than the 126 MB L2, so no L2 flush is needed between steps.
+
+Printed JSON keys follow the driver contract; see DESIGN.md section "Measurement" for roofline / cpu_baseline.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from lfm_public_b200 import host_api  # noqa: E402
+from lfm_public_b200.tools import casegen, meshgen  # noqa: E402
+
+BLOCKS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+MU = 7.17948717948718e-05          # examples/3D_Cylinder_Re3900/S thermophysicalProperties
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "lfm_solve_ref")
+REF_BIN_SP = os.path.join(ROOT, "oracle", "_ref", "lfm_solve_ref_sp")
+
+
+def b_alg(D, s, fbar):
+    """Algorithmic bytes per cell per RK stage: gradient pass G + flux/update pass F."""
+    G = s * ((D + 3) + (D * D + D)) + fbar * ((D + 1) * s + 8)
+    F = s * (2 * (D + 2) + (D * D + D) + 2 + 2 * (D + 2)) + fbar * ((2 * D + 1) * s + 8)
+    return G, F
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------------------
+# synthetic block case (fields are analytic in the GLOBAL coordinates so that every rank of a job agrees)
+# ----------------------------------------------------------------------------------------------------------
+def block_fields(m, n, blocks, rank):
+    nx, ny, nz = n
+    bx, by, bz = blocks
+    bi, bj, bk = rank % bx, (rank // bx) % by, rank // (bx * by)
+    h = 1.0 / (nx * bx)
+    L = (1.0, h * ny * by, h * nz * bz)
+    xc = (np.arange(nx) + 0.5 + bi * nx) * h
+    yc = (np.arange(ny) + 0.5 + bj * ny) * h
+    zc = (np.arange(nz) + 0.5 + bk * nz) * h
+    Z, Y, X = np.meshgrid(zc, yc, xc, indexing="ij")      # cell id = i + nx*(j + ny*k)
+    X, Y, Z = X.ravel(), Y.ravel(), Z.ravel()
+    sx, sy, sz = 2 * np.pi * X / L[0], 2 * np.pi * Y / L[1], 2 * np.pi * Z / L[2]
+    p = 1.0 + 0.01 * np.sin(sx) * np.cos(sy)
+    T = np.ones_like(p)
+    U = np.stack([0.2 * (1.0 + 0.05 * np.sin(sy)), 0.01 * np.sin(sx), 0.01 * np.sin(sz)], axis=1)
+    alpha = np.minimum(X, L[0] - X)                       # distance to the inlet / outlet planes
+    return dict(p=p, T=T, U=U, alpha=alpha), h
+
+
+def build_rank_case(n, blocks, rank, n_ranks, precision, scheme):
+    m = meshgen.hex_block((n, n, n), blocks, rank)
+    fields, h = block_fields(m, (n, n, n), blocks, rank)
+    dt = 0.5 * h / 1.2                                     # acoustic CFL ~ 0.5 (c = 1, |U| = 0.2)
+    o = host_api.default_opts(solver=scheme, dimension=3, delta_t=dt, Ls=0.15, mu0=MU, mach=0.2, comm_type=2,
+                              double_precision=1 if precision == 8 else 0)
+    o.U_inf[0] = 0.2
+    case = host_api.Case.from_mesh(m, o, fields, rank=rank, n_ranks=n_ranks)
+    return case, dt
+
+
+# ----------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        exe = shutil.which("nvidia-smi")
+        if not exe:
+            return
+        try:
+            self.proc = subprocess.Popen([exe, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return None
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# reference CPU arm: the reference's own solver binary on a bounded sample of the workload
+# ----------------------------------------------------------------------------------------------------------
+def reference_run(n_sample, n_ranks, steps, scheme, precision, keep_dir=None):
+    """Runs oracle/_ref/lfm_solve_ref[_sp] (the reference's unmodified src/*.cpp) on an n_sample^3 hex box split into
+    n_ranks blocks (mini-MPI shim: one forked process per rank) and returns cell-stages/s from the reference's own
+    `Rk Loop` timer (src/mesh_solver.cpp:906-919)."""
+    exe = REF_BIN if precision == 8 else REF_BIN_SP
+    if not os.path.exists(exe):
+        raise RuntimeError(f"{exe} missing (built by `make -C oracle ref` where /root/reference exists)")
+    blocks = {1: None, 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2), 16: (4, 2, 2), 32: (4, 4, 2), 64: (4, 4, 4)}[n_ranks]
+    tmp = keep_dir or tempfile.mkdtemp(prefix="lfm_ref_")
+    try:
+        m = meshgen.hex_box(n_sample, n_sample, n_sample, lengths=(1.0, 1.0, 1.0), z_cyclic=(blocks is None or blocks[2] == 1))
+        h = 1.0 / n_sample
+        dt = 0.5 * h / 1.2
+        cr = meshgen.block_assignment(m, blocks) if blocks else None
+        nx = n_sample
+        fields, _ = block_fields(m, (nx, nx, nx), (1, 1, 1), 0)
+        casegen.write_case(tmp, m, fields=fields, cell_rank=cr, solver=scheme, dimension=3, deltaT=dt, endTime=dt * steps,
+                           writeInterval=10 ** 7, Ls=0.15, mu=MU, haveResiduals=False, printInfoFreq=10 ** 6,
+                           doublePrecision=(precision == 8), commType=2)
+        env = dict(os.environ)
+        args = [exe]
+        if cr is not None:
+            env["LFM_MPI_NP"] = str(n_ranks)
+            args.append("-p")
+        out = subprocess.run(args, cwd=tmp, env=env, capture_output=True, text=True, timeout=1800)
+        if "Simulation finished successfully" not in out.stdout:
+            raise RuntimeError("reference run failed: " + out.stdout[-1500:] + out.stderr[-1500:])
+        rk = float(re.search(r"\[\s*([0-9.eE+-]+)\]: Rk Loop", out.stdout).group(1))
+        return dict(cells=n_sample ** 3, steps=steps, rk_loop_s=rk, value=n_sample ** 3 * 5 * steps / rk)
+    finally:
+        if not keep_dir:
+            shutil.rmtree(tmp, ignore_errors=True)
+
+
+def pick_cpu_ranks():
+    cores = os.cpu_count() or 1
+    p = 1
+    while p * 2 <= min(cores, 64):
+        p *= 2
+    return p, cores
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ranks, cores = pick_cpu_ranks()
+    n_sample = args.ref_n
+    steps = max(1, args.steps)
+    if args.warmup > 0:
+        reference_run(n_sample, ranks, max(1, min(args.warmup, 2)), args.scheme, args.precision)   # page-cache / binary warm-up
+    r = reference_run(n_sample, ranks, steps, args.scheme, args.precision)
+    ms = 1e3 * r["rk_loop_s"] / steps
+    sample = (f"{n_sample}^3 hex box ({r['cells']} cells) in {ranks} blocks, {steps} time steps x 5 RK stages, reference binary "
+              f"oracle/_ref/lfm_solve_ref over the mini-MPI shim (one process per rank), reference's own 'Rk Loop' timer")
+    line = {
+        "impl": "reference", "metric": "cell-updates/s per RK stage", "value": r["value"], "unit": "cell-updates/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.precision == 8 else "f32", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": r["value"], "unit": "cell-updates/s", "cores": ranks, "kind": "reference", "sample": sample,
+                         "host_cores": cores},
+        "e2e": {"value": r["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_gpus):
+    n = args.n
+    bl = BLOCKS[n_gpus]
+    return {"workload": f"synthetic 3D hex polyMesh weak scaling, {n}^3 = {n ** 3} cells per GPU, blocks {bl[0]}x{bl[1]}x{bl[2]} "
+                        f"({n ** 3 * n_gpus} cells), {'M2' if args.scheme == 1 else 'M1'} + laminar viscous + sponge, RK5, commType 2",
+            "cells_per_gpu": n ** 3, "total_cells": n ** 3 * n_gpus, "rk_stages_per_step": 5,
+            "l2_policy": "inputs larger than L2 (about 7 GB of state per GPU at 256^3), no flush"}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    from lfm_public_b200 import gpu_api
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one process per GPU)")
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_
+        dist = dist_
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if gpu_api.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    blocks = BLOCKS[world]
+    t0 = time.time()
+    case, dt = build_rank_case(args.n, blocks, rank, world, args.precision, args.scheme)
+    if world > 1:
+        host_api.exchange_distributed(case, rank)
+    else:
+        case.finish()
+    t_setup = time.time() - t0
+    g = gpu_api.GpuSolver(case, local_rank)
+    g.set_option("use_tiles", args.use_tiles)
+    if world > 1:
+        import torch
+        ids = [gpu_api.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        g.comm_init_nccl(ids[0], rank, world)
+    n_cells = g.n_cells
+    NQ, D, s = g.NQ, g.D, args.precision
+    K, W = args.steps, args.warmup
+
+    def barrier():
+        g.sync()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput -------------------------------------------------------------------------
+    g.warmup()
+    g.step(args.scheme, dt, W)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    l0 = g.launch_count
+    g.event_record(0)
+    g.step(args.scheme, dt, K)
+    g.event_record(1)
+    barrier()
+    ms_total = max_over_ranks(g.event_elapsed_ms(0, 1))
+    launches = g.launch_count - l0
+    clk = clocks.stop() if rank == 0 else None
+    q_check = g.download(0)
+    finite = bool(np.isfinite(q_check).all())
+    del q_check
+
+    # ---- per-kernel device times (separate pass, events around every launch) ---------------------------------
+    g.enable_kernel_timing(True)
+    g.step(args.scheme, dt, max(1, min(K, 3)))
+    g.sync()
+    ktimes = {}
+    for name in ("tile_stage", "tile_grad", "k_flux_face", "k_update_cell", "k_grad_cell", "k_set_bc", "k_pack", "k_unpack"):
+        ms, nl = g.kernel_time(name)
+        if nl:
+            ktimes[name] = (ms, nl)
+    g.enable_kernel_timing(False)
+
+    # ---- end-to-end through the C ABI with host buffers ----------------------------------------------------------
+    real = np.float64 if s == 8 else np.float32
+    pin_in = gpu_api.PinnedArray((NQ, n_cells), real)
+    pin_out = gpu_api.PinnedArray((NQ, n_cells), real)
+    g.download_q_soa_async(pin_in.ptr, pin_in.nbytes)
+    g.sync()
+    Ke = max(1, min(K, 5))
+    for it in range(1 + Ke):
+        if it == 1:
+            barrier()
+            g.event_record(2)
+        g.upload_q_soa_async(pin_in.ptr, pin_in.nbytes)
+        g.step(args.scheme, dt, 1)
+        g.download_q_soa_async(pin_out.ptr, pin_out.nbytes)
+    g.event_record(3)
+    barrier()
+    ms_e2e = max_over_ranks(g.event_elapsed_ms(2, 3)) / Ke
+    e2e_ok = bool(np.isfinite(pin_out.array).all())
+    pin_in.free()
+    pin_out.free()
+
+    total_cells = n_cells * world if dist is None else int(max_over_ranks(float(n_cells))) * world
+    ms_step = ms_total / K
+    value = total_cells * 5 / (ms_step * 1e-3)
+    e2e_value = total_cells * 5 / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        g.close()
+        return
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------------------------------
+    peak, peak_src = measured_peak()
+    fbar = 3.0
+    Gb, Fb = b_alg(D, s, fbar)
+    alg = {"tile_stage": Fb, "tile_grad": Gb, "k_grad_cell": Gb, "k_flux_face": Fb, "k_update_cell": Fb}
+    dom = max((k for k in ktimes if k in alg), key=lambda k: ktimes[k][0], default=None)
+    roofline = None
+    if dom:
+        ms, nl = ktimes[dom]
+        per_launch_cells = n_cells * (max(1, min(K, 3)) * 5) / nl      # cells one launch covers
+        achieved = alg[dom] * per_launch_cells / (ms / nl * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": peak_src, "alg_bytes_per_cell": alg[dom],
+                    "avg_launch_ms": ms / nl, "kernel_ms_per_step": {k: v[0] / max(1, min(K, 3)) for k, v in ktimes.items()},
+                    "stage_frac": (Gb + Fb) * n_cells * 5 / (ms_step * 1e-3) / 1e9 / peak}
+
+    # ---- CPU baseline: the reference binary on a bounded sample (rank 0, N == 1 only) ----------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            ranks, cores = pick_cpu_ranks()
+            r = reference_run(args.ref_n, ranks, args.ref_steps, args.scheme, args.precision)
+            cpu = {"value": r["value"], "unit": "cell-updates/s", "cores": ranks, "kind": "reference", "host_cores": cores,
+                   "sample": f"{args.ref_n}^3 hex box in {ranks} blocks, {args.ref_steps} steps x 5 RK stages, oracle/_ref/lfm_solve_ref "
+                             f"(reference src/*.cpp unchanged, mini-MPI shim), reference 'Rk Loop' timer = {r['rk_loop_s']:.3f} s"}
+        except Exception as e:      # the baseline is reported, never required for the GPU number
+            cpu = {"value": None, "unit": "cell-updates/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"[:300]}
+
+    line = {
+        "metric": "cell-updates/s per RK stage", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64" if s == 8 else "f32", "data": "synthetic", "config": workload_config(args, world),
+        "roofline": roofline, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": int(NQ * n_cells * s) * world,
+                "d2h_bytes_per_step": int(NQ * n_cells * s) * world, "ms_per_step": ms_e2e, "finite": e2e_ok},
+        "gpu_launches": int(launches), "clocks": clk, "finite": finite, "setup_s": t_setup,
+        "tiles": g.tile_info(), "use_tiles": args.use_tiles,
+    }
+    print(json.dumps(line), flush=True)
+    g.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gpu", choices=["gpu", "reference"])
+    ap.add_argument("--n", type=int, default=int(os.environ.get("LFM_BENCH_N", "256")), help="cells per side of each GPU's block")
+    ap.add_argument("--precision", type=int, default=8, choices=[4, 8])
+    ap.add_argument("--scheme", type=int, default=1, choices=[0, 1], help="0 = M1, 1 = M2")
+    ap.add_argument("--use-tiles", type=int, default=1)
+    ap.add_argument("--ref-n", type=int, default=64, help="cells per side of the CPU sample")
+    ap.add_argument("--ref-steps", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.gpus not in BLOCKS:
+        raise SystemExit("--gpus must be 1, 2, 4 or 8")
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -174,6 +174,10 @@ int lfmgpu_launch_count(lfmgpu_t h, uint64_t* n);            /* kernels launched
  * with CUDA events on the launching stream when timing is enabled */
 int lfmgpu_enable_kernel_timing(lfmgpu_t h, int on);
 int lfmgpu_kernel_time(lfmgpu_t h, const char* prefix, double* total_ms, uint64_t* launches);
+/* CUDA events on the handle's compute stream (after joining the halo stream): record into slot 0..7, read the
+ * device time between two recorded slots (blocks until slot_b has happened) */
+int lfmgpu_event_record(lfmgpu_t h, int slot);
+int lfmgpu_event_elapsed_ms(lfmgpu_t h, int slot_a, int slot_b, double* ms);
 /* shape of the fused-tile plan built at create time (n_tiles == 0: mesh served by the unfused kernels) */
 int lfmgpu_tile_info(lfmgpu_t h, int* n_tiles, int* tile_cells, size_t* smem_bytes, double* halo_face_ratio);
 

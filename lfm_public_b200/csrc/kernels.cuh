@@ -272,7 +272,7 @@ template <class R> __global__ void __launch_bounds__(kBlock) k_copy_q(const R* _
 // halo pack (cfd_v0.cpp:3303-3331 / 3398-3408 / 3475-3499) and unpack (3608-3692)
 // mode bit 0: q payload, bit 1: viscous payload.  Wire order per cell: q | dudx | dTdx | tauMC | sigmaU
 // ---------------------------------------------------------------------------------------------------
-template <class R, int D> __global__ void __launch_bounds__(kBlock) k_pack(DevMesh<R> m, const R* __restrict__ q, const int* __restrict__ send_cell, int n_send, int mode, R* __restrict__ buf) {
+template <class R, int D> __global__ void __launch_bounds__(kBlock) k_pack(DevMesh<R> m, const R* __restrict__ q, const R* __restrict__ qvis, const int* __restrict__ send_cell, int n_send, int mode, R* __restrict__ buf) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n_send) return;
 	constexpr int NQ = D + 2, NV = 2 * D * D + 2 * D;
@@ -294,7 +294,10 @@ template <class R, int D> __global__ void __launch_bounds__(kBlock) k_pack(DevMe
 			for (int b = 0; b < D; b++) dudx[a][b] = m.dudx[(size_t)(a * D + b) * m.ncs + c];
 			dTdx[a] = m.dTdx[(size_t)a * m.ncs + c];
 		}
-		vis_cell_terms<R, D>(m.k, cq, dudx, tauMC, sigmaU);
+		R vq[NQ];
+#pragma unroll
+		for (int k = 0; k < NQ; k++) vq[k] = qvis[k * m.ncs + c];
+		vis_cell_terms<R, D>(m.k, vq, dudx, tauMC, sigmaU);
 #pragma unroll
 		for (int a = 0; a < D; a++)
 #pragma unroll

@@ -111,6 +111,7 @@ struct lfmgpu_ctx {
 	unsigned updated_mask = 0;         // submeshes already advanced in the running stage
 	bool dq_zero = true;               // prepare_for_timestep seen, no stage yet
 	int rk_pending = 0;
+	bool vis_on_cur = true;            // the conservatives calc_VIS last saw are q[cur] (false after a flip: q[1-cur])
 	bool stage_done = false;           // at least one stage completed (q[1-cur] holds the pre-stage state)
 	double* d_res = nullptr;           // [NQ] sum of RES^2
 	double* d_res_partial = nullptr;
@@ -121,6 +122,7 @@ struct lfmgpu_ctx {
 	void* d_force_out = nullptr;
 	cudaStream_t s_main = nullptr, s_comm = nullptr;
 	cudaEvent_t ev_ready = nullptr;
+	cudaEvent_t ev_user[8] = {nullptr};
 	cudaEvent_t ev_packed[2] = {nullptr, nullptr}, ev_arrived[2] = {nullptr, nullptr};
 	bool pending[2] = {false, false};
 	// halo
@@ -335,6 +337,8 @@ int halo_spc(const lfmgpu_ctx* h, int step) {
 
 // buffer that holds the latest conservatives of cell range of submesh 0 (for packing)
 void* q_for_pack(lfmgpu_ctx* h) { return (h->updated_mask & 1u) ? h->q[1 - h->cur] : h->q[h->cur]; }
+// buffer that holds the conservatives the latest calc_VIS used (sigmaU of the packed payload is U.tau of THAT state)
+void* q_of_vis(lfmgpu_ctx* h) { return ((h->updated_mask & 1u) || h->vis_on_cur) ? h->q[h->cur] : h->q[1 - h->cur]; }
 
 template <class R, int D> int t_set_bc(lfmgpu_ctx* h) {
 	if (!h->n_bc) return 0;
@@ -360,6 +364,7 @@ void sub_range(const lfmgpu_ctx* h, int sub, int& c0, int& c1, int& f0, int& f1)
 template <class R, int D> int t_vis(lfmgpu_ctx* h, int sub) {
 	int c0, c1, f0, f1;
 	sub_range(h, sub, c0, c1, f0, f1);
+	h->vis_on_cur = true;
 	if (c1 <= c0) return 0;
 	if (h->use_tiles && h->tiles.ready) return tile_grad<R, D>(h, sub);
 	LAUNCH(h, "k_grad_cell", h->s_main, (k_grad_cell<R, D><<<blocks_for(c1 - c0), kBlock, 0, h->s_main>>>(h->mesh<R>(), (const R*)h->q[h->cur], c0, c1)));
@@ -406,6 +411,7 @@ template <class R, int D> int t_rk_stage(lfmgpu_ctx* h, int sub, int scheme, int
 		h->updated_mask = 0;
 		h->dq_zero = false;
 		h->stage_done = true;
+		h->vis_on_cur = false;
 	}
 	return 0;
 }
@@ -415,7 +421,7 @@ template <class R, int D> int t_pack(lfmgpu_ctx* h, int step, cudaStream_t s) {
 	const int mode = halo_mode(h, step);
 	h->last_send_count[step] = (size_t)ns * halo_spc(h, step);
 	if (!ns) return 0;
-	LAUNCH(h, "k_pack", s, (k_pack<R, D><<<blocks_for(ns), kBlock, 0, s>>>(h->mesh<R>(), (const R*)q_for_pack(h), h->d_send_cell, ns, mode, (R*)h->send_buf[step])));
+	LAUNCH(h, "k_pack", s, (k_pack<R, D><<<blocks_for(ns), kBlock, 0, s>>>(h->mesh<R>(), (const R*)q_for_pack(h), (const R*)q_of_vis(h), h->d_send_cell, ns, mode, (R*)h->send_buf[step])));
 	CHECK_LAUNCH();
 	return 0;
 }
@@ -690,6 +696,8 @@ int lfmgpu_destroy(lfmgpu_t h) {
 	}
 	for (void* p : h->allocs) cudaFree(p);
 	if (h->ev_ready) cudaEventDestroy(h->ev_ready);
+	for (int s = 0; s < 8; s++)
+		if (h->ev_user[s]) cudaEventDestroy(h->ev_user[s]);
 	for (int s = 0; s < 2; s++) {
 		if (h->ev_packed[s]) cudaEventDestroy(h->ev_packed[s]);
 		if (h->ev_arrived[s]) cudaEventDestroy(h->ev_arrived[s]);
@@ -840,7 +848,7 @@ int lfmgpu_download(lfmgpu_t h, int field, void* dst, size_t dst_bytes) {
 		// tauMC / sigmaU are not stored: rebuild them from q and dudx with the calc_VIS expressions on the host
 		std::vector<char> qh((size_t)NQ * n * es), gh((size_t)D * D * n * es);
 		// calc_VIS saw the conservatives of the stage it ran in: after a completed stage those are in the other buffer
-		const char* qsrc = (const char*)h->q[h->stage_done ? 1 - h->cur : h->cur];
+		const char* qsrc = (const char*)q_of_vis(h);
 		for (int i = 0; i < NQ; i++) CU(cudaMemcpy(qh.data() + (size_t)i * n * es, qsrc + (size_t)i * h->ncs * es, n * es, cudaMemcpyDeviceToHost));
 		for (int i = 0; i < D * D; i++) CU(cudaMemcpy(gh.data() + (size_t)i * n * es, dudx + (size_t)i * h->ncs * es, n * es, cudaMemcpyDeviceToHost));
 		auto run = [&](auto zero) {
@@ -1043,6 +1051,25 @@ int lfmgpu_kernel_time(lfmgpu_t h, const char* prefix, double* total_ms, uint64_
 	}
 	*total_ms = tot;
 	*launches = n;
+	return 0;
+}
+int lfmgpu_event_record(lfmgpu_t h, int slot) {
+	TRY(use(h));
+	if (slot < 0 || slot >= 8) return fail("event slot out of range");
+	if (!h->ev_user[slot]) CU(cudaEventCreate(&h->ev_user[slot]));
+	// the compute stream waits for the halo stream first so that the event closes everything enqueued so far
+	CU(cudaEventRecord(h->ev_ready, h->s_comm));
+	CU(cudaStreamWaitEvent(h->s_main, h->ev_ready, 0));
+	CU(cudaEventRecord(h->ev_user[slot], h->s_main));
+	return 0;
+}
+int lfmgpu_event_elapsed_ms(lfmgpu_t h, int slot_a, int slot_b, double* ms) {
+	TRY(use(h));
+	if (slot_a < 0 || slot_a >= 8 || slot_b < 0 || slot_b >= 8 || !h->ev_user[slot_a] || !h->ev_user[slot_b]) return fail("event slot not recorded");
+	CU(cudaEventSynchronize(h->ev_user[slot_b]));
+	float f = 0;
+	CU(cudaEventElapsedTime(&f, h->ev_user[slot_a], h->ev_user[slot_b]));
+	*ms = (double)f;
 	return 0;
 }
 int lfmgpu_tile_info(lfmgpu_t h, int* n_tiles, int* tile_cells, size_t* smem_bytes, double* halo_face_ratio) {

@@ -26,7 +26,7 @@ SYMBOLS = [
     "lfmgpu_set_option", "lfmgpu_download", "lfmgpu_upload_q", "lfmgpu_upload_q_soa_async", "lfmgpu_download_q_soa_async",
     "lfmgpu_host_alloc", "lfmgpu_host_free", "lfmgpu_nccl_unique_id", "lfmgpu_comm_init_nccl", "lfmgpu_comm_init_local",
     "lfmgpu_halo_send_count", "lfmgpu_download_send_buffer", "lfmgpu_launch_count", "lfmgpu_enable_kernel_timing",
-    "lfmgpu_kernel_time", "lfmgpu_tile_info",
+    "lfmgpu_kernel_time", "lfmgpu_tile_info", "lfmgpu_event_record", "lfmgpu_event_elapsed_ms",
 ]
 
 
@@ -53,6 +53,7 @@ def lib():
             "lfmgpu_halo_send_count": [vp, i, C.POINTER(sz)], "lfmgpu_download_send_buffer": [vp, i, vp, sz],
             "lfmgpu_launch_count": [vp, C.POINTER(C.c_uint64)], "lfmgpu_enable_kernel_timing": [vp, i],
             "lfmgpu_kernel_time": [vp, C.c_char_p, C.POINTER(d), C.POINTER(C.c_uint64)],
+            "lfmgpu_event_record": [vp, i], "lfmgpu_event_elapsed_ms": [vp, i, i, C.POINTER(d)],
             "lfmgpu_tile_info": [vp, C.POINTER(i), C.POINTER(i), C.POINTER(sz), C.POINTER(d)],
         }
         for name, args in sig.items():
@@ -221,6 +222,14 @@ class GpuSolver:
         n = C.c_uint64()
         _check(lib().lfmgpu_kernel_time(self.h, prefix.encode(), C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def event_record(self, slot):
+        _check(lib().lfmgpu_event_record(self.h, slot))
+
+    def event_elapsed_ms(self, a, b):
+        ms = C.c_double()
+        _check(lib().lfmgpu_event_elapsed_ms(self.h, a, b, C.byref(ms)))
+        return ms.value
 
     def tile_info(self):
         nt, tc, sm, hr = C.c_int(), C.c_int(), C.c_size_t(), C.c_double()

@@ -275,6 +275,83 @@ def tri_prism_box(nx, ny, lengths=(1.0, 1.0), shuffle_seed=None):
 # renumbering (RCM stop-gap for hpathRenumber; reference: examples/*/constant/renumberMeshDict)
 # ------------------------------------------------------------------------------------------------
 
+def hex_block(n, blocks=(1, 1, 1), rank=0, cell_size=None, z_cyclic=None):
+    """The processor mesh of ONE rank of a block-decomposed hex box, generated without ever building the global
+    mesh (weak-scaling runs: 16.8 M cells per rank).  n = (nx,ny,nz) cells of this block, blocks = (bx,by,bz),
+    rank = bi + bx*(bj + by*bk) as in block_assignment().  Physically identical to
+    decompose(hex_box(n*blocks), block_assignment)[rank] (same points, same cell order, same patches; the
+    processor-face ids are a different but consistent global numbering -- they only serve to match the two sides).
+    z is a cyclic pair when bz == 1 (default), walls otherwise."""
+    nx, ny, nz = n
+    bx, by, bz = blocks
+    bi, bj, bk = rank % bx, (rank // bx) % by, rank // (bx * by)
+    GX, GY, GZ = nx * bx, ny * by, nz * bz
+    if cell_size is None:
+        cell_size = (1.0 / GX, 1.0 / GX, 1.0 / GX)
+    if z_cyclic is None:
+        z_cyclic = bz == 1
+    assert not (z_cyclic and bz > 1)
+    L = (cell_size[0] * GX, cell_size[1] * GY, cell_size[2] * GZ)
+    faces, a, b, side, _ = _structured(nx, ny, nz)
+    xs = (L[0] * np.linspace(0.0, 1.0, GX + 1))[bi * nx:(bi + 1) * nx + 1]
+    ys = (L[1] * np.linspace(0.0, 1.0, GY + 1))[bj * ny:(bj + 1) * ny + 1]
+    zs = (L[2] * np.linspace(0.0, 1.0, GZ + 1))[bk * nz:(bk + 1) * nz + 1]
+    X, Y, Z = np.meshgrid(xs, ys, zs, indexing="ij")
+    points = np.stack([X.transpose(2, 1, 0).ravel(), Y.transpose(2, 1, 0).ravel(), Z.transpose(2, 1, 0).ravel()], axis=1)
+    patch_defs = [dict(name="inlet", type="patch"), dict(name="outlet", type="patch"), dict(name="walls", type="wall")]
+    phys = [0, 1, 2, 2, 2, 2]
+    if z_cyclic:
+        patch_defs.append(dict(name="periodic_m", type="cyclic", neighbourPatch="periodic_p"))
+        patch_defs.append(dict(name="periodic_p", type="cyclic", neighbourPatch="periodic_m"))
+        phys[4], phys[5] = 3, 4
+    # neighbour rank across each logical side (-1: domain boundary)
+    def rk(i, j, k):
+        return i + bx * (j + by * k)
+    nbr = [rk(bi - 1, bj, bk) if bi > 0 else -1, rk(bi + 1, bj, bk) if bi < bx - 1 else -1,
+           rk(bi, bj - 1, bk) if bj > 0 else -1, rk(bi, bj + 1, bk) if bj < by - 1 else -1,
+           rk(bi, bj, bk - 1) if bk > 0 else -1, rk(bi, bj, bk + 1) if bk < bz - 1 else -1]
+    proc_ranks = sorted(set(r for r in nbr if r >= 0))
+    n_phys = len(patch_defs)
+    for r in proc_ranks:
+        patch_defs.append(dict(name=f"procBoundary{rank}to{r}", type="processor", myProcNo=rank, neighbProcNo=r))
+    side_patch = [phys[s] if nbr[s] < 0 else n_phys + proc_ranks.index(nbr[s]) for s in range(6)]
+    # a global id for every boundary face of the block (unique per geometric face, the same on both ranks)
+    nf = len(side)
+    n_i, n_j = (nx + 1) * ny * nz, nx * (ny + 1) * nz
+    idx = np.arange(nf, dtype=np.int64)
+    gid = np.zeros(nf, dtype=np.int64)
+    # i-faces: local (i,j,k) from meshgrid(indexing="ij").ravel() -> i slowest
+    li = idx[:n_i]
+    i, j, k = li // (ny * nz), (li // nz) % ny, li % nz
+    gid[:n_i] = (bi * nx + i) + (GX + 1) * ((bj * ny + j) + GY * (bk * nz + k))
+    lj = idx[n_i:n_i + n_j] - n_i
+    i, j, k = lj // ((ny + 1) * nz), (lj // nz) % (ny + 1), lj % nz
+    gid[n_i:n_i + n_j] = (GX + 1) * GY * GZ + (bi * nx + i) + GX * ((bj * ny + j) + (GY + 1) * (bk * nz + k))
+    lk = idx[n_i + n_j:] - n_i - n_j
+    i, j, k = lk // (ny * (nz + 1)), (lk // (nz + 1)) % ny, lk % (nz + 1)
+    gid[n_i + n_j:] = (GX + 1) * GY * GZ + GX * (GY + 1) * GZ + (bi * nx + i) + GX * ((bj * ny + j) + GY * (bk * nz + k))
+    patch_id = np.full(nf, -1, dtype=np.int64)
+    for s in range(6):
+        patch_id[side == s] = side_patch[s]
+    # cyclic twins must share the same offset inside their patches: order the two z planes by (i,j) == gid within a plane
+    m = assemble(points, faces, a, b, patch_id, patch_defs, nx * ny * nz, cyclic_keys=gid)
+    # recover the id of each assembled face (assemble sorts; redo its ordering on gid)
+    internal = b >= 0
+    own = np.where(internal, np.minimum(a, b), a)
+    nei = np.where(internal, np.maximum(a, b), -1)
+    idx_int = np.nonzero(internal)[0]
+    order_int = idx_int[np.lexsort((nei[idx_int], own[idx_int]))]
+    idx_bnd = np.nonzero(~internal)[0]
+    order_bnd = idx_bnd[np.lexsort((gid[idx_bnd], patch_id[idx_bnd]))]
+    order = np.concatenate([order_int, order_bnd])
+    m["faceProcAddressing"] = (gid[order] + 1).astype(np.int64)
+    assert m["faceProcAddressing"].max() < 2 ** 31
+    m["faceProcAddressing"] = m["faceProcAddressing"].astype(np.int32)
+    m["logical"] = (nx, ny, nz)
+    m["block"] = (bi, bj, bk)
+    return m
+
+
 def renumber_cells(m, new_of_old):
     """Applies a cell permutation and restores canonical (upper-triangular) face order."""
     new_of_old = np.asarray(new_of_old, dtype=np.int64)
