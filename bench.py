@@ -78,9 +78,15 @@ def block_fields(m, n, blocks, rank):
     return dict(p=p, T=T, U=U, alpha=alpha), h
 
 
-def build_rank_case(n, blocks, rank, n_ranks, precision, scheme):
-    m = meshgen.hex_block((n, n, n), blocks, rank)
+def build_rank_case(n, blocks, rank, n_ranks, precision, scheme, tile=None):
+    m = meshgen.hex_block((n, n, n), blocks, rank, tile=tile)
     fields, h = block_fields(m, (n, n, n), blocks, rank)
+    if "new_of_old" in m:                                  # fields were built in lexicographic order: renumber them too
+        perm = m["new_of_old"]
+        for k, v in fields.items():
+            out = np.empty_like(v)
+            out[perm] = v
+            fields[k] = out
     dt = 0.5 * h / 1.2                                     # acoustic CFL ~ 0.5 (c = 1, |U| = 0.2)
     o = host_api.default_opts(solver=scheme, dimension=3, delta_t=dt, Ls=0.15, mu0=MU, mach=0.2, comm_type=2,
                               double_precision=1 if precision == 8 else 0)
@@ -219,7 +225,7 @@ def workload_config(args, n_gpus):
     bl = BLOCKS[n_gpus]
     return {"workload": f"synthetic 3D hex polyMesh weak scaling, {n}^3 = {n ** 3} cells per GPU, blocks {bl[0]}x{bl[1]}x{bl[2]} "
                         f"({n ** 3 * n_gpus} cells), {'M2' if args.scheme == 1 else 'M1'} + laminar viscous + sponge, RK5, commType 2",
-            "cells_per_gpu": n ** 3, "total_cells": n ** 3 * n_gpus, "rk_stages_per_step": 5,
+            "cell_numbering": f"bricks {args.tile}", "cells_per_gpu": n ** 3, "total_cells": n ** 3 * n_gpus, "rk_stages_per_step": 5,
             "l2_policy": "inputs larger than L2 (about 7 GB of state per GPU at 256^3), no flush"}
 
 
@@ -245,7 +251,8 @@ def run_gpu_arm(args):
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
     blocks = BLOCKS[world]
     t0 = time.time()
-    case, dt = build_rank_case(args.n, blocks, rank, world, args.precision, args.scheme)
+    tile = tuple(int(x) for x in args.tile.split(",")) if args.tile and args.tile != "none" else None
+    case, dt = build_rank_case(args.n, blocks, rank, world, args.precision, args.scheme, tile)
     if world > 1:
         host_api.exchange_distributed(case, rank)
     else:
@@ -387,6 +394,7 @@ def main():
     ap.add_argument("--precision", type=int, default=8, choices=[4, 8])
     ap.add_argument("--scheme", type=int, default=1, choices=[0, 1], help="0 = M1, 1 = M2")
     ap.add_argument("--use-tiles", type=int, default=1)
+    ap.add_argument("--tile", default="8,4,4", help="brick numbering of the synthetic mesh (renumberMesh analogue), or 'none'")
     ap.add_argument("--ref-n", type=int, default=64, help="cells per side of the CPU sample")
     ap.add_argument("--ref-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")

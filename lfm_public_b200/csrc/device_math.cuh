@@ -39,13 +39,21 @@ template <class R> struct Consts {
 	R rhoUInf[3], rhoEInf;                           // rhoInf*UInf[i], rhoInf*EInf (sponge targets)
 };
 
-// What one side of a face needs.  `U` is rhoU*rho_inv (flux loops), `Ud` is rhoU/rho (calc_VIS block);
-// the reference uses both forms and they differ in the last bit.
+// What one side of a face needs (the record the tile kernels stage in shared memory).
+//   aux: M1 -> sqrt(gamma*Rpsi) (speed of sound), M2 -> rhoE/rho + Rpsi (total enthalpy): the per-cell
+//   square root / true division of the flux loops, evaluated once per staged cell.
+//   sigmaU: U.tau of calc_VIS (uses rhoU/rho, a true division, unlike the flux loops' rhoU*rho_inv).
+// tauMC is a cheap function of dudx and is rebuilt per face side instead of being stored.
 template <class R, int D> struct CellState {
 	R q[D + 2];
-	R rho_inv, Rpsi, T;
-	R U[D];
-	R dudx[D][D], dTdx[D], tauMC[D][D], sigmaU[D];
+	R rho_inv, Rpsi, aux;
+	R dudx[D][D], dTdx[D], sigmaU[D];
+};
+
+// Per-face geometry that does not change in time, derived once from (S, d) with the expressions of the
+// viscous block (cfd_v0.cpp:2681-2690, 2747-2760): S_mag, 1/|d|, the non-orthogonal split K = S - delta and |delta|.
+template <class R, int D> struct FaceGeo {
+	R S[D], w, K[D], delta_mag, dmag_inv, S_mag;
 };
 
 template <class R, int D> __device__ __forceinline__ void primitives(const Consts<R>& k, const R* q, R& rho_inv, R* U, R& Rpsi, R& T) {
@@ -105,11 +113,46 @@ template <class R, int D> __device__ __forceinline__ void grad_face_values(const
 	face_T = interp<R>(w, Rpsi_o, Rpsi_n) * k.Rgas_inv;
 }
 
+template <class R, int D> __device__ __forceinline__ void make_geo(const R* S, const R* dv, R w, FaceGeo<R, D>& g) {
+	const R ONE = R(1.0), ZERO = R(0.0);
+	R S_mag = ZERO;
+#pragma unroll
+	for (int i = 0; i < D; i++) S_mag += S[i] * S[i];
+	S_mag = LFM_SQRT(S_mag);
+	R d_mag = dv[0] * dv[0];
+#pragma unroll
+	for (int i = 1; i < D; i++) d_mag += dv[i] * dv[i];
+	d_mag = LFM_SQRT(d_mag);
+	g.dmag_inv = ONE / d_mag;
+	const R Sd = dotD<R, D>(S, dv);
+	R delta_mag = ZERO;
+#pragma unroll
+	for (int i = 0; i < D; i++) {
+		const R delta = dv[i] * S_mag * S_mag / Sd;
+		delta_mag += delta * delta;
+		g.K[i] = S[i] - delta;
+		g.S[i] = S[i];
+	}
+	g.delta_mag = LFM_SQRT(delta_mag);
+	g.S_mag = S_mag;
+	g.w = w;
+}
+
 // One face of one_rk_step_M1 / _M2: rhs[D+2] seen from the owner (c = owner, n = neighbour).
-// ghost: the neighbour is a physical-boundary ghost (is_ghost) -> one-sided gradients.
-template <class R, int D, int SCHEME> __device__ __forceinline__ void face_flux(const Consts<R>& k, const CellState<R, D>& c, const CellState<R, D>& n, const R* S, const R* dv, R weight, bool ghost, R* rhs) {
+// ghost: the neighbour is a physical-boundary ghost (is_ghost) -> one-sided gradients; dv (the owner->ghost
+// vector) is only read in that case.
+template <class R, int D, int SCHEME> __device__ __forceinline__ void face_flux(const Consts<R>& k, const CellState<R, D>& c, const CellState<R, D>& n, const FaceGeo<R, D>& g, bool ghost, const R* dv, R* rhs) {
 	const R ONE = R(1.0), HALF = R(0.5), ZERO = R(0.0);
-	R S_mag;
+	const R weight = g.w;
+	const R* S = g.S;
+	const R S_mag = g.S_mag;
+	R cU[D], nU[D];
+#pragma unroll
+	for (int i = 0; i < D; i++) {
+		cU[i] = c.q[i + 1] * c.rho_inv;
+		nU[i] = n.q[i + 1] * n.rho_inv;
+	}
+	const R cT = c.Rpsi * k.Rgas_inv, nT = n.Rpsi * k.Rgas_inv;
 	if (SCHEME == 0) {
 		const R omw = ONE - weight;
 		const R rhoPos = interp<R>(weight, c.q[0], n.q[0]);
@@ -126,8 +169,8 @@ template <class R, int D, int SCHEME> __device__ __forceinline__ void face_flux(
 		R adjc_e = R(2) * n.q[D + 1] * n.rho_inv;
 #pragma unroll
 		for (int nD = 0; nD < D; nD++) {
-			cell_e -= c.U[nD] * c.U[nD];
-			adjc_e -= n.U[nD] * n.U[nD];
+			cell_e -= cU[nD] * cU[nD];
+			adjc_e -= nU[nD] * nU[nD];
 		}
 		cell_e *= HALF;
 		adjc_e *= HALF;
@@ -137,10 +180,8 @@ template <class R, int D, int SCHEME> __device__ __forceinline__ void face_flux(
 		const R RpsiNeg = interp<R>(omw, n.Rpsi, c.Rpsi);
 		const R pPos = rhoPos * RpsiPos;
 		const R pNeg = rhoNeg * RpsiNeg;
-		const R cP = LFM_SQRT(k.gamma * c.Rpsi);
-		const R cN = LFM_SQRT(k.gamma * n.Rpsi);
-		const R cPos = interp<R>(weight, cP, cN);
-		const R cNeg = interp<R>(omw, cN, cP);
+		const R cPos = interp<R>(weight, c.aux, n.aux);
+		const R cNeg = interp<R>(omw, n.aux, c.aux);
 		R phiPos = ZERO, phiNeg = ZERO;
 		R uPos[D], uNeg[D];
 #pragma unroll
@@ -150,10 +191,6 @@ template <class R, int D, int SCHEME> __device__ __forceinline__ void face_flux(
 			phiPos += uPos[i] * S[i];
 			phiNeg += -uNeg[i] * S[i];
 		}
-		S_mag = ZERO;
-#pragma unroll
-		for (int i = 0; i < D; i++) S_mag += S[i] * S[i];
-		S_mag = LFM_SQRT(S_mag);
 		R psiPos = phiPos + cPos * S_mag;
 		{
 			const R b = -phiNeg + cNeg * S_mag;
@@ -193,19 +230,13 @@ template <class R, int D, int SCHEME> __device__ __forceinline__ void face_flux(
 		for (int i = 0; i < D; i++) rhoUavg[i] = HALF * (c.q[i + 1] + n.q[i + 1]);
 		const R Rpsiavg = HALF * (c.Rpsi + n.Rpsi);
 		const R pavg = rhoavg * Rpsiavg;
-		const R cell_H = c.q[D + 1] / c.q[0] + c.Rpsi;
-		const R adjc_H = n.q[D + 1] / n.q[0] + n.Rpsi;
-		const R Havg = HALF * (cell_H + adjc_H);
+		const R Havg = HALF * (c.aux + n.aux);
 		R phiavg = ZERO;
 #pragma unroll
 		for (int i = 0; i < D; i++) {
 			const R uavg = rhoUavg[i] * rhoavg_inv;
 			phiavg += uavg * S[i];
 		}
-		S_mag = ZERO;
-#pragma unroll
-		for (int i = 0; i < D; i++) S_mag += S[i] * S[i];
-		S_mag = LFM_SQRT(S_mag);
 		rhs[0] = -rhoavg * phiavg;
 #pragma unroll
 		for (int i = 0; i < D; i++) rhs[i + 1] = -(rhoUavg[i] * phiavg + pavg * S[i]);
@@ -213,61 +244,66 @@ template <class R, int D, int SCHEME> __device__ __forceinline__ void face_flux(
 	}
 
 	// ---- viscosity ----
-	R d_mag = dv[0] * dv[0];
-#pragma unroll
-	for (int i = 1; i < D; i++) d_mag += dv[i] * dv[i];
-	d_mag = LFM_SQRT(d_mag);
-	const R dmag_inv = ONE / d_mag;
-	R d_norm[D];
-#pragma unroll
-	for (int i = 0; i < D; i++) d_norm[i] = dv[i] * dmag_inv;
+	const R dmag_inv = g.dmag_inv;
 	R dudx[D][D], dTdx[D], tauMC[D][D], sigmaU[D];
 	if (!ghost) {
+		R ctau[D][D], ntau[D][D];
+		tauMC_from<R, D>(k, c.dudx, ctau);
+		tauMC_from<R, D>(k, n.dudx, ntau);
 #pragma unroll
 		for (int i = 0; i < D; i++) {
 #pragma unroll
 			for (int j = 0; j < D; j++) {
 				dudx[i][j] = interp<R>(weight, c.dudx[i][j], n.dudx[i][j]);
-				tauMC[i][j] = interp<R>(weight, c.tauMC[i][j], n.tauMC[i][j]);
+				tauMC[i][j] = interp<R>(weight, ctau[i][j], ntau[i][j]);
 			}
 			dTdx[i] = interp<R>(weight, c.dTdx[i], n.dTdx[i]);
 			sigmaU[i] = interp<R>(weight, c.sigmaU[i], n.sigmaU[i]);
 		}
 	} else {
+		R d_norm[D];
+#pragma unroll
+		for (int i = 0; i < D; i++) d_norm[i] = dv[i] * dmag_inv;
 #pragma unroll
 		for (int i = 0; i < D; i++) {
 #pragma unroll
-			for (int j = 0; j < D; j++) dudx[i][j] = (n.U[i] - c.U[i]) * d_norm[j] * dmag_inv;
-			dTdx[i] = (n.T - c.T) * d_norm[i] * dmag_inv;
+			for (int j = 0; j < D; j++) dudx[i][j] = (nU[i] - cU[i]) * d_norm[j] * dmag_inv;
+			dTdx[i] = (nT - cT) * d_norm[i] * dmag_inv;
 		}
 		R tau[D][D], U_f[D];
 		stress<R, D>(k, dudx, tau);
 		tauMC_from<R, D>(k, dudx, tauMC);
 #pragma unroll
-		for (int i = 0; i < D; i++) U_f[i] = interp<R>(weight, c.U[i], n.U[i]);
+		for (int i = 0; i < D; i++) U_f[i] = interp<R>(weight, cU[i], nU[i]);
 #pragma unroll
 		for (int i = 0; i < D; i++) sigmaU[i] = dotD<R, D>(U_f, tau[i]);
 	}
 	R divTauMC[D];
 #pragma unroll
 	for (int i = 0; i < D; i++) divTauMC[i] = dotD<R, D>(tauMC[i], S);
-	const R Sd = dotD<R, D>(S, dv);
-	R delta_mag = ZERO, K[D];
 #pragma unroll
 	for (int i = 0; i < D; i++) {
-		const R delta = dv[i] * S_mag * S_mag / Sd;
-		delta_mag += delta * delta;
-		K[i] = S[i] - delta;
-	}
-	delta_mag = LFM_SQRT(delta_mag);
-#pragma unroll
-	for (int i = 0; i < D; i++) {
-		const R lapU = k.mu * (delta_mag * (n.U[i] - c.U[i]) * dmag_inv + dotD<R, D>(K, dudx[i]));
+		const R lapU = k.mu * (g.delta_mag * (nU[i] - cU[i]) * dmag_inv + dotD<R, D>(g.K, dudx[i]));
 		rhs[i + 1] += divTauMC[i] + lapU;
 	}
-	const R lapT = k.kappa * (delta_mag * (n.T - c.T) * dmag_inv + dotD<R, D>(K, dTdx));
+	const R lapT = k.kappa * (g.delta_mag * (nT - cT) * dmag_inv + dotD<R, D>(g.K, dTdx));
 	const R divSigmaU = dotD<R, D>(sigmaU, S);
 	rhs[D + 1] += divSigmaU + lapT;
+}
+
+// Fills the derived members of a CellState whose q (and, for real cells, dudx) are already loaded.
+// real: a cell of this rank (sigmaU from calc_VIS's block); otherwise sigmaU must be supplied by the caller.
+template <class R, int D, int SCHEME> __device__ __forceinline__ void derive_state(const Consts<R>& k, CellState<R, D>& s, bool real) {
+	R U[D], T;
+	primitives<R, D>(k, s.q, s.rho_inv, U, s.Rpsi, T);
+	if (SCHEME == 0)
+		s.aux = LFM_SQRT(k.gamma * s.Rpsi);
+	else
+		s.aux = s.q[D + 1] / s.q[0] + s.Rpsi;
+	if (real) {
+		R tauMC[D][D];
+		vis_cell_terms<R, D>(k, s.q, s.dudx, tauMC, s.sigmaU);
+	}
 }
 
 }  // namespace lfm

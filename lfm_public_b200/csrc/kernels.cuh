@@ -154,18 +154,18 @@ template <class R, int D> __global__ void __launch_bounds__(kBlock) k_grad_cell(
 }
 
 // Loads everything face_flux needs about cell x (real cell, physical ghost or MPI ghost).
-template <class R, int D> __device__ __forceinline__ void load_state(const DevMesh<R>& m, const R* __restrict__ q, int x, CellState<R, D>& s) {
+template <class R, int D, int SCHEME> __device__ __forceinline__ void load_state(const DevMesh<R>& m, const R* __restrict__ q, int x, CellState<R, D>& s) {
 #pragma unroll
 	for (int i = 0; i < D + 2; i++) s.q[i] = q[i * m.ncs + x];
-	primitives<R, D>(m.k, s.q, s.rho_inv, s.U, s.Rpsi, s.T);
 	const bool bc_ghost = x >= m.n_cells && x < m.n_cells + m.n_bc;
 	if (bc_ghost) {
 #pragma unroll
 		for (int i = 0; i < D; i++) {
 			s.dTdx[i] = s.sigmaU[i] = R(0);
 #pragma unroll
-			for (int j = 0; j < D; j++) s.dudx[i][j] = s.tauMC[i][j] = R(0);
+			for (int j = 0; j < D; j++) s.dudx[i][j] = R(0);
 		}
+		derive_state<R, D, SCHEME>(m.k, s, false);
 		return;
 	}
 #pragma unroll
@@ -174,17 +174,12 @@ template <class R, int D> __device__ __forceinline__ void load_state(const DevMe
 		for (int j = 0; j < D; j++) s.dudx[i][j] = m.dudx[(size_t)(i * D + j) * m.ncs + x];
 		s.dTdx[i] = m.dTdx[(size_t)i * m.ncs + x];
 	}
-	if (x < m.n_cells) {
-		vis_cell_terms<R, D>(m.k, s.q, s.dudx, s.tauMC, s.sigmaU);
-	} else {
+	if (x >= m.n_cells) {
 		const int g = x - m.n_cells - m.n_bc;
 #pragma unroll
-		for (int i = 0; i < D; i++) {
-#pragma unroll
-			for (int j = 0; j < D; j++) s.tauMC[i][j] = m.g_tauMC[(size_t)(i * D + j) * m.ngs + g];
-			s.sigmaU[i] = m.g_sigmaU[(size_t)i * m.ngs + g];
-		}
+		for (int i = 0; i < D; i++) s.sigmaU[i] = m.g_sigmaU[(size_t)i * m.ngs + g];
 	}
+	derive_state<R, D, SCHEME>(m.k, s, x < m.n_cells);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -195,16 +190,18 @@ template <class R, int D, int SCHEME> __global__ void __launch_bounds__(kBlock) 
 	if (f >= f1) return;
 	const int o = m.face_owner[f], n = m.face_neigh[f];
 	CellState<R, D> c, a;
-	load_state<R, D>(m, q, o, c);
-	load_state<R, D>(m, q, n, a);
+	load_state<R, D, SCHEME>(m, q, o, c);
+	load_state<R, D, SCHEME>(m, q, n, a);
 	R S[D], dv[D], rhs[D + 2];
 #pragma unroll
 	for (int i = 0; i < D; i++) {
 		S[i] = m.S[i * m.nfs + f];
 		dv[i] = m.d[i * m.nfs + f];
 	}
+	FaceGeo<R, D> g;
+	make_geo<R, D>(S, dv, m.w[f], g);
 	const bool ghost = n >= m.n_cells && n < m.n_cells + m.n_bc;
-	face_flux<R, D, SCHEME>(m.k, c, a, S, dv, m.w[f], ghost, rhs);
+	face_flux<R, D, SCHEME>(m.k, c, a, g, ghost, dv, rhs);
 #pragma unroll
 	for (int i = 0; i < D + 2; i++) m.flux[i * m.nfs + f] = rhs[i];
 }
@@ -471,7 +468,7 @@ __global__ void __launch_bounds__(kBlock) k_res_final(const double* __restrict__
 // postProcForces (cfd_v0.cpp:3173-3240): per wall face contributions, then a sequential sum in the
 // reference's face order (bit-exact with the CPU loop)
 // ---------------------------------------------------------------------------------------------------
-template <class R, int D> __global__ void __launch_bounds__(kBlock) k_forces_face(DevMesh<R> m, const R* __restrict__ q, int patch, R* __restrict__ contrib /*[n_bc][2*D]*/, int* __restrict__ used) {
+template <class R, int D> __global__ void __launch_bounds__(kBlock) k_forces_face(DevMesh<R> m, const R* __restrict__ q, const R* __restrict__ qghost, int patch, R* __restrict__ contrib /*[n_bc][2*D]*/, int* __restrict__ used) {
 	const int g = blockIdx.x * blockDim.x + threadIdx.x;
 	if (g >= m.n_bc) return;
 	if (m.bc_patch[g] != patch) {
@@ -490,7 +487,7 @@ template <class R, int D> __global__ void __launch_bounds__(kBlock) k_forces_fac
 #pragma unroll
 	for (int i = 0; i < D + 2; i++) {
 		cq[i] = q[i * m.ncs + t];
-		nq[i] = q[i * m.ncs + n];
+		nq[i] = qghost[i * m.ncs + n];
 	}
 	const R r = cq[0], rE = cq[D + 1];
 	R Umag = R(0);

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -138,6 +139,8 @@ struct lfmgpu_ctx {
 	// tiles (fused path)
 	TilePlan tiles;
 	int use_tiles = 1;
+	int tile_cells = 128;              // cells per tile requested (halved until the plan fits the budget)
+	int tile_smem_budget = 75 * 1024;  // bytes of shared memory one tile CTA may use
 	// introspection
 	uint64_t launches = 0;
 	bool timing = false;
@@ -456,7 +459,7 @@ template <class R, int D> int t_average(lfmgpu_ctx* h, int time_step) {
 template <class R, int D> int t_forces(lfmgpu_ctx* h, int patch, double* Fpre, double* Fvis) {
 	for (int i = 0; i < D; i++) Fpre[i] = Fvis[i] = 0.0;
 	if (!h->n_bc) return 0;
-	LAUNCH(h, "k_forces_face", h->s_main, (k_forces_face<R, D><<<blocks_for(h->n_bc), kBlock, 0, h->s_main>>>(h->mesh<R>(), (const R*)h->q[h->cur], patch, (R*)h->d_force_contrib, h->d_force_used)));
+	LAUNCH(h, "k_forces_face", h->s_main, (k_forces_face<R, D><<<blocks_for(h->n_bc), kBlock, 0, h->s_main>>>(h->mesh<R>(), (const R*)h->q[h->cur], (const R*)h->q[h->stage_done ? 1 - h->cur : h->cur], patch, (R*)h->d_force_contrib, h->d_force_used)));
 	LAUNCH(h, "k_forces_sum", h->s_main, (k_forces_sum<R, D><<<1, 32, 0, h->s_main>>>(h->n_bc, (const R*)h->d_force_contrib, h->d_force_used, (R*)h->d_force_out)));
 	CHECK_LAUNCH();
 	R out[6];
@@ -469,9 +472,265 @@ template <class R, int D> int t_forces(lfmgpu_ctx* h, int patch, double* Fpre, d
 	return 0;
 }
 
-int tile_plan_build(lfmgpu_ctx*, const lfmgpu_desc*) { return 0; }
-template <class R, int D> int tile_grad(lfmgpu_ctx*, int) { return fail("tiled path not built"); }
-template <class R, int D> int tile_stage(lfmgpu_ctx*, int, int, R, R, R, int, int) { return fail("tiled path not built"); }
+// ---- fused tile path: plan (host) + launchers --------------------------------------------------------
+template <class R> TileView<R> tile_view(lfmgpu_ctx* h, int smax, int fmax) {
+	TilePlan& p = h->tiles;
+	TileView<R> v;
+	v.tiles = p.d_tiles;
+	v.halo_cell = p.d_halo_cell;
+	v.inc_face = p.d_inc_face;
+	v.inc_lowner = p.d_inc_lowner;
+	v.face_lneigh = p.d_face_lneigh;
+	v.csr_local = p.d_csr_local;
+	v.gK = (const R*)p.d_gK;
+	v.g_delta_mag = (const R*)p.d_delta_mag;
+	v.g_dmag_inv = (const R*)p.d_dmag_inv;
+	v.g_Smag = (const R*)p.d_Smag;
+	v.smax = smax;
+	v.fmax = fmax;
+	return v;
+}
+
+void tile_range(const lfmgpu_ctx* h, int sub, int& t0, int& t1, int& smax, int& fmax) {
+	const TilePlan& p = h->tiles;
+	if (sub < 0) {
+		t0 = 0;
+		t1 = p.n_tiles;
+		smax = fmax = 0;
+		for (int s = 0; s < h->n_sub; s++) {
+			smax = std::max(smax, p.sub_smax[s]);
+			fmax = std::max(fmax, p.sub_fmax[s]);
+		}
+	} else {
+		t0 = p.sub_tile_start[sub];
+		t1 = p.sub_tile_start[sub + 1];
+		smax = p.sub_smax[sub];
+		fmax = p.sub_fmax[sub];
+	}
+}
+
+constexpr int kTileThreads = 128;
+
+template <class R, int D> size_t stage_smem(int smax, int fmax) { return ((size_t)StagedLayout<D>::NS * smax + (size_t)(D + 2) * fmax) * sizeof(R); }
+template <class R, int D> size_t grad_smem(int smax) { return (size_t)(D + 1) * smax * sizeof(R); }
+
+template <class R, int D> int tile_grad(lfmgpu_ctx* h, int sub) {
+	int t0, t1, smax, fmax;
+	tile_range(h, sub, t0, t1, smax, fmax);
+	if (t1 <= t0) return 0;
+	const size_t smem = grad_smem<R, D>(smax);
+	auto kern = k_tile_grad<R, D, kTileThreads>;
+	if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	LAUNCH(h, "tile_grad", h->s_main, (kern<<<t1 - t0, kTileThreads, smem, h->s_main>>>(h->mesh<R>(), tile_view<R>(h, smax, fmax), (const R*)h->q[h->cur], t0)));
+	CHECK_LAUNCH();
+	return 0;
+}
+
+template <class R, int D, int SCHEME> int tile_stage_s(lfmgpu_ctx* h, int sub, R dt, R Ak, R Bk, int first, int res) {
+	int t0, t1, smax, fmax;
+	tile_range(h, sub, t0, t1, smax, fmax);
+	if (t1 <= t0) return 0;
+	const size_t smem = stage_smem<R, D>(smax, fmax);
+	auto kern = k_tile_stage<R, D, SCHEME, kTileThreads>;
+	if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	LAUNCH(h, "tile_stage", h->s_main,
+	       (kern<<<t1 - t0, kTileThreads, smem, h->s_main>>>(h->mesh<R>(), tile_view<R>(h, smax, fmax), (const R*)h->q[h->cur], (R*)h->q[1 - h->cur], t0, dt, Ak, Bk, first, res)));
+	CHECK_LAUNCH();
+	return 0;
+}
+template <class R, int D> int tile_stage(lfmgpu_ctx* h, int sub, int scheme, R dt, R Ak, R Bk, int first, int res) {
+	return scheme == LFMGPU_SCHEME_M1 ? tile_stage_s<R, D, 0>(h, sub, dt, Ak, Bk, first, res) : tile_stage_s<R, D, 1>(h, sub, dt, Ak, Bk, first, res);
+}
+
+template <class R, int D> int tile_geo(lfmgpu_ctx* h) {
+	TilePlan& p = h->tiles;
+	TRY(dev_alloc(h, &p.d_gK, (size_t)D * h->nfs * sizeof(R)));
+	TRY(dev_alloc(h, &p.d_delta_mag, h->nfs * sizeof(R)));
+	TRY(dev_alloc(h, &p.d_dmag_inv, h->nfs * sizeof(R)));
+	TRY(dev_alloc(h, &p.d_Smag, h->nfs * sizeof(R)));
+	if (h->n_faces) {
+		k_face_geo<R, D><<<blocks_for(h->n_faces), kBlock>>>(h->mesh<R>(), (R*)p.d_gK, (R*)p.d_delta_mag, (R*)p.d_dmag_inv, (R*)p.d_Smag);
+		CHECK_LAUNCH();
+	}
+	return 0;
+}
+
+// Cuts every submesh into runs of `tile_cells` consecutive cells and derives, per tile, the halo cells, the
+// incoming faces and the tile-local indices the kernels use.  Returns 0 with plan.ready == false when the mesh
+// does not fit the shared-memory budget even with the smallest tile (the unfused kernels serve it then).
+int tile_plan_build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
+	TilePlan& p = h->tiles;
+	p.ready = false;
+	const int nc = h->n_cells, nf = h->n_faces, F = h->F, D = h->D;
+	if (nc == 0) return 0;
+	int dev_smem = 0;
+	CU(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+	const size_t budget = std::min<size_t>((size_t)dev_smem, (size_t)h->tile_smem_budget);
+	const size_t es = (size_t)h->prec;
+	const int NS = (D == 3 ? StagedLayout<3>::NS : StagedLayout<2>::NS), NQ = h->NQ;
+
+	// sorted signed cell->face lists (same order the device csr uses)
+	std::vector<int> csr((size_t)nc * F, 0);
+	for (int c = 0; c < nc; c++) {
+		int n = 0;
+		int* row = &csr[(size_t)c * F];
+		for (int s = 0; s < F; s++) {
+			const int e = ds->cell_slot_face[(size_t)c * F + s];
+			if (e) row[n++] = e;
+		}
+		std::sort(row, row + n, [](int a, int b) { return std::abs(a) < std::abs(b); });
+	}
+	std::vector<int> cfs((size_t)nc + 1, 0);   // first own face of each cell
+	for (int f = 0; f < nf; f++) cfs[(size_t)ds->face_owner[f] + 1]++;
+	for (int c = 0; c < nc; c++) cfs[(size_t)c + 1] += cfs[(size_t)c];
+
+	std::vector<TileDesc> tiles;
+	std::vector<int> halo_cell, inc_face;
+	std::vector<uint16_t> inc_lowner, face_lneigh;
+	std::vector<int16_t> csr_local;
+	std::vector<int> stamp((size_t)h->n_tot, -1), local_of((size_t)h->n_tot, 0);
+	int TC = h->tile_cells;
+	int probe_id = -1;
+	for (;;) {
+		tiles.clear();
+		halo_cell.clear();
+		inc_face.clear();
+		inc_lowner.clear();
+		face_lneigh.assign((size_t)nf, 0);
+		csr_local.assign((size_t)F * nc, 0);
+		std::fill(stamp.begin(), stamp.end(), -1);
+		bool ok = true;
+		long long tot_own = 0, tot_inc = 0, tot_halo = 0;
+		for (int s = 0; s < h->n_sub && ok; s++) {
+			p.sub_tile_start[s] = (int)tiles.size();
+			int smax = 0, fmax = 0;
+			for (int c0 = h->sub_cell_start[s], c1 = 0; c0 < h->sub_cell_start[s + 1]; c0 = c1) {
+				const int cmax = std::min(c0 + TC, h->sub_cell_start[s + 1]);
+				// Choose the cut: grow the run cell by cell, tracking the halo size incrementally, and close the tile
+				// where halo/tile is smallest inside the window [0.55 TC, TC] (ties: the longer run).  For block- or
+				// space-filling-curve-numbered meshes this snaps tiles to the compact runs of the numbering.
+				{
+					const int probe = --probe_id;   // negative stamps: never collide with tile ids
+					int nh = 0;
+					double best = 1e300;
+					c1 = cmax;
+					const int cmin = std::min(cmax, c0 + std::max(1, (TC * 11) / 20));
+					for (int c = c0; c < cmax; c++) {
+						if (stamp[(size_t)c] == probe) nh--;
+						const int* row = &csr[(size_t)c * F];
+						for (int k = 0; k < F && row[k]; k++) {
+							const int e = row[k], f = std::abs(e) - 1;
+							const int other = e > 0 ? ds->face_neigh[f] : ds->face_owner[f];
+							if (other >= c0 && other <= c) continue;
+							if (stamp[(size_t)other] != probe) {
+								stamp[(size_t)other] = probe;
+								nh++;
+							}
+						}
+						if (c + 1 >= cmin) {
+							const double ratio = (double)nh / (double)(c + 1 - c0);
+							if (ratio <= best) {
+								best = ratio;
+								c1 = c + 1;
+							}
+						}
+					}
+				}
+				const int tid = (int)tiles.size();
+				TileDesc td;
+				td.c0 = c0;
+				td.nt = c1 - c0;
+				td.fo0 = cfs[(size_t)c0];
+				td.nfo = cfs[(size_t)c1] - cfs[(size_t)c0];
+				td.halo_off = (int)halo_cell.size();
+				td.inc_off = (int)inc_face.size();
+				// halo cells and incoming faces
+				for (int c = c0; c < c1; c++) {
+					const int* row = &csr[(size_t)c * F];
+					for (int k = 0; k < F && row[k]; k++) {
+						const int e = row[k], f = std::abs(e) - 1;
+						const int other = e > 0 ? ds->face_neigh[f] : ds->face_owner[f];
+						if (other >= c0 && other < c1) continue;
+						if (stamp[(size_t)other] != tid) {
+							stamp[(size_t)other] = tid;
+							halo_cell.push_back(other);
+						}
+						if (e < 0) inc_face.push_back(f);
+					}
+				}
+				std::sort(halo_cell.begin() + td.halo_off, halo_cell.end());
+				std::sort(inc_face.begin() + td.inc_off, inc_face.end());
+				td.nh = (int)halo_cell.size() - td.halo_off;
+				td.ninc = (int)inc_face.size() - td.inc_off;
+				for (int i = 0; i < td.nh; i++) local_of[(size_t)halo_cell[(size_t)td.halo_off + i]] = td.nt + i;
+				if (td.nt + td.nh >= 32768 || td.nfo + td.ninc >= 32767) {
+					ok = false;
+					break;
+				}
+				// tile-local indices
+				for (int f = td.fo0; f < td.fo0 + td.nfo; f++) {
+					const int n = ds->face_neigh[f];
+					const int ln = (n >= c0 && n < c1) ? n - c0 : local_of[(size_t)n];
+					const bool ghost = n >= nc && n < nc + h->n_bc;
+					face_lneigh[(size_t)f] = (uint16_t)(ln | (ghost ? 0x8000 : 0));
+				}
+				inc_lowner.resize(inc_face.size());
+				for (int k = 0; k < td.ninc; k++) inc_lowner[(size_t)td.inc_off + k] = (uint16_t)local_of[(size_t)ds->face_owner[inc_face[(size_t)td.inc_off + k]]];
+				for (int c = c0; c < c1; c++) {
+					const int* row = &csr[(size_t)c * F];
+					for (int k = 0; k < F && row[k]; k++) {
+						const int e = row[k], f = std::abs(e) - 1;
+						int lf;
+						if (f >= td.fo0 && f < td.fo0 + td.nfo) {
+							lf = f - td.fo0;
+						} else {
+							const int* b = inc_face.data() + td.inc_off;
+							lf = td.nfo + (int)(std::lower_bound(b, b + td.ninc, f) - b);
+						}
+						csr_local[(size_t)k * nc + c] = (int16_t)(e > 0 ? lf + 1 : -(lf + 1));
+					}
+				}
+				smax = std::max(smax, td.nt + td.nh);
+				fmax = std::max(fmax, td.nfo + td.ninc);
+				tot_own += td.nfo;
+				tot_inc += td.ninc;
+				tot_halo += td.nh;
+				tiles.push_back(td);
+			}
+			// keep shared-memory rows 16-byte aligned and bank friendly
+			smax = (smax + 3) / 4 * 4 + 1;
+			fmax = (fmax + 3) / 4 * 4 + 1;
+			p.sub_smax[s] = smax;
+			p.sub_fmax[s] = fmax;
+			if (((size_t)NS * smax + (size_t)NQ * fmax) * es > budget) ok = false;
+		}
+		p.sub_tile_start[h->n_sub] = (int)tiles.size();
+		if (ok) {
+			p.halo_face_ratio = tot_own ? (double)tot_inc / (double)tot_own : 0.0;
+			p.halo_cell_ratio = (double)tot_halo / (double)nc;
+			break;
+		}
+		if (TC <= 16) return 0;   // not tileable within the budget: unfused kernels
+		TC /= 2;
+	}
+	p.tile_cells = TC;
+	p.n_tiles = (int)tiles.size();
+	int smax = 0, fmax = 0;
+	for (int s = 0; s < h->n_sub; s++) {
+		smax = std::max(smax, p.sub_smax[s]);
+		fmax = std::max(fmax, p.sub_fmax[s]);
+	}
+	p.smem_bytes = ((size_t)NS * smax + (size_t)NQ * fmax) * es;
+	TRY(upload<TileDesc>(h, &p.d_tiles, tiles.data(), tiles.size()));
+	TRY(upload<int>(h, &p.d_halo_cell, halo_cell.data(), halo_cell.size()));
+	TRY(upload<int>(h, &p.d_inc_face, inc_face.data(), inc_face.size()));
+	TRY(upload<uint16_t>(h, &p.d_inc_lowner, inc_lowner.data(), inc_lowner.size()));
+	TRY(upload<uint16_t>(h, &p.d_face_lneigh, face_lneigh.data(), face_lneigh.size()));
+	TRY(upload<int16_t>(h, &p.d_csr_local, csr_local.data(), csr_local.size()));
+	TRY(h->prec == 8 ? (D == 3 ? tile_geo<double, 3>(h) : tile_geo<double, 2>(h)) : (D == 3 ? tile_geo<float, 3>(h) : tile_geo<float, 2>(h)));
+	p.ready = true;
+	return 0;
+}
 
 #define DISPATCH(h, fn, ...) \
 	((h)->prec == 8 ? ((h)->D == 3 ? fn<double, 3>(__VA_ARGS__) : fn<double, 2>(__VA_ARGS__)) \
@@ -675,6 +934,8 @@ int lfmgpu_create(const lfmgpu_desc* ds, int device, lfmgpu_t* out) {
 		}
 		rc = h->prec == 8 ? build<double>(h, ds) : build<float>(h, ds);
 	}
+	if (const char* e = getenv("LFMGPU_TILE_CELLS")) h->tile_cells = std::max(16, atoi(e));
+	if (const char* e = getenv("LFMGPU_TILE_SMEM")) h->tile_smem_budget = std::max(16, atoi(e)) * 1024;
 	if (!rc) rc = tile_plan_build(h, ds);
 	if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = fail("upload failed: %s", cudaGetErrorString(cudaGetLastError()));
 	if (rc) {

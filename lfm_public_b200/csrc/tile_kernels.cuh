@@ -1,11 +1,313 @@
-// Fused tile kernels: placeholder plan until the tiled path is built.
+// Fused shared-memory tile kernels ("v2"): the production path of the per-iteration solve.
+//
+// A tile is a run of consecutive cells in traversal order (never straddling a submesh).  One CTA owns one
+// tile per launch and
+//   A. stages the state of the tile's cells AND of every cell across one of their faces (the halo) in shared
+//      memory, evaluating the per-cell divisions / square roots once per staged cell,
+//   B. evaluates every face that touches a tile cell exactly once per tile: the tile's own faces (a contiguous
+//      face range, because faces are numbered by owner) plus the "incoming" faces owned by earlier cells outside
+//      the tile -- the only redundant flux evaluations, a surface-to-volume effect of the cell numbering,
+//   C. gathers per cell in ascending face id (the reference's summation order, kernels.cuh) from shared memory,
+//      adds the sponge term and applies the low-storage RK update, writing q_new / dq (and RES) coalesced.
+// Nothing but the final cell state goes back to HBM: face fluxes never leave the SM, prepare_for_RKstep's
+// `dq *= A_k` and zeroing passes are folded in.  The conservatives are double-buffered (q -> qn) because other
+// tiles still read the pre-stage state of this tile's cells (the reference's in-place sweep is a Jacobi update,
+// SURVEY.md 3.2).
+//
+//   calc_VIS (cfd_v0.cpp:1744)                 -> k_tile_grad   (Green-Gauss gather from staged primitives)
+//   one_rk_step_M1/_M2 (cfd_v0.cpp:2530/1897)  -> k_tile_stage  (flux + gather + sponge + RK update)
 #pragma once
 #include <cstddef>
+#include <cstdint>
+
+#include "kernels.cuh"
+#include "lfmgpu.h"
+
 namespace lfm {
+
+struct TileDesc {
+	int c0, nt;          // first cell, number of cells
+	int halo_off, nh;    // halo cells: halo_cell[halo_off .. +nh)
+	int fo0, nfo;        // own faces: [fo0, fo0+nfo)
+	int inc_off, ninc;   // incoming faces: inc_face[inc_off .. +ninc)
+};
+
+template <class R> struct TileView {
+	const TileDesc* tiles;
+	const int* halo_cell;            // global cell id of each halo entry (ascending inside a tile)
+	const int* inc_face;             // global face id of each incoming face (ascending inside a tile)
+	const uint16_t* inc_lowner;      // staged index of the incoming face's owner
+	const uint16_t* face_lneigh;     // [n_faces] staged index of the neighbour inside the owner's tile; bit 15: physical ghost
+	const int16_t* csr_local;        // [F][n_cells] +-(tile-local face index + 1), ascending face id, 0-padded
+	const R *gK, *g_delta_mag, *g_dmag_inv, *g_Smag;   // per-face constants: [D][nfs], [nfs], [nfs], [nfs]
+	int smax, fmax;                  // shared-memory strides of this launch (staged cells, faces)
+};
+
+// per-face constants (make_geo) computed once on the device with the same expressions the flux loops use
+template <class R, int D> __global__ void __launch_bounds__(kBlock) k_face_geo(DevMesh<R> m, R* gK, R* g_delta_mag, R* g_dmag_inv, R* g_Smag) {
+	const int f = blockIdx.x * blockDim.x + threadIdx.x;
+	if (f >= m.n_faces) return;
+	R S[D], dv[D];
+#pragma unroll
+	for (int i = 0; i < D; i++) {
+		S[i] = m.S[i * m.nfs + f];
+		dv[i] = m.d[i * m.nfs + f];
+	}
+	FaceGeo<R, D> g;
+	make_geo<R, D>(S, dv, m.w[f], g);
+#pragma unroll
+	for (int i = 0; i < D; i++) gK[i * m.nfs + f] = g.K[i];
+	g_delta_mag[f] = g.delta_mag;
+	g_dmag_inv[f] = g.dmag_inv;
+	g_Smag[f] = g.S_mag;
+}
+
+template <int D> struct StagedLayout {
+	static constexpr int NQ = D + 2;
+	static constexpr int RHO_INV = NQ, RPSI = NQ + 1, AUX = NQ + 2, DUDX = NQ + 3, DTDX = DUDX + D * D, SIGMAU = DTDX + D;
+	static constexpr int NS = SIGMAU + D;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// calc_VIS on one tile
+// ---------------------------------------------------------------------------------------------------
+template <class R, int D, int NT> __global__ void __launch_bounds__(NT) k_tile_grad(DevMesh<R> m, TileView<R> tv, const R* __restrict__ q, int tile0) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	R* pr = reinterpret_cast<R*>(smem_raw);      // [D+1][smax]: U, Rpsi
+	const TileDesc td = tv.tiles[tile0 + blockIdx.x];
+	const int ns = td.nt + td.nh;
+	const int smax = tv.smax;
+	for (int i = threadIdx.x; i < ns; i += NT) {
+		const int x = i < td.nt ? td.c0 + i : tv.halo_cell[td.halo_off + i - td.nt];
+		R cq[D + 2], U[D], rho_inv, Rpsi, T;
+#pragma unroll
+		for (int k = 0; k < D + 2; k++) cq[k] = q[k * m.ncs + x];
+		primitives<R, D>(m.k, cq, rho_inv, U, Rpsi, T);
+#pragma unroll
+		for (int k = 0; k < D; k++) pr[k * smax + i] = U[k];
+		pr[D * smax + i] = Rpsi;
+	}
+	__syncthreads();
+	for (int lc = threadIdx.x; lc < td.nt; lc += NT) {
+		const int c = td.c0 + lc;
+		R cU[D];
+#pragma unroll
+		for (int k = 0; k < D; k++) cU[k] = pr[k * smax + lc];
+		const R c_Rpsi = pr[D * smax + lc];
+		const R vinv = m.vol_inv[c];
+		R dudx[D][D], dTdx[D];
+#pragma unroll
+		for (int i = 0; i < D; i++) {
+			dTdx[i] = R(0);
+#pragma unroll
+			for (int j = 0; j < D; j++) dudx[i][j] = R(0);
+		}
+		for (int s = 0; s < m.F; s++) {
+			const int e = tv.csr_local[(size_t)s * m.n_cells + c];
+			if (e == 0) break;
+			const bool own = e > 0;
+			const int lf = (own ? e : -e) - 1;
+			int f, lo;
+			if (lf < td.nfo) {
+				f = td.fo0 + lf;
+				// own face of a tile cell: the other side is the neighbour when c is the owner, else the owner
+				lo = own ? (int)(tv.face_lneigh[f] & 0x7fffu) : m.face_owner[f] - td.c0;
+			} else {
+				const int k = td.inc_off + lf - td.nfo;
+				f = tv.inc_face[k];
+				lo = tv.inc_lowner[k];
+			}
+			R oU[D];
+#pragma unroll
+			for (int k = 0; k < D; k++) oU[k] = pr[k * smax + lo];
+			const R o_Rpsi = pr[D * smax + lo];
+			const R w = m.w[f];
+			R face_U[D], face_T, sov[D];
+			if (own) {
+				grad_face_values<R, D>(m.k, w, cU, c_Rpsi, oU, o_Rpsi, face_U, face_T);
+#pragma unroll
+				for (int i = 0; i < D; i++) sov[i] = m.S[i * m.nfs + f] * vinv;
+			} else {
+				grad_face_values<R, D>(m.k, w, oU, o_Rpsi, cU, c_Rpsi, face_U, face_T);
+#pragma unroll
+				for (int i = 0; i < D; i++) sov[i] = -m.S[i * m.nfs + f] * vinv;
+			}
+#pragma unroll
+			for (int i = 0; i < D; i++) {
+#pragma unroll
+				for (int j = 0; j < D; j++) dudx[i][j] += face_U[i] * sov[j];
+				dTdx[i] += face_T * sov[i];
+			}
+		}
+#pragma unroll
+		for (int i = 0; i < D; i++) {
+#pragma unroll
+			for (int j = 0; j < D; j++) m.dudx[(size_t)(i * D + j) * m.ncs + c] = dudx[i][j];
+			m.dTdx[(size_t)i * m.ncs + c] = dTdx[i];
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// one_rk_step_M1/_M2 on one tile (flux, gather, sponge, RK update)
+// ---------------------------------------------------------------------------------------------------
+template <class R, int D> __device__ __forceinline__ void staged_store(R* st, int smax, int i, const CellState<R, D>& s) {
+	using L = StagedLayout<D>;
+#pragma unroll
+	for (int k = 0; k < D + 2; k++) st[k * smax + i] = s.q[k];
+	st[L::RHO_INV * smax + i] = s.rho_inv;
+	st[L::RPSI * smax + i] = s.Rpsi;
+	st[L::AUX * smax + i] = s.aux;
+#pragma unroll
+	for (int a = 0; a < D; a++) {
+#pragma unroll
+		for (int b = 0; b < D; b++) st[(L::DUDX + a * D + b) * smax + i] = s.dudx[a][b];
+		st[(L::DTDX + a) * smax + i] = s.dTdx[a];
+		st[(L::SIGMAU + a) * smax + i] = s.sigmaU[a];
+	}
+}
+template <class R, int D> __device__ __forceinline__ void staged_load(const R* st, int smax, int i, CellState<R, D>& s) {
+	using L = StagedLayout<D>;
+#pragma unroll
+	for (int k = 0; k < D + 2; k++) s.q[k] = st[k * smax + i];
+	s.rho_inv = st[L::RHO_INV * smax + i];
+	s.Rpsi = st[L::RPSI * smax + i];
+	s.aux = st[L::AUX * smax + i];
+#pragma unroll
+	for (int a = 0; a < D; a++) {
+#pragma unroll
+		for (int b = 0; b < D; b++) s.dudx[a][b] = st[(L::DUDX + a * D + b) * smax + i];
+		s.dTdx[a] = st[(L::DTDX + a) * smax + i];
+		s.sigmaU[a] = st[(L::SIGMAU + a) * smax + i];
+	}
+}
+
+template <class R, int D, int SCHEME, int NT>
+__global__ void __launch_bounds__(NT) k_tile_stage(DevMesh<R> m, TileView<R> tv, const R* __restrict__ q, R* __restrict__ qn, int tile0, R dt, R Ak, R Bk, int first, int res) {
+	using L = StagedLayout<D>;
+	constexpr int NQ = D + 2;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int smax = tv.smax, fmax = tv.fmax;
+	R* st = reinterpret_cast<R*>(smem_raw);      // [NS][smax]
+	R* fl = st + (size_t)L::NS * smax;           // [NQ][fmax]
+	const TileDesc td = tv.tiles[tile0 + blockIdx.x];
+	const int ns = td.nt + td.nh;
+
+	// ---- A: stage cell states ------------------------------------------------------------------------
+	for (int i = threadIdx.x; i < ns; i += NT) {
+		const int x = i < td.nt ? td.c0 + i : tv.halo_cell[td.halo_off + i - td.nt];
+		CellState<R, D> s;
+		load_state<R, D, SCHEME>(m, q, x, s);
+		staged_store<R, D>(st, smax, i, s);
+	}
+	__syncthreads();
+
+	// ---- B: every face of the tile once ----------------------------------------------------------------
+	const int nf = td.nfo + td.ninc;
+	for (int lf = threadIdx.x; lf < nf; lf += NT) {
+		int f, lo, ln;
+		bool ghost = false;
+		if (lf < td.nfo) {
+			f = td.fo0 + lf;
+			lo = m.face_owner[f] - td.c0;
+			const unsigned v = tv.face_lneigh[f];
+			ln = (int)(v & 0x7fffu);
+			ghost = (v >> 15) != 0;
+		} else {
+			const int k = td.inc_off + lf - td.nfo;
+			f = tv.inc_face[k];
+			lo = tv.inc_lowner[k];
+			ln = m.face_neigh[f] - td.c0;
+		}
+		CellState<R, D> c, a;
+		staged_load<R, D>(st, smax, lo, c);
+		staged_load<R, D>(st, smax, ln, a);
+		FaceGeo<R, D> g;
+		R dv[D];
+#pragma unroll
+		for (int i = 0; i < D; i++) {
+			g.S[i] = m.S[i * m.nfs + f];
+			g.K[i] = tv.gK[i * m.nfs + f];
+			dv[i] = R(0);
+		}
+		g.w = m.w[f];
+		g.delta_mag = tv.g_delta_mag[f];
+		g.dmag_inv = tv.g_dmag_inv[f];
+		g.S_mag = SCHEME == 0 ? tv.g_Smag[f] : R(0);
+		if (ghost) {
+#pragma unroll
+			for (int i = 0; i < D; i++) dv[i] = m.d[i * m.nfs + f];
+		}
+		R rhs[NQ];
+		face_flux<R, D, SCHEME>(m.k, c, a, g, ghost, dv, rhs);
+#pragma unroll
+		for (int i = 0; i < NQ; i++) fl[i * fmax + lf] = rhs[i];
+	}
+	__syncthreads();
+
+	// ---- C: ordered gather, sponge, RK update ----------------------------------------------------------
+	for (int lc = threadIdx.x; lc < td.nt; lc += NT) {
+		const int c = td.c0 + lc;
+		R dq[NQ], RES[NQ];
+#pragma unroll
+		for (int i = 0; i < NQ; i++) {
+			dq[i] = first ? R(0) : m.dq[(size_t)i * m.n_cells + c] * Ak;
+			RES[i] = R(0);
+		}
+		const R vinv = m.vol_inv[c];
+		for (int s = 0; s < m.F; s++) {
+			const int e = tv.csr_local[(size_t)s * m.n_cells + c];
+			if (e == 0) break;
+			const int lf = (e > 0 ? e : -e) - 1;
+			if (e > 0) {
+#pragma unroll
+				for (int i = 0; i < NQ; i++) {
+					const R r = fl[i * fmax + lf];
+					if (res) RES[i] += r;
+					dq[i] += dt * r * vinv;
+				}
+			} else {
+#pragma unroll
+				for (int i = 0; i < NQ; i++) {
+					const R r = fl[i * fmax + lf];
+					if (res) RES[i] -= r;
+					dq[i] -= dt * r * vinv;
+				}
+			}
+		}
+		R cq[NQ];
+#pragma unroll
+		for (int i = 0; i < NQ; i++) cq[i] = st[i * smax + lc];
+		const R sg = m.sigma[c];
+		dq[0] += dt * sg * (m.k.rhoInf - cq[0]);
+#pragma unroll
+		for (int i = 0; i < D; i++) dq[i + 1] += dt * sg * (m.k.rhoUInf[i] - cq[i + 1]);
+		dq[D + 1] += dt * sg * (m.k.rhoEInf - cq[D + 1]);
+#pragma unroll
+		for (int i = 0; i < NQ; i++) {
+			m.dq[(size_t)i * m.n_cells + c] = dq[i];
+			qn[i * m.ncs + c] = cq[i] + Bk * dq[i];
+			if (res) m.RES[(size_t)i * m.n_cells + c] = RES[i];
+		}
+	}
+}
+
+// host-side description of the plan (device arrays are owned by the handle's allocation list)
 struct TilePlan {
 	bool ready = false;
-	int n_tiles = 0, tile_cells = 0;
-	size_t smem_bytes = 0;
-	double halo_face_ratio = 0.0;
+	int n_tiles = 0, tile_cells = 0, threads = 128;
+	int sub_tile_start[LFMGPU_MAX_SUBMESH + 1] = {0};
+	int sub_smax[LFMGPU_MAX_SUBMESH] = {0}, sub_fmax[LFMGPU_MAX_SUBMESH] = {0};
+	size_t smem_bytes = 0;            // largest k_tile_stage request
+	double halo_face_ratio = 0.0;     // incoming faces / own faces (redundant flux evaluations)
+	double halo_cell_ratio = 0.0;     // halo cells / tile cells
+	TileDesc* d_tiles = nullptr;
+	int* d_halo_cell = nullptr;
+	int* d_inc_face = nullptr;
+	uint16_t* d_inc_lowner = nullptr;
+	uint16_t* d_face_lneigh = nullptr;
+	int16_t* d_csr_local = nullptr;
+	void *d_gK = nullptr, *d_delta_mag = nullptr, *d_dmag_inv = nullptr, *d_Smag = nullptr;
 };
+
 }  // namespace lfm

@@ -275,13 +275,31 @@ def tri_prism_box(nx, ny, lengths=(1.0, 1.0), shuffle_seed=None):
 # renumbering (RCM stop-gap for hpathRenumber; reference: examples/*/constant/renumberMeshDict)
 # ------------------------------------------------------------------------------------------------
 
-def hex_block(n, blocks=(1, 1, 1), rank=0, cell_size=None, z_cyclic=None):
+def blocked_order(ni, nj, nk, tile, offset=(0, 0, 0)):
+    """Cell permutation new_of_old for a logical (ni,nj,nk) block: cells are numbered tile by tile (tiles of
+    tile=(ti,tj,tk) cells, i fastest inside a tile and across tiles), the structured analogue of the reference's
+    renumberMesh pre-processing (hpathRenumber / CuthillMcKee): consecutive cell ids form compact 3D bricks, which
+    is what the shared-memory tile kernels want.  offset shifts the tile lattice (offset=(1,1,1) aligns the bricks
+    with the interior submesh, whose first cell is (1,1,1))."""
+    ti, tj, tk = tile
+    c = np.arange(ni * nj * nk, dtype=np.int64)
+    i, j, k = c % ni, (c // ni) % nj, c // (ni * nj)
+    io, jo, ko = i + (ti - offset[0]) % ti, j + (tj - offset[1]) % tj, k + (tk - offset[2]) % tk
+    order = np.lexsort((io % ti, jo % tj, ko % tk, io // ti, jo // tj, ko // tk))   # last key is primary
+    new_of_old = np.empty(len(c), dtype=np.int64)
+    new_of_old[order] = c
+    return new_of_old
+
+
+def hex_block(n, blocks=(1, 1, 1), rank=0, cell_size=None, z_cyclic=None, tile=None):
     """The processor mesh of ONE rank of a block-decomposed hex box, generated without ever building the global
     mesh (weak-scaling runs: 16.8 M cells per rank).  n = (nx,ny,nz) cells of this block, blocks = (bx,by,bz),
     rank = bi + bx*(bj + by*bk) as in block_assignment().  Physically identical to
     decompose(hex_box(n*blocks), block_assignment)[rank] (same points, same cell order, same patches; the
     processor-face ids are a different but consistent global numbering -- they only serve to match the two sides).
-    z is a cyclic pair when bz == 1 (default), walls otherwise."""
+    z is a cyclic pair when bz == 1 (default), walls otherwise.
+    tile=(ti,tj,tk): number the cells brick by brick (blocked_order, aligned with the interior submesh); the
+    permutation is returned as m["new_of_old"] (fields given in lexicographic order must be permuted with it)."""
     nx, ny, nz = n
     bx, by, bz = blocks
     bi, bj, bk = rank % bx, (rank // bx) % by, rank // (bx * by)
@@ -333,6 +351,11 @@ def hex_block(n, blocks=(1, 1, 1), rank=0, cell_size=None, z_cyclic=None):
     patch_id = np.full(nf, -1, dtype=np.int64)
     for s in range(6):
         patch_id[side == s] = side_patch[s]
+    new_of_old = None
+    if tile is not None:
+        new_of_old = blocked_order(nx, ny, nz, tile, offset=(1, 1, 1))
+        a = new_of_old[a]
+        b = np.where(b >= 0, new_of_old[np.maximum(b, 0)], -1)
     # cyclic twins must share the same offset inside their patches: order the two z planes by (i,j) == gid within a plane
     m = assemble(points, faces, a, b, patch_id, patch_defs, nx * ny * nz, cyclic_keys=gid)
     # recover the id of each assembled face (assemble sorts; redo its ordering on gid)
@@ -349,6 +372,8 @@ def hex_block(n, blocks=(1, 1, 1), rank=0, cell_size=None, z_cyclic=None):
     m["faceProcAddressing"] = m["faceProcAddressing"].astype(np.int32)
     m["logical"] = (nx, ny, nz)
     m["block"] = (bi, bj, bk)
+    if new_of_old is not None:
+        m["new_of_old"] = new_of_old
     return m
 
 
