@@ -138,35 +138,81 @@ template <class R, int D> __device__ __forceinline__ void make_geo(const R* S, c
 	g.w = w;
 }
 
+// Accessors: face_flux reads a side's state through one of these, so the same expression tree serves values held
+// in registers (unfused kernels) and values staged in shared memory (tile kernels, loaded where they are used to
+// keep the register footprint small).
+template <class R, int D> struct RegSide {
+	const CellState<R, D>& s;
+	__device__ __forceinline__ R q(int k) const { return s.q[k]; }
+	__device__ __forceinline__ R rho_inv() const { return s.rho_inv; }
+	__device__ __forceinline__ R Rpsi() const { return s.Rpsi; }
+	__device__ __forceinline__ R aux() const { return s.aux; }
+	__device__ __forceinline__ R dudx(int i, int j) const { return s.dudx[i][j]; }
+	__device__ __forceinline__ R dTdx(int i) const { return s.dTdx[i]; }
+	__device__ __forceinline__ R sigmaU(int i) const { return s.sigmaU[i]; }
+};
+
+// one-sided viscous terms of a physical-boundary face (cfd_v0.cpp:2701-2707, 2732-2745, 2774-2782); rare, kept out of line
+template <class R, int D> __device__ __forceinline__ void ghost_face_viscous(const Consts<R>& k, const R* cU, const R* nU, R cT, R nT, const R* S, const R* K, R weight, R delta_mag, R dmag_inv, const R* dv, R* rhs) {
+	R d_norm[D], dudx[D][D], dTdx[D], tauMC[D][D], sigmaU[D];
+#pragma unroll
+	for (int i = 0; i < D; i++) d_norm[i] = dv[i] * dmag_inv;
+#pragma unroll
+	for (int i = 0; i < D; i++) {
+#pragma unroll
+		for (int j = 0; j < D; j++) dudx[i][j] = (nU[i] - cU[i]) * d_norm[j] * dmag_inv;
+		dTdx[i] = (nT - cT) * d_norm[i] * dmag_inv;
+	}
+	R tau[D][D], U_f[D];
+	stress<R, D>(k, dudx, tau);
+	tauMC_from<R, D>(k, dudx, tauMC);
+#pragma unroll
+	for (int i = 0; i < D; i++) U_f[i] = interp<R>(weight, cU[i], nU[i]);
+#pragma unroll
+	for (int i = 0; i < D; i++) sigmaU[i] = dotD<R, D>(U_f, tau[i]);
+#pragma unroll
+	for (int i = 0; i < D; i++) {
+		const R divTauMC = dotD<R, D>(tauMC[i], S);
+		const R lapU = k.mu * (delta_mag * (nU[i] - cU[i]) * dmag_inv + dotD<R, D>(K, dudx[i]));
+		rhs[i + 1] += divTauMC + lapU;
+	}
+	const R lapT = k.kappa * (delta_mag * (nT - cT) * dmag_inv + dotD<R, D>(K, dTdx));
+	const R divSigmaU = dotD<R, D>(sigmaU, S);
+	rhs[D + 1] += divSigmaU + lapT;
+}
+
 // One face of one_rk_step_M1 / _M2: rhs[D+2] seen from the owner (c = owner, n = neighbour).
 // ghost: the neighbour is a physical-boundary ghost (is_ghost) -> one-sided gradients; dv (the owner->ghost
 // vector) is only read in that case.
-template <class R, int D, int SCHEME> __device__ __forceinline__ void face_flux(const Consts<R>& k, const CellState<R, D>& c, const CellState<R, D>& n, const FaceGeo<R, D>& g, bool ghost, const R* dv, R* rhs) {
+template <class R, int D, int SCHEME, class SideC, class SideN>
+__device__ __forceinline__ void face_flux(const Consts<R>& k, const SideC& c, const SideN& n, const FaceGeo<R, D>& g, bool ghost, const R* dv, R* rhs) {
 	const R ONE = R(1.0), HALF = R(0.5), ZERO = R(0.0);
 	const R weight = g.w;
 	const R* S = g.S;
-	const R S_mag = g.S_mag;
 	R cU[D], nU[D];
+	{
+		const R cri = c.rho_inv(), nri = n.rho_inv();
 #pragma unroll
-	for (int i = 0; i < D; i++) {
-		cU[i] = c.q[i + 1] * c.rho_inv;
-		nU[i] = n.q[i + 1] * n.rho_inv;
+		for (int i = 0; i < D; i++) {
+			cU[i] = c.q(i + 1) * cri;
+			nU[i] = n.q(i + 1) * nri;
+		}
 	}
-	const R cT = c.Rpsi * k.Rgas_inv, nT = n.Rpsi * k.Rgas_inv;
 	if (SCHEME == 0) {
+		const R S_mag = g.S_mag;
 		const R omw = ONE - weight;
-		const R rhoPos = interp<R>(weight, c.q[0], n.q[0]);
-		const R rhoNeg = interp<R>(omw, n.q[0], c.q[0]);
+		const R rhoPos = interp<R>(weight, c.q(0), n.q(0));
+		const R rhoNeg = interp<R>(omw, n.q(0), c.q(0));
 		const R rhoPos_inv = ONE / rhoPos;
 		const R rhoNeg_inv = ONE / rhoNeg;
 		R rhoUPos[D], rhoUNeg[D];
 #pragma unroll
 		for (int i = 0; i < D; i++) {
-			rhoUPos[i] = interp<R>(weight, c.q[i + 1], n.q[i + 1]);
-			rhoUNeg[i] = interp<R>(omw, n.q[i + 1], c.q[i + 1]);
+			rhoUPos[i] = interp<R>(weight, c.q(i + 1), n.q(i + 1));
+			rhoUNeg[i] = interp<R>(omw, n.q(i + 1), c.q(i + 1));
 		}
-		R cell_e = R(2) * c.q[D + 1] * c.rho_inv;
-		R adjc_e = R(2) * n.q[D + 1] * n.rho_inv;
+		R cell_e = R(2) * c.q(D + 1) * c.rho_inv();
+		R adjc_e = R(2) * n.q(D + 1) * n.rho_inv();
 #pragma unroll
 		for (int nD = 0; nD < D; nD++) {
 			cell_e -= cU[nD] * cU[nD];
@@ -176,12 +222,12 @@ template <class R, int D, int SCHEME> __device__ __forceinline__ void face_flux(
 		adjc_e *= HALF;
 		const R ePos = interp<R>(weight, cell_e, adjc_e);
 		const R eNeg = interp<R>(omw, adjc_e, cell_e);
-		const R RpsiPos = interp<R>(weight, c.Rpsi, n.Rpsi);
-		const R RpsiNeg = interp<R>(omw, n.Rpsi, c.Rpsi);
+		const R RpsiPos = interp<R>(weight, c.Rpsi(), n.Rpsi());
+		const R RpsiNeg = interp<R>(omw, n.Rpsi(), c.Rpsi());
 		const R pPos = rhoPos * RpsiPos;
 		const R pNeg = rhoNeg * RpsiNeg;
-		const R cPos = interp<R>(weight, c.aux, n.aux);
-		const R cNeg = interp<R>(omw, n.aux, c.aux);
+		const R cPos = interp<R>(weight, c.aux(), n.aux());
+		const R cNeg = interp<R>(omw, n.aux(), c.aux());
 		R phiPos = ZERO, phiNeg = ZERO;
 		R uPos[D], uNeg[D];
 #pragma unroll
@@ -223,17 +269,16 @@ template <class R, int D, int SCHEME> __device__ __forceinline__ void face_flux(
 		}
 		rhs[D + 1] = -(aPos * rhoEPos + aNeg * rhoENeg + (rhoENeg - rhoEPos) * a1 + (aPos * pPos + aNeg * pNeg)) * a0;
 	} else {
-		const R rhoavg = HALF * (c.q[0] + n.q[0]);
+		const R rhoavg = HALF * (c.q(0) + n.q(0));
 		const R rhoavg_inv = ONE / rhoavg;
-		R rhoUavg[D];
-#pragma unroll
-		for (int i = 0; i < D; i++) rhoUavg[i] = HALF * (c.q[i + 1] + n.q[i + 1]);
-		const R Rpsiavg = HALF * (c.Rpsi + n.Rpsi);
+		const R Rpsiavg = HALF * (c.Rpsi() + n.Rpsi());
 		const R pavg = rhoavg * Rpsiavg;
-		const R Havg = HALF * (c.aux + n.aux);
+		const R Havg = HALF * (c.aux() + n.aux());
+		R rhoUavg[D];
 		R phiavg = ZERO;
 #pragma unroll
 		for (int i = 0; i < D; i++) {
+			rhoUavg[i] = HALF * (c.q(i + 1) + n.q(i + 1));
 			const R uavg = rhoUavg[i] * rhoavg_inv;
 			phiavg += uavg * S[i];
 		}
@@ -244,66 +289,70 @@ template <class R, int D, int SCHEME> __device__ __forceinline__ void face_flux(
 	}
 
 	// ---- viscosity ----
-	const R dmag_inv = g.dmag_inv;
-	R dudx[D][D], dTdx[D], tauMC[D][D], sigmaU[D];
-	if (!ghost) {
-		R ctau[D][D], ntau[D][D];
-		tauMC_from<R, D>(k, c.dudx, ctau);
-		tauMC_from<R, D>(k, n.dudx, ntau);
-#pragma unroll
-		for (int i = 0; i < D; i++) {
-#pragma unroll
-			for (int j = 0; j < D; j++) {
-				dudx[i][j] = interp<R>(weight, c.dudx[i][j], n.dudx[i][j]);
-				tauMC[i][j] = interp<R>(weight, ctau[i][j], ntau[i][j]);
-			}
-			dTdx[i] = interp<R>(weight, c.dTdx[i], n.dTdx[i]);
-			sigmaU[i] = interp<R>(weight, c.sigmaU[i], n.sigmaU[i]);
-		}
-	} else {
-		R d_norm[D];
-#pragma unroll
-		for (int i = 0; i < D; i++) d_norm[i] = dv[i] * dmag_inv;
-#pragma unroll
-		for (int i = 0; i < D; i++) {
-#pragma unroll
-			for (int j = 0; j < D; j++) dudx[i][j] = (nU[i] - cU[i]) * d_norm[j] * dmag_inv;
-			dTdx[i] = (nT - cT) * d_norm[i] * dmag_inv;
-		}
-		R tau[D][D], U_f[D];
-		stress<R, D>(k, dudx, tau);
-		tauMC_from<R, D>(k, dudx, tauMC);
-#pragma unroll
-		for (int i = 0; i < D; i++) U_f[i] = interp<R>(weight, cU[i], nU[i]);
-#pragma unroll
-		for (int i = 0; i < D; i++) sigmaU[i] = dotD<R, D>(U_f, tau[i]);
+	const R cT = c.Rpsi() * k.Rgas_inv, nT = n.Rpsi() * k.Rgas_inv;
+	if (ghost) {
+		ghost_face_viscous<R, D>(k, cU, nU, cT, nT, S, g.K, weight, g.delta_mag, g.dmag_inv, dv, rhs);
+		return;
 	}
-	R divTauMC[D];
+	const R dmag_inv = g.dmag_inv;
+	// diagonal part of tauMC of each side: (-tr dudx) * (mu*2/3)
+	R cdiag = ZERO, ndiag = ZERO;
 #pragma unroll
-	for (int i = 0; i < D; i++) divTauMC[i] = dotD<R, D>(tauMC[i], S);
+	for (int nD = 0; nD < D; nD++) {
+		cdiag -= c.dudx(nD, nD);
+		ndiag -= n.dudx(nD, nD);
+	}
+	cdiag *= k.c_diag;
+	ndiag *= k.c_diag;
 #pragma unroll
 	for (int i = 0; i < D; i++) {
-		const R lapU = k.mu * (g.delta_mag * (nU[i] - cU[i]) * dmag_inv + dotD<R, D>(g.K, dudx[i]));
-		rhs[i + 1] += divTauMC[i] + lapU;
+		// divTauMC[i] = sum_j interp(w, tauMC_c[i][j], tauMC_n[i][j]) * S[j],  tauMC[i][j] = mu*dudx[j][i] (+ diag on i == j)
+		R divTauMC = ZERO, Kdudx = ZERO;
+#pragma unroll
+		for (int j = 0; j < D; j++) {
+			R ct = k.mu * c.dudx(j, i), nt = k.mu * n.dudx(j, i);
+			if (j == i) {
+				ct += cdiag;
+				nt += ndiag;
+			}
+			const R t = interp<R>(weight, ct, nt) * S[j];
+			const R d = g.K[j] * interp<R>(weight, c.dudx(i, j), n.dudx(i, j));
+			if (j == 0) {
+				divTauMC = t;
+				Kdudx = d;
+			} else {
+				divTauMC += t;
+				Kdudx += d;
+			}
+		}
+		const R lapU = k.mu * (g.delta_mag * (nU[i] - cU[i]) * dmag_inv + Kdudx);
+		rhs[i + 1] += divTauMC + lapU;
 	}
-	const R lapT = k.kappa * (g.delta_mag * (nT - cT) * dmag_inv + dotD<R, D>(g.K, dTdx));
-	const R divSigmaU = dotD<R, D>(sigmaU, S);
+	R KdTdx = ZERO, divSigmaU = ZERO;
+#pragma unroll
+	for (int j = 0; j < D; j++) {
+		const R d = g.K[j] * interp<R>(weight, c.dTdx(j), n.dTdx(j));
+		const R t = interp<R>(weight, c.sigmaU(j), n.sigmaU(j)) * S[j];
+		if (j == 0) {
+			KdTdx = d;
+			divSigmaU = t;
+		} else {
+			KdTdx += d;
+			divSigmaU += t;
+		}
+	}
+	const R lapT = k.kappa * (g.delta_mag * (nT - cT) * dmag_inv + KdTdx);
 	rhs[D + 1] += divSigmaU + lapT;
 }
 
-// Fills the derived members of a CellState whose q (and, for real cells, dudx) are already loaded.
-// real: a cell of this rank (sigmaU from calc_VIS's block); otherwise sigmaU must be supplied by the caller.
-template <class R, int D, int SCHEME> __device__ __forceinline__ void derive_state(const Consts<R>& k, CellState<R, D>& s, bool real) {
+// Fills the derived members of a CellState whose q is already loaded (dudx, dTdx, sigmaU come from memory).
+template <class R, int D, int SCHEME> __device__ __forceinline__ void derive_state(const Consts<R>& k, CellState<R, D>& s) {
 	R U[D], T;
 	primitives<R, D>(k, s.q, s.rho_inv, U, s.Rpsi, T);
 	if (SCHEME == 0)
 		s.aux = LFM_SQRT(k.gamma * s.Rpsi);
 	else
 		s.aux = s.q[D + 1] / s.q[0] + s.Rpsi;
-	if (real) {
-		R tauMC[D][D];
-		vis_cell_terms<R, D>(k, s.q, s.dudx, tauMC, s.sigmaU);
-	}
 }
 
 }  // namespace lfm

@@ -33,8 +33,7 @@ template <class R> struct DevMesh {
 	R* RES;                            // [NQ][n_cells]
 	R* dudx;                           // [D*D][ncs]
 	R* dTdx;                           // [D][ncs]
-	R* g_tauMC;                        // [D*D][ngs]  as received for MPI ghosts
-	R* g_sigmaU;                       // [D][ngs]
+	R* sigmaU;                         // [D][ncs]    U.tau of calc_VIS (real cells: k_*grad*; MPI ghosts: as received)
 	R* flux;                           // [NQ][nfs]   materialised face fluxes (v1 path)
 	R *pAVG, *pRMS;
 	const int *bc_cell, *bc_kind, *bc_face, *bc_patch;
@@ -145,11 +144,14 @@ template <class R, int D> __global__ void __launch_bounds__(kBlock) k_grad_cell(
 			dTdx[i] += face_T * sov[i];
 		}
 	}
+	R tauMC[D][D], sigmaU[D];
+	vis_cell_terms<R, D>(m.k, cq, dudx, tauMC, sigmaU);
 #pragma unroll
 	for (int i = 0; i < D; i++) {
 #pragma unroll
 		for (int j = 0; j < D; j++) m.dudx[(size_t)(i * D + j) * m.ncs + c] = dudx[i][j];
 		m.dTdx[(size_t)i * m.ncs + c] = dTdx[i];
+		m.sigmaU[(size_t)i * m.ncs + c] = sigmaU[i];
 	}
 }
 
@@ -165,21 +167,16 @@ template <class R, int D, int SCHEME> __device__ __forceinline__ void load_state
 #pragma unroll
 			for (int j = 0; j < D; j++) s.dudx[i][j] = R(0);
 		}
-		derive_state<R, D, SCHEME>(m.k, s, false);
-		return;
-	}
+	} else {
 #pragma unroll
-	for (int i = 0; i < D; i++) {
+		for (int i = 0; i < D; i++) {
 #pragma unroll
-		for (int j = 0; j < D; j++) s.dudx[i][j] = m.dudx[(size_t)(i * D + j) * m.ncs + x];
-		s.dTdx[i] = m.dTdx[(size_t)i * m.ncs + x];
+			for (int j = 0; j < D; j++) s.dudx[i][j] = m.dudx[(size_t)(i * D + j) * m.ncs + x];
+			s.dTdx[i] = m.dTdx[(size_t)i * m.ncs + x];
+			s.sigmaU[i] = m.sigmaU[(size_t)i * m.ncs + x];
+		}
 	}
-	if (x >= m.n_cells) {
-		const int g = x - m.n_cells - m.n_bc;
-#pragma unroll
-		for (int i = 0; i < D; i++) s.sigmaU[i] = m.g_sigmaU[(size_t)i * m.ngs + g];
-	}
-	derive_state<R, D, SCHEME>(m.k, s, x < m.n_cells);
+	derive_state<R, D, SCHEME>(m.k, s);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -201,7 +198,7 @@ template <class R, int D, int SCHEME> __global__ void __launch_bounds__(kBlock) 
 	FaceGeo<R, D> g;
 	make_geo<R, D>(S, dv, m.w[f], g);
 	const bool ghost = n >= m.n_cells && n < m.n_cells + m.n_bc;
-	face_flux<R, D, SCHEME>(m.k, c, a, g, ghost, dv, rhs);
+	face_flux<R, D, SCHEME>(m.k, RegSide<R, D>{c}, RegSide<R, D>{a}, g, ghost, dv, rhs);
 #pragma unroll
 	for (int i = 0; i < D + 2; i++) m.flux[i * m.nfs + f] = rhs[i];
 }
@@ -269,7 +266,7 @@ template <class R> __global__ void __launch_bounds__(kBlock) k_copy_q(const R* _
 // halo pack (cfd_v0.cpp:3303-3331 / 3398-3408 / 3475-3499) and unpack (3608-3692)
 // mode bit 0: q payload, bit 1: viscous payload.  Wire order per cell: q | dudx | dTdx | tauMC | sigmaU
 // ---------------------------------------------------------------------------------------------------
-template <class R, int D> __global__ void __launch_bounds__(kBlock) k_pack(DevMesh<R> m, const R* __restrict__ q, const R* __restrict__ qvis, const int* __restrict__ send_cell, int n_send, int mode, R* __restrict__ buf) {
+template <class R, int D> __global__ void __launch_bounds__(kBlock) k_pack(DevMesh<R> m, const R* __restrict__ q, const int* __restrict__ send_cell, int n_send, int mode, R* __restrict__ buf) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n_send) return;
 	constexpr int NQ = D + 2, NV = 2 * D * D + 2 * D;
@@ -291,10 +288,9 @@ template <class R, int D> __global__ void __launch_bounds__(kBlock) k_pack(DevMe
 			for (int b = 0; b < D; b++) dudx[a][b] = m.dudx[(size_t)(a * D + b) * m.ncs + c];
 			dTdx[a] = m.dTdx[(size_t)a * m.ncs + c];
 		}
-		R vq[NQ];
+		tauMC_from<R, D>(m.k, dudx, tauMC);
 #pragma unroll
-		for (int k = 0; k < NQ; k++) vq[k] = qvis[k * m.ncs + c];
-		vis_cell_terms<R, D>(m.k, vq, dudx, tauMC, sigmaU);
+		for (int a = 0; a < D; a++) sigmaU[a] = m.sigmaU[(size_t)a * m.ncs + c];
 #pragma unroll
 		for (int a = 0; a < D; a++)
 #pragma unroll
@@ -326,10 +322,9 @@ template <class R, int D> __global__ void __launch_bounds__(kBlock) k_unpack(Dev
 		for (int a = 0; a < D * D; a++) m.dudx[(size_t)a * m.ncs + g] = *o++;
 #pragma unroll
 		for (int a = 0; a < D; a++) m.dTdx[(size_t)a * m.ncs + g] = *o++;
+		o += D * D;   // tauMC is a function of the dudx just stored (same expression on both ranks): not kept
 #pragma unroll
-		for (int a = 0; a < D * D; a++) m.g_tauMC[(size_t)a * m.ngs + i] = *o++;
-#pragma unroll
-		for (int a = 0; a < D; a++) m.g_sigmaU[(size_t)a * m.ngs + i] = *o++;
+		for (int a = 0; a < D; a++) m.sigmaU[(size_t)a * m.ncs + g] = *o++;
 	}
 }
 

@@ -140,6 +140,7 @@ struct lfmgpu_ctx {
 	TilePlan tiles;
 	int use_tiles = 1;
 	int tile_cells = 128;              // cells per tile requested (halved until the plan fits the budget)
+	int stage_cfg = 0;
 	int tile_smem_budget = 75 * 1024;  // bytes of shared memory one tile CTA may use
 	// introspection
 	uint64_t launches = 0;
@@ -270,8 +271,7 @@ template <class R> int build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
 	TRY(dev_alloc(h, (void**)&m.RES, (size_t)NQ * h->n_cells * sizeof(R)));
 	TRY(dev_alloc(h, (void**)&m.dudx, (size_t)D * D * h->ncs * sizeof(R)));
 	TRY(dev_alloc(h, (void**)&m.dTdx, (size_t)D * h->ncs * sizeof(R)));
-	TRY(dev_alloc(h, (void**)&m.g_tauMC, (size_t)D * D * h->ngs * sizeof(R)));
-	TRY(dev_alloc(h, (void**)&m.g_sigmaU, (size_t)D * h->ngs * sizeof(R)));
+	TRY(dev_alloc(h, (void**)&m.sigmaU, (size_t)D * h->ncs * sizeof(R)));
 	m.flux = nullptr;   // allocated on first use of the materialised path
 	TRY(dev_alloc(h, (void**)&m.pAVG, (size_t)h->n_cells * sizeof(R)));
 	TRY(dev_alloc(h, (void**)&m.pRMS, (size_t)h->n_cells * sizeof(R)));
@@ -424,7 +424,7 @@ template <class R, int D> int t_pack(lfmgpu_ctx* h, int step, cudaStream_t s) {
 	const int mode = halo_mode(h, step);
 	h->last_send_count[step] = (size_t)ns * halo_spc(h, step);
 	if (!ns) return 0;
-	LAUNCH(h, "k_pack", s, (k_pack<R, D><<<blocks_for(ns), kBlock, 0, s>>>(h->mesh<R>(), (const R*)q_for_pack(h), (const R*)q_of_vis(h), h->d_send_cell, ns, mode, (R*)h->send_buf[step])));
+	LAUNCH(h, "k_pack", s, (k_pack<R, D><<<blocks_for(ns), kBlock, 0, s>>>(h->mesh<R>(), (const R*)q_for_pack(h), h->d_send_cell, ns, mode, (R*)h->send_buf[step])));
 	CHECK_LAUNCH();
 	return 0;
 }
@@ -509,32 +509,53 @@ void tile_range(const lfmgpu_ctx* h, int sub, int& t0, int& t1, int& smax, int& 
 	}
 }
 
-constexpr int kTileThreads = 128;
+constexpr int kGradThreads = 128;
+
 
 template <class R, int D> size_t stage_smem(int smax, int fmax) { return ((size_t)StagedLayout<D>::NS * smax + (size_t)(D + 2) * fmax) * sizeof(R); }
-template <class R, int D> size_t grad_smem(int smax) { return (size_t)(D + 1) * smax * sizeof(R); }
+template <class R, int D> size_t grad_smem(int smax, int fmax) { return (size_t)(D + 1) * (smax + fmax) * sizeof(R) + (size_t)fmax * sizeof(uint32_t); }
 
 template <class R, int D> int tile_grad(lfmgpu_ctx* h, int sub) {
+	if (sub < 0) {   // every submesh: one launch each, so that each gets its own shared-memory size
+		for (int s = 0; s < h->n_sub; s++) TRY((tile_grad<R, D>(h, s)));
+		return 0;
+	}
 	int t0, t1, smax, fmax;
 	tile_range(h, sub, t0, t1, smax, fmax);
 	if (t1 <= t0) return 0;
-	const size_t smem = grad_smem<R, D>(smax);
-	auto kern = k_tile_grad<R, D, kTileThreads>;
+	const size_t smem = grad_smem<R, D>(smax, fmax);
+	auto kern = k_tile_grad<R, D, kGradThreads>;
 	if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	LAUNCH(h, "tile_grad", h->s_main, (kern<<<t1 - t0, kTileThreads, smem, h->s_main>>>(h->mesh<R>(), tile_view<R>(h, smax, fmax), (const R*)h->q[h->cur], t0)));
+	LAUNCH(h, "tile_grad", h->s_main, (kern<<<t1 - t0, kGradThreads, smem, h->s_main>>>(h->mesh<R>(), tile_view<R>(h, smax, fmax), (const R*)h->q[h->cur], t0)));
 	CHECK_LAUNCH();
 	return 0;
 }
 
 template <class R, int D, int SCHEME> int tile_stage_s(lfmgpu_ctx* h, int sub, R dt, R Ak, R Bk, int first, int res) {
+	if (sub < 0) {
+		for (int s = 0; s < h->n_sub; s++) TRY((tile_stage_s<R, D, SCHEME>(h, s, dt, Ak, Bk, first, res)));
+		return 0;
+	}
 	int t0, t1, smax, fmax;
 	tile_range(h, sub, t0, t1, smax, fmax);
 	if (t1 <= t0) return 0;
 	const size_t smem = stage_smem<R, D>(smax, fmax);
-	auto kern = k_tile_stage<R, D, SCHEME, kTileThreads>;
-	if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	LAUNCH(h, "tile_stage", h->s_main,
-	       (kern<<<t1 - t0, kTileThreads, smem, h->s_main>>>(h->mesh<R>(), tile_view<R>(h, smax, fmax), (const R*)h->q[h->cur], (R*)h->q[1 - h->cur], t0, dt, Ak, Bk, first, res)));
+#define LFM_STAGE_CFG(NT_, MB_) \
+	{ \
+		auto kern = k_tile_stage<R, D, SCHEME, NT_, MB_>; \
+		if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+		LAUNCH(h, "tile_stage", h->s_main, \
+		       (kern<<<t1 - t0, NT_, smem, h->s_main>>>(h->mesh<R>(), tile_view<R>(h, smax, fmax), (const R*)h->q[h->cur], (R*)h->q[1 - h->cur], t0, dt, Ak, Bk, first, res))); \
+	}
+	switch (h->stage_cfg) {
+		case 1: LFM_STAGE_CFG(128, 4) break;
+		case 2: LFM_STAGE_CFG(128, 6) break;
+		case 3: LFM_STAGE_CFG(128, 8) break;
+		case 4: LFM_STAGE_CFG(64, 8) break;
+		case 5: LFM_STAGE_CFG(64, 12) break;
+		default: LFM_STAGE_CFG(256, 3) break;
+	}
+#undef LFM_STAGE_CFG
 	CHECK_LAUNCH();
 	return 0;
 }
@@ -589,9 +610,11 @@ int tile_plan_build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
 	std::vector<uint16_t> inc_lowner, face_lneigh;
 	std::vector<int16_t> csr_local;
 	std::vector<int> stamp((size_t)h->n_tot, -1), local_of((size_t)h->n_tot, 0);
-	int TC = h->tile_cells;
+	int TCs[LFMGPU_MAX_SUBMESH];
+	for (int s = 0; s < LFMGPU_MAX_SUBMESH; s++) TCs[s] = h->tile_cells;
 	int probe_id = -1;
 	for (;;) {
+		int failed_sub = -1;
 		tiles.clear();
 		halo_cell.clear();
 		inc_face.clear();
@@ -602,6 +625,7 @@ int tile_plan_build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
 		bool ok = true;
 		long long tot_own = 0, tot_inc = 0, tot_halo = 0;
 		for (int s = 0; s < h->n_sub && ok; s++) {
+			const int TC = TCs[s];
 			p.sub_tile_start[s] = (int)tiles.size();
 			int smax = 0, fmax = 0;
 			for (int c0 = h->sub_cell_start[s], c1 = 0; c0 < h->sub_cell_start[s + 1]; c0 = c1) {
@@ -665,6 +689,7 @@ int tile_plan_build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
 				for (int i = 0; i < td.nh; i++) local_of[(size_t)halo_cell[(size_t)td.halo_off + i]] = td.nt + i;
 				if (td.nt + td.nh >= 32768 || td.nfo + td.ninc >= 32767) {
 					ok = false;
+					failed_sub = s;
 					break;
 				}
 				// tile-local indices
@@ -702,7 +727,10 @@ int tile_plan_build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
 			fmax = (fmax + 3) / 4 * 4 + 1;
 			p.sub_smax[s] = smax;
 			p.sub_fmax[s] = fmax;
-			if (((size_t)NS * smax + (size_t)NQ * fmax) * es > budget) ok = false;
+			if (ok && ((size_t)NS * smax + (size_t)NQ * fmax) * es > budget) {
+				ok = false;
+				failed_sub = s;
+			}
 		}
 		p.sub_tile_start[h->n_sub] = (int)tiles.size();
 		if (ok) {
@@ -710,10 +738,10 @@ int tile_plan_build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
 			p.halo_cell_ratio = (double)tot_halo / (double)nc;
 			break;
 		}
-		if (TC <= 16) return 0;   // not tileable within the budget: unfused kernels
-		TC /= 2;
+		if (failed_sub < 0 || TCs[failed_sub] <= 16) return 0;   // not tileable within the budget: unfused kernels
+		TCs[failed_sub] /= 2;
 	}
-	p.tile_cells = TC;
+	p.tile_cells = TCs[h->n_sub - 1];
 	p.n_tiles = (int)tiles.size();
 	int smax = 0, fmax = 0;
 	for (int s = 0; s < h->n_sub; s++) {
@@ -935,6 +963,7 @@ int lfmgpu_create(const lfmgpu_desc* ds, int device, lfmgpu_t* out) {
 		rc = h->prec == 8 ? build<double>(h, ds) : build<float>(h, ds);
 	}
 	if (const char* e = getenv("LFMGPU_TILE_CELLS")) h->tile_cells = std::max(16, atoi(e));
+	if (const char* e = getenv("LFMGPU_STAGE_CFG")) h->stage_cfg = atoi(e);
 	if (const char* e = getenv("LFMGPU_TILE_SMEM")) h->tile_smem_budget = std::max(16, atoi(e)) * 1024;
 	if (!rc) rc = tile_plan_build(h, ds);
 	if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = fail("upload failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1100,7 +1129,7 @@ int lfmgpu_download(lfmgpu_t h, int field, void* dst, size_t dst_bytes) {
 		case LFMGPU_FIELD_PRMS: base = h->prec == 8 ? (const char*)h->md.pRMS : (const char*)h->mf.pRMS; stride = (size_t)nc; break;
 		case LFMGPU_FIELD_QGHOST: base = (const char*)h->q[h->cur]; stride = h->ncs; comps = NQ; off = (size_t)nc; n = (size_t)(h->n_bc + h->n_mpi); break;
 		case LFMGPU_FIELD_TAUMC: comps = D * D; derived = true; break;
-		case LFMGPU_FIELD_SIGMAU: comps = D; derived = true; break;
+		case LFMGPU_FIELD_SIGMAU: base = h->prec == 8 ? (const char*)h->md.sigmaU : (const char*)h->mf.sigmaU; stride = h->ncs; comps = D; break;
 		default: return fail("unknown field %d", field);
 	}
 	if (dst_bytes < n * comps * es) return fail("lfmgpu_download: destination too small (%zu < %zu)", dst_bytes, n * comps * es);

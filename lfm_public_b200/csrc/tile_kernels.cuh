@@ -68,15 +68,37 @@ template <int D> struct StagedLayout {
 	static constexpr int NS = SIGMAU + D;
 };
 
+// a side of a face staged in shared memory (SoA rows of stride smax); values are loaded where they are used
+template <class R, int D> struct SmemSide {
+	const R* st;
+	int smax, i;
+	using L = StagedLayout<D>;
+	__device__ __forceinline__ R q(int k) const { return st[k * smax + i]; }
+	__device__ __forceinline__ R rho_inv() const { return st[L::RHO_INV * smax + i]; }
+	__device__ __forceinline__ R Rpsi() const { return st[L::RPSI * smax + i]; }
+	__device__ __forceinline__ R aux() const { return st[L::AUX * smax + i]; }
+	__device__ __forceinline__ R dudx(int a, int b) const { return st[(L::DUDX + a * D + b) * smax + i]; }
+	__device__ __forceinline__ R dTdx(int a) const { return st[(L::DTDX + a) * smax + i]; }
+	__device__ __forceinline__ R sigmaU(int a) const { return st[(L::SIGMAU + a) * smax + i]; }
+};
+
+constexpr int kMaxSlots = 6;   // FACE_CNT of the reference is at most 6 (hexahedra)
+
 // ---------------------------------------------------------------------------------------------------
-// calc_VIS on one tile
+// calc_VIS on one tile: dudx, dTdx, sigmaU of the tile's cells
+//   A. primitives (U, Rpsi) of tile + halo cells and (w, S, owner/neighbour staged index) of the tile's faces
+//      go to shared memory with independent, coalesced loads;
+//   C. per cell, ordered Green-Gauss gather from shared memory, then the tau/sigmaU block of calc_VIS.
 // ---------------------------------------------------------------------------------------------------
 template <class R, int D, int NT> __global__ void __launch_bounds__(NT) k_tile_grad(DevMesh<R> m, TileView<R> tv, const R* __restrict__ q, int tile0) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int smax = tv.smax, fmax = tv.fmax;
 	R* pr = reinterpret_cast<R*>(smem_raw);      // [D+1][smax]: U, Rpsi
+	R* fg = pr + (size_t)(D + 1) * smax;         // [D+1][fmax]: S, w
+	uint32_t* fi = reinterpret_cast<uint32_t*>(fg + (size_t)(D + 1) * fmax);   // [fmax]: owner | neighbour << 16 (staged indices)
 	const TileDesc td = tv.tiles[tile0 + blockIdx.x];
 	const int ns = td.nt + td.nh;
-	const int smax = tv.smax;
+	const int nf = td.nfo + td.ninc;
 	for (int i = threadIdx.x; i < ns; i += NT) {
 		const int x = i < td.nt ? td.c0 + i : tv.halo_cell[td.halo_off + i - td.nt];
 		R cq[D + 2], U[D], rho_inv, Rpsi, T;
@@ -87,14 +109,38 @@ template <class R, int D, int NT> __global__ void __launch_bounds__(NT) k_tile_g
 		for (int k = 0; k < D; k++) pr[k * smax + i] = U[k];
 		pr[D * smax + i] = Rpsi;
 	}
+	for (int lf = threadIdx.x; lf < nf; lf += NT) {
+		int f;
+		uint32_t lo, ln;
+		if (lf < td.nfo) {
+			f = td.fo0 + lf;
+			lo = (uint32_t)(m.face_owner[f] - td.c0);
+			ln = tv.face_lneigh[f] & 0x7fffu;
+		} else {
+			const int k = td.inc_off + lf - td.nfo;
+			f = tv.inc_face[k];
+			lo = tv.inc_lowner[k];
+			ln = (uint32_t)(m.face_neigh[f] - td.c0);
+		}
+#pragma unroll
+		for (int k = 0; k < D; k++) fg[k * fmax + lf] = m.S[k * m.nfs + f];
+		fg[D * fmax + lf] = m.w[f];
+		fi[lf] = lo | (ln << 16);
+	}
 	__syncthreads();
 	for (int lc = threadIdx.x; lc < td.nt; lc += NT) {
 		const int c = td.c0 + lc;
+		int e[kMaxSlots];
+#pragma unroll
+		for (int s = 0; s < kMaxSlots; s++) e[s] = s < m.F ? (int)tv.csr_local[(size_t)s * m.n_cells + c] : 0;
+		const R vinv = m.vol_inv[c];
+		R cq[D + 2];
+#pragma unroll
+		for (int k = 0; k < D + 2; k++) cq[k] = q[k * m.ncs + c];
 		R cU[D];
 #pragma unroll
 		for (int k = 0; k < D; k++) cU[k] = pr[k * smax + lc];
 		const R c_Rpsi = pr[D * smax + lc];
-		const R vinv = m.vol_inv[c];
 		R dudx[D][D], dTdx[D];
 #pragma unroll
 		for (int i = 0; i < D; i++) {
@@ -102,35 +148,27 @@ template <class R, int D, int NT> __global__ void __launch_bounds__(NT) k_tile_g
 #pragma unroll
 			for (int j = 0; j < D; j++) dudx[i][j] = R(0);
 		}
-		for (int s = 0; s < m.F; s++) {
-			const int e = tv.csr_local[(size_t)s * m.n_cells + c];
-			if (e == 0) break;
-			const bool own = e > 0;
-			const int lf = (own ? e : -e) - 1;
-			int f, lo;
-			if (lf < td.nfo) {
-				f = td.fo0 + lf;
-				// own face of a tile cell: the other side is the neighbour when c is the owner, else the owner
-				lo = own ? (int)(tv.face_lneigh[f] & 0x7fffu) : m.face_owner[f] - td.c0;
-			} else {
-				const int k = td.inc_off + lf - td.nfo;
-				f = tv.inc_face[k];
-				lo = tv.inc_lowner[k];
-			}
+#pragma unroll
+		for (int s = 0; s < kMaxSlots; s++) {
+			if (e[s] == 0) break;
+			const bool own = e[s] > 0;
+			const int lf = (own ? e[s] : -e[s]) - 1;
+			const uint32_t idx = fi[lf];
+			const int lo = own ? (int)(idx >> 16) : (int)(idx & 0xffffu);   // the other side
 			R oU[D];
 #pragma unroll
 			for (int k = 0; k < D; k++) oU[k] = pr[k * smax + lo];
 			const R o_Rpsi = pr[D * smax + lo];
-			const R w = m.w[f];
+			const R w = fg[D * fmax + lf];
 			R face_U[D], face_T, sov[D];
 			if (own) {
 				grad_face_values<R, D>(m.k, w, cU, c_Rpsi, oU, o_Rpsi, face_U, face_T);
 #pragma unroll
-				for (int i = 0; i < D; i++) sov[i] = m.S[i * m.nfs + f] * vinv;
+				for (int i = 0; i < D; i++) sov[i] = fg[i * fmax + lf] * vinv;
 			} else {
 				grad_face_values<R, D>(m.k, w, oU, o_Rpsi, cU, c_Rpsi, face_U, face_T);
 #pragma unroll
-				for (int i = 0; i < D; i++) sov[i] = -m.S[i * m.nfs + f] * vinv;
+				for (int i = 0; i < D; i++) sov[i] = -fg[i * fmax + lf] * vinv;
 			}
 #pragma unroll
 			for (int i = 0; i < D; i++) {
@@ -139,11 +177,14 @@ template <class R, int D, int NT> __global__ void __launch_bounds__(NT) k_tile_g
 				dTdx[i] += face_T * sov[i];
 			}
 		}
+		R tauMC[D][D], sigmaU[D];
+		vis_cell_terms<R, D>(m.k, cq, dudx, tauMC, sigmaU);
 #pragma unroll
 		for (int i = 0; i < D; i++) {
 #pragma unroll
 			for (int j = 0; j < D; j++) m.dudx[(size_t)(i * D + j) * m.ncs + c] = dudx[i][j];
 			m.dTdx[(size_t)i * m.ncs + c] = dTdx[i];
+			m.sigmaU[(size_t)i * m.ncs + c] = sigmaU[i];
 		}
 	}
 }
@@ -166,24 +207,9 @@ template <class R, int D> __device__ __forceinline__ void staged_store(R* st, in
 		st[(L::SIGMAU + a) * smax + i] = s.sigmaU[a];
 	}
 }
-template <class R, int D> __device__ __forceinline__ void staged_load(const R* st, int smax, int i, CellState<R, D>& s) {
-	using L = StagedLayout<D>;
-#pragma unroll
-	for (int k = 0; k < D + 2; k++) s.q[k] = st[k * smax + i];
-	s.rho_inv = st[L::RHO_INV * smax + i];
-	s.Rpsi = st[L::RPSI * smax + i];
-	s.aux = st[L::AUX * smax + i];
-#pragma unroll
-	for (int a = 0; a < D; a++) {
-#pragma unroll
-		for (int b = 0; b < D; b++) s.dudx[a][b] = st[(L::DUDX + a * D + b) * smax + i];
-		s.dTdx[a] = st[(L::DTDX + a) * smax + i];
-		s.sigmaU[a] = st[(L::SIGMAU + a) * smax + i];
-	}
-}
 
-template <class R, int D, int SCHEME, int NT>
-__global__ void __launch_bounds__(NT) k_tile_stage(DevMesh<R> m, TileView<R> tv, const R* __restrict__ q, R* __restrict__ qn, int tile0, R dt, R Ak, R Bk, int first, int res) {
+template <class R, int D, int SCHEME, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_tile_stage(DevMesh<R> m, TileView<R> tv, const R* __restrict__ q, R* __restrict__ qn, int tile0, R dt, R Ak, R Bk, int first, int res) {
 	using L = StagedLayout<D>;
 	constexpr int NQ = D + 2;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -219,9 +245,6 @@ __global__ void __launch_bounds__(NT) k_tile_stage(DevMesh<R> m, TileView<R> tv,
 			lo = tv.inc_lowner[k];
 			ln = m.face_neigh[f] - td.c0;
 		}
-		CellState<R, D> c, a;
-		staged_load<R, D>(st, smax, lo, c);
-		staged_load<R, D>(st, smax, ln, a);
 		FaceGeo<R, D> g;
 		R dv[D];
 #pragma unroll
@@ -239,7 +262,7 @@ __global__ void __launch_bounds__(NT) k_tile_stage(DevMesh<R> m, TileView<R> tv,
 			for (int i = 0; i < D; i++) dv[i] = m.d[i * m.nfs + f];
 		}
 		R rhs[NQ];
-		face_flux<R, D, SCHEME>(m.k, c, a, g, ghost, dv, rhs);
+		face_flux<R, D, SCHEME>(m.k, SmemSide<R, D>{st, smax, lo}, SmemSide<R, D>{st, smax, ln}, g, ghost, dv, rhs);
 #pragma unroll
 		for (int i = 0; i < NQ; i++) fl[i * fmax + lf] = rhs[i];
 	}
@@ -248,6 +271,9 @@ __global__ void __launch_bounds__(NT) k_tile_stage(DevMesh<R> m, TileView<R> tv,
 	// ---- C: ordered gather, sponge, RK update ----------------------------------------------------------
 	for (int lc = threadIdx.x; lc < td.nt; lc += NT) {
 		const int c = td.c0 + lc;
+		int e[kMaxSlots];
+#pragma unroll
+		for (int s = 0; s < kMaxSlots; s++) e[s] = s < m.F ? (int)tv.csr_local[(size_t)s * m.n_cells + c] : 0;
 		R dq[NQ], RES[NQ];
 #pragma unroll
 		for (int i = 0; i < NQ; i++) {
@@ -255,11 +281,12 @@ __global__ void __launch_bounds__(NT) k_tile_stage(DevMesh<R> m, TileView<R> tv,
 			RES[i] = R(0);
 		}
 		const R vinv = m.vol_inv[c];
-		for (int s = 0; s < m.F; s++) {
-			const int e = tv.csr_local[(size_t)s * m.n_cells + c];
-			if (e == 0) break;
-			const int lf = (e > 0 ? e : -e) - 1;
-			if (e > 0) {
+		const R sg = m.sigma[c];
+#pragma unroll
+		for (int s = 0; s < kMaxSlots; s++) {
+			if (e[s] == 0) break;
+			const int lf = (e[s] > 0 ? e[s] : -e[s]) - 1;
+			if (e[s] > 0) {
 #pragma unroll
 				for (int i = 0; i < NQ; i++) {
 					const R r = fl[i * fmax + lf];
@@ -278,7 +305,6 @@ __global__ void __launch_bounds__(NT) k_tile_stage(DevMesh<R> m, TileView<R> tv,
 		R cq[NQ];
 #pragma unroll
 		for (int i = 0; i < NQ; i++) cq[i] = st[i * smax + lc];
-		const R sg = m.sigma[c];
 		dq[0] += dt * sg * (m.k.rhoInf - cq[0]);
 #pragma unroll
 		for (int i = 0; i < D; i++) dq[i + 1] += dt * sg * (m.k.rhoUInf[i] - cq[i + 1]);
