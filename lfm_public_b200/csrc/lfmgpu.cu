@@ -141,6 +141,7 @@ struct lfmgpu_ctx {
 	int use_tiles = 1;
 	int tile_cells = 128;              // cells per tile requested (halved until the plan fits the budget)
 	int stage_cfg = 0;
+	int prefetch_distance = 0;
 	int tile_smem_budget = 75 * 1024;  // bytes of shared memory one tile CTA may use
 	// introspection
 	uint64_t launches = 0;
@@ -488,6 +489,8 @@ template <class R> TileView<R> tile_view(lfmgpu_ctx* h, int smax, int fmax) {
 	v.g_Smag = (const R*)p.d_Smag;
 	v.smax = smax;
 	v.fmax = fmax;
+	v.prefetch_distance = h->prefetch_distance;
+	v.n_launch_tiles = 0;
 	return v;
 }
 
@@ -539,13 +542,16 @@ template <class R, int D, int SCHEME> int tile_stage_s(lfmgpu_ctx* h, int sub, R
 	int t0, t1, smax, fmax;
 	tile_range(h, sub, t0, t1, smax, fmax);
 	if (t1 <= t0) return 0;
-	const size_t smem = stage_smem<R, D>(smax, fmax);
+	size_t smem = stage_smem<R, D>(smax, fmax);
+	if (const char* e = getenv("LFMGPU_SMEM_PAD")) smem += (size_t)atoi(e) * 1024;   // experiment knob: fewer resident CTAs
+	TileView<R> tview = tile_view<R>(h, smax, fmax);
+	tview.n_launch_tiles = t1 - t0;
 #define LFM_STAGE_CFG(NT_, MB_) \
 	{ \
 		auto kern = k_tile_stage<R, D, SCHEME, NT_, MB_>; \
 		if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
 		LAUNCH(h, "tile_stage", h->s_main, \
-		       (kern<<<t1 - t0, NT_, smem, h->s_main>>>(h->mesh<R>(), tile_view<R>(h, smax, fmax), (const R*)h->q[h->cur], (R*)h->q[1 - h->cur], t0, dt, Ak, Bk, first, res))); \
+		       (kern<<<t1 - t0, NT_, smem, h->s_main>>>(h->mesh<R>(), tview, (const R*)h->q[h->cur], (R*)h->q[1 - h->cur], t0, dt, Ak, Bk, first, res))); \
 	}
 	switch (h->stage_cfg) {
 		case 1: LFM_STAGE_CFG(128, 4) break;
@@ -626,18 +632,27 @@ int tile_plan_build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
 		long long tot_own = 0, tot_inc = 0, tot_halo = 0;
 		for (int s = 0; s < h->n_sub && ok; s++) {
 			const int TC = TCs[s];
+			// shared-memory caps of one tile: faces ~ (F/2 own + 25% incoming) per cell, the rest of the budget for staged cells
+			const int f_cap = std::max(F, (int)(0.625 * F * TC));
+			const int s_cap = (int)(((long long)(budget / es) - (long long)NQ * (f_cap + 4)) / NS) - 4;
+			if (s_cap < 2 * F) {
+				ok = false;
+				failed_sub = s;
+				break;
+			}
 			p.sub_tile_start[s] = (int)tiles.size();
 			int smax = 0, fmax = 0;
 			for (int c0 = h->sub_cell_start[s], c1 = 0; c0 < h->sub_cell_start[s + 1]; c0 = c1) {
 				const int cmax = std::min(c0 + TC, h->sub_cell_start[s + 1]);
-				// Choose the cut: grow the run cell by cell, tracking the halo size incrementally, and close the tile
-				// where halo/tile is smallest inside the window [0.55 TC, TC] (ties: the longer run).  For block- or
-				// space-filling-curve-numbered meshes this snaps tiles to the compact runs of the numbering.
+				// Choose the cut: grow the run cell by cell, tracking halo cells and incoming faces incrementally, and
+				// close the tile where halo/tile is smallest inside the window [0.55 TC, TC] among the prefixes that fit
+				// the shared-memory caps (ties: the longer run); if no prefix in the window fits, the longest that does.
+				// For block- or space-filling-curve-numbered meshes this snaps tiles to the compact runs of the numbering.
 				{
 					const int probe = --probe_id;   // negative stamps: never collide with tile ids
-					int nh = 0;
+					int nh = 0, ninc = 0;
 					double best = 1e300;
-					c1 = cmax;
+					int best_in_window = -1, longest_fit = -1;
 					const int cmin = std::min(cmax, c0 + std::max(1, (TC * 11) / 20));
 					for (int c = c0; c < cmax; c++) {
 						if (stamp[(size_t)c] == probe) nh--;
@@ -646,18 +661,28 @@ int tile_plan_build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
 							const int e = row[k], f = std::abs(e) - 1;
 							const int other = e > 0 ? ds->face_neigh[f] : ds->face_owner[f];
 							if (other >= c0 && other <= c) continue;
+							if (e < 0) ninc++;
 							if (stamp[(size_t)other] != probe) {
 								stamp[(size_t)other] = probe;
 								nh++;
 							}
 						}
+						const int nt = c + 1 - c0;
+						const bool fits = nt + nh <= s_cap && (cfs[(size_t)c + 1] - cfs[(size_t)c0]) + ninc <= f_cap;
+						if (!fits) continue;   // (not monotone: a later prefix may fit again once halo cells join the tile)
+						longest_fit = c + 1;
 						if (c + 1 >= cmin) {
-							const double ratio = (double)nh / (double)(c + 1 - c0);
+							const double ratio = (double)nh / (double)nt;
 							if (ratio <= best) {
 								best = ratio;
-								c1 = c + 1;
+								best_in_window = c + 1;
 							}
 						}
+					}
+					c1 = best_in_window > 0 ? best_in_window : longest_fit;
+					if (c1 <= c0) {
+						ok = false;   // a single cell does not fit: not tileable
+						break;
 					}
 				}
 				const int tid = (int)tiles.size();
@@ -740,6 +765,23 @@ int tile_plan_build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
 		}
 		if (failed_sub < 0 || TCs[failed_sub] <= 16) return 0;   // not tileable within the budget: unfused kernels
 		TCs[failed_sub] /= 2;
+	}
+	if (getenv("LFMGPU_PLAN_STATS")) {
+		for (int sb = 0; sb < h->n_sub; sb++) {
+			std::vector<int> a, b, c;
+			for (int t = p.sub_tile_start[sb]; t < p.sub_tile_start[sb + 1]; t++) {
+				a.push_back(tiles[(size_t)t].nt + tiles[(size_t)t].nh);
+				b.push_back(tiles[(size_t)t].nfo + tiles[(size_t)t].ninc);
+				c.push_back(tiles[(size_t)t].nt);
+			}
+			if (a.empty()) continue;
+			std::sort(a.begin(), a.end());
+			std::sort(b.begin(), b.end());
+			std::sort(c.begin(), c.end());
+			auto q = [](const std::vector<int>& v, double f) { return v[(size_t)(f * (v.size() - 1))]; };
+			fprintf(stderr, "[lfmgpu plan] sub %d: TC %d, %zu tiles; cells/tile min %d med %d max %d; staged med %d p90 %d p99 %d max %d; faces med %d p90 %d p99 %d max %d\n", sb,
+			        TCs[sb], a.size(), c.front(), q(c, 0.5), c.back(), q(a, 0.5), q(a, 0.9), q(a, 0.99), a.back(), q(b, 0.5), q(b, 0.9), q(b, 0.99), b.back());
+		}
 	}
 	p.tile_cells = TCs[h->n_sub - 1];
 	p.n_tiles = (int)tiles.size();
@@ -964,6 +1006,7 @@ int lfmgpu_create(const lfmgpu_desc* ds, int device, lfmgpu_t* out) {
 	}
 	if (const char* e = getenv("LFMGPU_TILE_CELLS")) h->tile_cells = std::max(16, atoi(e));
 	if (const char* e = getenv("LFMGPU_STAGE_CFG")) h->stage_cfg = atoi(e);
+	if (const char* e = getenv("LFMGPU_PREFETCH")) h->prefetch_distance = atoi(e);
 	if (const char* e = getenv("LFMGPU_TILE_SMEM")) h->tile_smem_budget = std::max(16, atoi(e)) * 1024;
 	if (!rc) rc = tile_plan_build(h, ds);
 	if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = fail("upload failed: %s", cudaGetErrorString(cudaGetLastError()));

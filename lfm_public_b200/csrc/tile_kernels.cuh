@@ -41,6 +41,8 @@ template <class R> struct TileView {
 	const int16_t* csr_local;        // [F][n_cells] +-(tile-local face index + 1), ascending face id, 0-padded
 	const R *gK, *g_delta_mag, *g_dmag_inv, *g_Smag;   // per-face constants: [D][nfs], [nfs], [nfs], [nfs]
 	int smax, fmax;                  // shared-memory strides of this launch (staged cells, faces)
+	int prefetch_distance;           // tiles ahead whose rows are pulled into L2 (0: off)
+	int n_launch_tiles;              // tiles of this launch
 };
 
 // per-face constants (make_geo) computed once on the device with the same expressions the flux loops use
@@ -208,6 +210,56 @@ template <class R, int D> __device__ __forceinline__ void staged_store(R* st, in
 	}
 }
 
+// L2 prefetch of `nrows` rows (row r starts at base + r*stride elements) of `n` elements starting at element `first`:
+// one prefetch instruction per 128-byte line, spread over the CTA.  No registers are tied up and nothing waits.
+template <class T> __device__ __forceinline__ void l2_prefetch_rows(const T* base, size_t stride, int nrows, int first, int n, int tid, int nthreads) {
+	if (n <= 0) return;
+	const int lines = (n * (int)sizeof(T) + 127) / 128 + 1;
+	for (int i = tid; i < nrows * lines; i += nthreads) {
+		const int r = i / lines, l = i - r * lines;
+		const char* p = reinterpret_cast<const char*>(base + (size_t)r * stride + first) + (size_t)l * 128;
+		asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+	}
+}
+
+// everything phase B needs about one face, fetched from global memory ahead of its use
+template <class R, int D> struct FaceIn {
+	int lo, ln;
+	bool ghost;
+	FaceGeo<R, D> g;
+	R dv[D];
+};
+template <class R, int D, int SCHEME> __device__ __forceinline__ void fetch_face(const DevMesh<R>& m, const TileView<R>& tv, const TileDesc& td, int lf, FaceIn<R, D>& in) {
+	int f;
+	in.ghost = false;
+	if (lf < td.nfo) {
+		f = td.fo0 + lf;
+		in.lo = m.face_owner[f] - td.c0;
+		const unsigned v = tv.face_lneigh[f];
+		in.ln = (int)(v & 0x7fffu);
+		in.ghost = (v >> 15) != 0;
+	} else {
+		const int k = td.inc_off + lf - td.nfo;
+		f = tv.inc_face[k];
+		in.lo = tv.inc_lowner[k];
+		in.ln = m.face_neigh[f] - td.c0;
+	}
+#pragma unroll
+	for (int i = 0; i < D; i++) {
+		in.g.S[i] = m.S[i * m.nfs + f];
+		in.g.K[i] = tv.gK[i * m.nfs + f];
+		in.dv[i] = R(0);
+	}
+	in.g.w = m.w[f];
+	in.g.delta_mag = tv.g_delta_mag[f];
+	in.g.dmag_inv = tv.g_dmag_inv[f];
+	in.g.S_mag = SCHEME == 0 ? tv.g_Smag[f] : R(0);
+	if (in.ghost) {
+#pragma unroll
+		for (int i = 0; i < D; i++) in.dv[i] = m.d[i * m.nfs + f];
+	}
+}
+
 template <class R, int D, int SCHEME, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_tile_stage(DevMesh<R> m, TileView<R> tv, const R* __restrict__ q, R* __restrict__ qn, int tile0, R dt, R Ak, R Bk, int first, int res) {
 	using L = StagedLayout<D>;
@@ -218,6 +270,26 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_stage(DevMesh<R> m, TileView<
 	R* fl = st + (size_t)L::NS * smax;           // [NQ][fmax]
 	const TileDesc td = tv.tiles[tile0 + blockIdx.x];
 	const int ns = td.nt + td.nh;
+	const int nf = td.nfo + td.ninc;
+
+	// Pull the streamed rows of a tile that will be scheduled a little later into L2 (its cells' state and its own
+	// faces' constants), so that its staging phase meets L2 latency instead of HBM latency.
+	if (tv.prefetch_distance > 0 && (int)blockIdx.x + tv.prefetch_distance < tv.n_launch_tiles) {
+		const TileDesc pd = tv.tiles[tile0 + blockIdx.x + tv.prefetch_distance];
+		const int t = threadIdx.x;
+		l2_prefetch_rows<R>(q, m.ncs, NQ, pd.c0, pd.nt, t, NT);
+		l2_prefetch_rows<R>(m.dudx, m.ncs, D * D, pd.c0, pd.nt, t, NT);
+		l2_prefetch_rows<R>(m.dTdx, m.ncs, D, pd.c0, pd.nt, t, NT);
+		l2_prefetch_rows<R>(m.sigmaU, m.ncs, D, pd.c0, pd.nt, t, NT);
+		if (!first) l2_prefetch_rows<R>(m.dq, (size_t)m.n_cells, NQ, pd.c0, pd.nt, t, NT);
+		l2_prefetch_rows<R>(m.vol_inv, 0, 1, pd.c0, pd.nt, t, NT);
+		l2_prefetch_rows<R>(m.sigma, 0, 1, pd.c0, pd.nt, t, NT);
+		l2_prefetch_rows<R>(m.S, m.nfs, D, pd.fo0, pd.nfo, t, NT);
+		l2_prefetch_rows<R>(tv.gK, m.nfs, D, pd.fo0, pd.nfo, t, NT);
+		l2_prefetch_rows<R>(m.w, 0, 1, pd.fo0, pd.nfo, t, NT);
+		l2_prefetch_rows<R>(tv.g_delta_mag, 0, 1, pd.fo0, pd.nfo, t, NT);
+		l2_prefetch_rows<R>(tv.g_dmag_inv, 0, 1, pd.fo0, pd.nfo, t, NT);
+	}
 
 	// ---- A: stage cell states ------------------------------------------------------------------------
 	for (int i = threadIdx.x; i < ns; i += NT) {
@@ -229,92 +301,78 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_stage(DevMesh<R> m, TileView<
 	__syncthreads();
 
 	// ---- B: every face of the tile once ----------------------------------------------------------------
-	const int nf = td.nfo + td.ninc;
 	for (int lf = threadIdx.x; lf < nf; lf += NT) {
-		int f, lo, ln;
-		bool ghost = false;
-		if (lf < td.nfo) {
-			f = td.fo0 + lf;
-			lo = m.face_owner[f] - td.c0;
-			const unsigned v = tv.face_lneigh[f];
-			ln = (int)(v & 0x7fffu);
-			ghost = (v >> 15) != 0;
-		} else {
-			const int k = td.inc_off + lf - td.nfo;
-			f = tv.inc_face[k];
-			lo = tv.inc_lowner[k];
-			ln = m.face_neigh[f] - td.c0;
-		}
-		FaceGeo<R, D> g;
-		R dv[D];
-#pragma unroll
-		for (int i = 0; i < D; i++) {
-			g.S[i] = m.S[i * m.nfs + f];
-			g.K[i] = tv.gK[i * m.nfs + f];
-			dv[i] = R(0);
-		}
-		g.w = m.w[f];
-		g.delta_mag = tv.g_delta_mag[f];
-		g.dmag_inv = tv.g_dmag_inv[f];
-		g.S_mag = SCHEME == 0 ? tv.g_Smag[f] : R(0);
-		if (ghost) {
-#pragma unroll
-			for (int i = 0; i < D; i++) dv[i] = m.d[i * m.nfs + f];
-		}
+		FaceIn<R, D> cur;
+		fetch_face<R, D, SCHEME>(m, tv, td, lf, cur);
 		R rhs[NQ];
-		face_flux<R, D, SCHEME>(m.k, SmemSide<R, D>{st, smax, lo}, SmemSide<R, D>{st, smax, ln}, g, ghost, dv, rhs);
+		face_flux<R, D, SCHEME>(m.k, SmemSide<R, D>{st, smax, cur.lo}, SmemSide<R, D>{st, smax, cur.ln}, cur.g, cur.ghost, cur.dv, rhs);
 #pragma unroll
 		for (int i = 0; i < NQ; i++) fl[i * fmax + lf] = rhs[i];
 	}
-	__syncthreads();
 
 	// ---- C: ordered gather, sponge, RK update ----------------------------------------------------------
-	for (int lc = threadIdx.x; lc < td.nt; lc += NT) {
+	// Two threads share a cell when the tile leaves half the CTA idle: the ordered sums are per component, so
+	// splitting the components between threads does not change any result.
+	const int parts = (2 * td.nt <= NT) ? 2 : 1;
+	const int items = td.nt * parts;
+	bool synced = false;
+	for (int it = threadIdx.x; it < items || !synced; it += NT) {
+		const bool active = it < items;
+		const int lc = active ? (parts == 2 ? (it >> 1) : it) : 0;
+		const int part = parts == 2 ? (it & 1) : 0;
+		const int i0 = parts == 2 ? (part == 0 ? 0 : (NQ + 1) / 2) : 0;
+		const int i1 = parts == 2 ? (part == 0 ? (NQ + 1) / 2 : NQ) : NQ;
 		const int c = td.c0 + lc;
 		int e[kMaxSlots];
+		R dq[NQ], RES[NQ], vinv = R(0), sg = R(0);
+		if (active) {
 #pragma unroll
-		for (int s = 0; s < kMaxSlots; s++) e[s] = s < m.F ? (int)tv.csr_local[(size_t)s * m.n_cells + c] : 0;
-		R dq[NQ], RES[NQ];
+			for (int s = 0; s < kMaxSlots; s++) e[s] = s < m.F ? (int)tv.csr_local[(size_t)s * m.n_cells + c] : 0;
 #pragma unroll
-		for (int i = 0; i < NQ; i++) {
-			dq[i] = first ? R(0) : m.dq[(size_t)i * m.n_cells + c] * Ak;
-			RES[i] = R(0);
+			for (int i = 0; i < NQ; i++) {
+				dq[i] = (first || i < i0 || i >= i1) ? R(0) : m.dq[(size_t)i * m.n_cells + c] * Ak;
+				RES[i] = R(0);
+			}
+			vinv = m.vol_inv[c];
+			sg = m.sigma[c];
 		}
-		const R vinv = m.vol_inv[c];
-		const R sg = m.sigma[c];
+		if (!synced) {          // the loads above are in flight while the CTA waits for phase B to finish
+			__syncthreads();
+			synced = true;
+		}
+		if (!active) continue;
 #pragma unroll
 		for (int s = 0; s < kMaxSlots; s++) {
 			if (e[s] == 0) break;
-			const int lf = (e[s] > 0 ? e[s] : -e[s]) - 1;
+			const int lfc = (e[s] > 0 ? e[s] : -e[s]) - 1;
 			if (e[s] > 0) {
 #pragma unroll
-				for (int i = 0; i < NQ; i++) {
-					const R r = fl[i * fmax + lf];
-					if (res) RES[i] += r;
-					dq[i] += dt * r * vinv;
-				}
+				for (int i = 0; i < NQ; i++)
+					if (i >= i0 && i < i1) {
+						const R r = fl[i * fmax + lfc];
+						if (res) RES[i] += r;
+						dq[i] += dt * r * vinv;
+					}
 			} else {
 #pragma unroll
-				for (int i = 0; i < NQ; i++) {
-					const R r = fl[i * fmax + lf];
-					if (res) RES[i] -= r;
-					dq[i] -= dt * r * vinv;
-				}
+				for (int i = 0; i < NQ; i++)
+					if (i >= i0 && i < i1) {
+						const R r = fl[i * fmax + lfc];
+						if (res) RES[i] -= r;
+						dq[i] -= dt * r * vinv;
+					}
 			}
 		}
-		R cq[NQ];
 #pragma unroll
-		for (int i = 0; i < NQ; i++) cq[i] = st[i * smax + lc];
-		dq[0] += dt * sg * (m.k.rhoInf - cq[0]);
-#pragma unroll
-		for (int i = 0; i < D; i++) dq[i + 1] += dt * sg * (m.k.rhoUInf[i] - cq[i + 1]);
-		dq[D + 1] += dt * sg * (m.k.rhoEInf - cq[D + 1]);
-#pragma unroll
-		for (int i = 0; i < NQ; i++) {
-			m.dq[(size_t)i * m.n_cells + c] = dq[i];
-			qn[i * m.ncs + c] = cq[i] + Bk * dq[i];
-			if (res) m.RES[(size_t)i * m.n_cells + c] = RES[i];
-		}
+		for (int i = 0; i < NQ; i++)
+			if (i >= i0 && i < i1) {
+				const R cqi = st[i * smax + lc];
+				const R target = i == 0 ? m.k.rhoInf : (i == NQ - 1 ? m.k.rhoEInf : m.k.rhoUInf[i > 0 && i < NQ - 1 ? i - 1 : 0]);
+				dq[i] += dt * sg * (target - cqi);
+				m.dq[(size_t)i * m.n_cells + c] = dq[i];
+				qn[i * m.ncs + c] = cqi + Bk * dq[i];
+				if (res) m.RES[(size_t)i * m.n_cells + c] = RES[i];
+			}
 	}
 }
 
