@@ -45,7 +45,33 @@ constexpr int kBlock = 256;
 // ---------------------------------------------------------------------------------------------------
 // set_boundary_conditions (cfd_v0.cpp:1010-1133): ghost conservatives of wall / inlet / outlet faces
 // ---------------------------------------------------------------------------------------------------
-template <class R, int D> __global__ void __launch_bounds__(kBlock) k_set_bc(DevMesh<R> m, R* __restrict__ q) {
+// The three derived values that travel with the conservatives of a cell (tile kernels copy them instead of
+// recomputing them per staged cell): 1/rho, R*psi (cfdv0_solver.h:252-261) and, per scheme, the speed of sound
+// sqrt(gamma R psi) (M1, cfd_v0.cpp:2600-2603) or the total enthalpy rhoE/rho + R psi (M2, cfd_v0.cpp:1975-1978).
+template <class R, int D> __device__ __forceinline__ void store_derived(const Consts<R>& k, const R* cq, int scheme, R* __restrict__ drv, size_t ncs, size_t x) {
+	CellState<R, D> s;
+#pragma unroll
+	for (int i = 0; i < D + 2; i++) s.q[i] = cq[i];
+	if (scheme == 0)
+		derive_state<R, D, 0>(k, s);
+	else
+		derive_state<R, D, 1>(k, s);
+	drv[x] = s.rho_inv;
+	drv[ncs + x] = s.Rpsi;
+	drv[2 * ncs + x] = s.aux;
+}
+
+// derived values of cells [c0, c1) (after an upload, or when the scheme changes)
+template <class R, int D> __global__ void __launch_bounds__(kBlock) k_derive(DevMesh<R> m, const R* __restrict__ q, R* __restrict__ drv, int c0, int c1, int scheme) {
+	const int x = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+	if (x >= c1) return;
+	R cq[D + 2];
+#pragma unroll
+	for (int i = 0; i < D + 2; i++) cq[i] = q[i * m.ncs + x];
+	store_derived<R, D>(m.k, cq, scheme, drv, m.ncs, (size_t)x);
+}
+
+template <class R, int D> __global__ void __launch_bounds__(kBlock) k_set_bc(DevMesh<R> m, R* __restrict__ q, R* __restrict__ drv, int scheme) {
 	const int g = blockIdx.x * blockDim.x + threadIdx.x;
 	if (g >= m.n_bc) return;
 	const int b = m.bc_cell[g];
@@ -96,6 +122,7 @@ template <class R, int D> __global__ void __launch_bounds__(kBlock) k_set_bc(Dev
 	}
 #pragma unroll
 	for (int i = 0; i < D + 2; i++) q[i * m.ncs + gi] = gq[i];
+	store_derived<R, D>(m.k, gq, scheme, drv, m.ncs, gi);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -306,7 +333,7 @@ template <class R, int D> __global__ void __launch_bounds__(kBlock) k_pack(DevMe
 	}
 }
 
-template <class R, int D> __global__ void __launch_bounds__(kBlock) k_unpack(DevMesh<R> m, R* __restrict__ q, int n_recv, int mode, const R* __restrict__ buf) {
+template <class R, int D> __global__ void __launch_bounds__(kBlock) k_unpack(DevMesh<R> m, R* __restrict__ q, R* __restrict__ drv, int scheme, int n_recv, int mode, const R* __restrict__ buf) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n_recv) return;
 	constexpr int NQ = D + 2, NV = 2 * D * D + 2 * D;
@@ -314,8 +341,13 @@ template <class R, int D> __global__ void __launch_bounds__(kBlock) k_unpack(Dev
 	const size_t g = (size_t)m.n_cells + m.n_bc + i;
 	const R* o = buf + (size_t)i * spc;
 	if (mode & 1) {
+		R gq[NQ];
 #pragma unroll
-		for (int k = 0; k < NQ; k++) q[k * m.ncs + g] = *o++;
+		for (int k = 0; k < NQ; k++) {
+			gq[k] = *o++;
+			q[k * m.ncs + g] = gq[k];
+		}
+		store_derived<R, D>(m.k, gq, scheme, drv, m.ncs, g);
 	}
 	if (mode & 2) {
 #pragma unroll

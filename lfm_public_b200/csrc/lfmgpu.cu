@@ -108,6 +108,10 @@ struct lfmgpu_ctx {
 	DevMesh<double> md{};
 	DevMesh<float> mf{};
 	void* q[2] = {nullptr, nullptr};
+	void* drv[2] = {nullptr, nullptr};   // [3][ncs] derived values (1/rho, Rpsi, c|H) of q[b] (tile kernels)
+	bool drv_valid[2] = {false, false};  // real cells of drv[b] match q[b]
+	bool drv_dirty_next = false;         // a submesh of the running stage was advanced without writing drv
+	int drv_scheme = -1;                 // scheme the third derived value was computed for
 	int cur = 0;
 	unsigned updated_mask = 0;         // submeshes already advanced in the running stage
 	bool dq_zero = true;               // prepare_for_timestep seen, no stage yet
@@ -157,6 +161,7 @@ namespace {
 
 int tile_plan_build(lfmgpu_ctx* h, const lfmgpu_desc* ds);
 template <class R, int D> int tile_grad(lfmgpu_ctx* h, int sub);
+template <class R, int D> int ensure_drv(lfmgpu_ctx* h, int scheme);
 template <class R, int D> int tile_stage(lfmgpu_ctx* h, int sub, int scheme, R dt, R Ak, R Bk, int first, int res);
 
 struct LaunchScope {
@@ -260,6 +265,7 @@ template <class R> int build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
 		m.csr = p;
 	}
 	for (int b = 0; b < 2; b++) TRY(dev_alloc(h, &h->q[b], (size_t)NQ * h->ncs * sizeof(R)));
+	for (int b = 0; b < 2; b++) TRY(dev_alloc(h, &h->drv[b], (size_t)3 * h->ncs * sizeof(R)));
 	{
 		std::vector<R> tmp((size_t)NQ * h->ncs, R(0));
 		const R* q0 = (const R*)ds->q0;
@@ -346,7 +352,7 @@ void* q_of_vis(lfmgpu_ctx* h) { return ((h->updated_mask & 1u) || h->vis_on_cur)
 
 template <class R, int D> int t_set_bc(lfmgpu_ctx* h) {
 	if (!h->n_bc) return 0;
-	LAUNCH(h, "k_set_bc", h->s_main, (k_set_bc<R, D><<<blocks_for(h->n_bc), kBlock, 0, h->s_main>>>(h->mesh<R>(), (R*)h->q[h->cur])));
+	LAUNCH(h, "k_set_bc", h->s_main, (k_set_bc<R, D><<<blocks_for(h->n_bc), kBlock, 0, h->s_main>>>(h->mesh<R>(), (R*)h->q[h->cur], (R*)h->drv[h->cur], h->drv_scheme < 0 ? 1 : h->drv_scheme)));
 	CHECK_LAUNCH();
 	return 0;
 }
@@ -365,12 +371,28 @@ void sub_range(const lfmgpu_ctx* h, int sub, int& c0, int& c1, int& f0, int& f1)
 	}
 }
 
+// The tile kernels copy the derived values (1/rho, Rpsi, c|H) of every staged cell from drv[cur]: make them match
+// q[cur].  In steady state the previous stage kernel, set_bc and the halo unpack have written them already; after
+// an upload, a stage served by the unfused kernels or a change of scheme they are rebuilt here (ghosts included).
+template <class R, int D> int ensure_drv(lfmgpu_ctx* h, int scheme) {
+	const int want = scheme >= 0 ? scheme : (h->drv_scheme >= 0 ? h->drv_scheme : 1);
+	if (h->drv_valid[h->cur] && want == h->drv_scheme) return 0;
+	LAUNCH(h, "k_derive", h->s_main, (k_derive<R, D><<<blocks_for(h->n_tot), kBlock, 0, h->s_main>>>(h->mesh<R>(), (const R*)h->q[h->cur], (R*)h->drv[h->cur], 0, h->n_tot, want)));
+	CHECK_LAUNCH();
+	h->drv_valid[h->cur] = true;
+	h->drv_scheme = want;
+	return 0;
+}
+
 template <class R, int D> int t_vis(lfmgpu_ctx* h, int sub) {
 	int c0, c1, f0, f1;
 	sub_range(h, sub, c0, c1, f0, f1);
 	h->vis_on_cur = true;
 	if (c1 <= c0) return 0;
-	if (h->use_tiles && h->tiles.ready) return tile_grad<R, D>(h, sub);
+	if (h->use_tiles && h->tiles.ready) {
+		TRY((ensure_drv<R, D>(h, -1)));
+		return tile_grad<R, D>(h, sub);
+	}
 	LAUNCH(h, "k_grad_cell", h->s_main, (k_grad_cell<R, D><<<blocks_for(c1 - c0), kBlock, 0, h->s_main>>>(h->mesh<R>(), (const R*)h->q[h->cur], c0, c1)));
 	CHECK_LAUNCH();
 	return 0;
@@ -387,8 +409,10 @@ template <class R, int D> int t_rk_stage(lfmgpu_ctx* h, int sub, int scheme, int
 	const R Ak = (R)h->c.Ak[rk], Bk = (R)h->c.Bk[rk];
 	if (c1 > c0) {
 		if (h->use_tiles && h->tiles.ready) {
+			TRY((ensure_drv<R, D>(h, scheme)));
 			TRY((tile_stage<R, D>(h, sub, scheme, (R)dt, Ak, Bk, first, res)));
 		} else {
+			h->drv_dirty_next = true;
 			if (!m.flux) TRY(dev_alloc(h, (void**)&m.flux, (size_t)h->NQ * h->nfs * sizeof(R)));
 			if (f1 > f0) {
 				if (scheme == LFMGPU_SCHEME_M1)
@@ -412,6 +436,8 @@ template <class R, int D> int t_rk_stage(lfmgpu_ctx* h, int sub, int scheme, int
 	h->updated_mask |= (sub < 0) ? all : (1u << sub);
 	if (h->updated_mask == all) {
 		h->cur = 1 - h->cur;
+		h->drv_valid[h->cur] = !h->drv_dirty_next;
+		h->drv_dirty_next = false;
 		h->updated_mask = 0;
 		h->dq_zero = false;
 		h->stage_done = true;
@@ -433,7 +459,7 @@ template <class R, int D> int t_pack(lfmgpu_ctx* h, int step, cudaStream_t s) {
 template <class R, int D> int t_unpack(lfmgpu_ctx* h, int step) {
 	const int nr = h->recv_start[(size_t)h->n_nbr];
 	if (!nr) return 0;
-	LAUNCH(h, "k_unpack", h->s_main, (k_unpack<R, D><<<blocks_for(nr), kBlock, 0, h->s_main>>>(h->mesh<R>(), (R*)h->q[h->cur], nr, halo_mode(h, step), (const R*)h->recv_buf[step])));
+	LAUNCH(h, "k_unpack", h->s_main, (k_unpack<R, D><<<blocks_for(nr), kBlock, 0, h->s_main>>>(h->mesh<R>(), (R*)h->q[h->cur], (R*)h->drv[h->cur], h->drv_scheme < 0 ? 1 : h->drv_scheme, nr, halo_mode(h, step), (const R*)h->recv_buf[step])));
 	CHECK_LAUNCH();
 	return 0;
 }
@@ -479,18 +505,18 @@ template <class R> TileView<R> tile_view(lfmgpu_ctx* h, int smax, int fmax) {
 	TileView<R> v;
 	v.tiles = p.d_tiles;
 	v.halo_cell = p.d_halo_cell;
-	v.inc_face = p.d_inc_face;
-	v.inc_lowner = p.d_inc_lowner;
-	v.face_lneigh = p.d_face_lneigh;
+	v.f_idx = p.d_f_idx;
+	v.f_gface = p.d_f_gface;
+	v.fS = (const R*)p.d_fS;
+	v.fK = (const R*)p.d_fK;
+	v.fw = (const R*)p.d_fw;
+	v.fdm = (const R*)p.d_fdm;
+	v.fdi = (const R*)p.d_fdi;
+	v.fSmag = (const R*)p.d_fSmag;
+	v.T = p.T;
 	v.csr_local = p.d_csr_local;
-	v.gK = (const R*)p.d_gK;
-	v.g_delta_mag = (const R*)p.d_delta_mag;
-	v.g_dmag_inv = (const R*)p.d_dmag_inv;
-	v.g_Smag = (const R*)p.d_Smag;
 	v.smax = smax;
 	v.fmax = fmax;
-	v.prefetch_distance = h->prefetch_distance;
-	v.n_launch_tiles = 0;
 	return v;
 }
 
@@ -516,7 +542,7 @@ constexpr int kGradThreads = 128;
 
 
 template <class R, int D> size_t stage_smem(int smax, int fmax) { return ((size_t)StagedLayout<D>::NS * smax + (size_t)(D + 2) * fmax) * sizeof(R); }
-template <class R, int D> size_t grad_smem(int smax, int fmax) { return (size_t)(D + 1) * (smax + fmax) * sizeof(R) + (size_t)fmax * sizeof(uint32_t); }
+template <class R, int D> size_t grad_smem(int smax, int fmax) { return ((size_t)(D + 2) * smax + (size_t)(D + 1) * fmax) * sizeof(R) + (size_t)fmax * sizeof(uint32_t); }
 
 template <class R, int D> int tile_grad(lfmgpu_ctx* h, int sub) {
 	if (sub < 0) {   // every submesh: one launch each, so that each gets its own shared-memory size
@@ -529,7 +555,7 @@ template <class R, int D> int tile_grad(lfmgpu_ctx* h, int sub) {
 	const size_t smem = grad_smem<R, D>(smax, fmax);
 	auto kern = k_tile_grad<R, D, kGradThreads>;
 	if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	LAUNCH(h, "tile_grad", h->s_main, (kern<<<t1 - t0, kGradThreads, smem, h->s_main>>>(h->mesh<R>(), tile_view<R>(h, smax, fmax), (const R*)h->q[h->cur], t0)));
+	LAUNCH(h, "tile_grad", h->s_main, (kern<<<t1 - t0, kGradThreads, smem, h->s_main>>>(h->mesh<R>(), tile_view<R>(h, smax, fmax), (const R*)h->q[h->cur], (const R*)h->drv[h->cur], t0)));
 	CHECK_LAUNCH();
 	return 0;
 }
@@ -545,13 +571,13 @@ template <class R, int D, int SCHEME> int tile_stage_s(lfmgpu_ctx* h, int sub, R
 	size_t smem = stage_smem<R, D>(smax, fmax);
 	if (const char* e = getenv("LFMGPU_SMEM_PAD")) smem += (size_t)atoi(e) * 1024;   // experiment knob: fewer resident CTAs
 	TileView<R> tview = tile_view<R>(h, smax, fmax);
-	tview.n_launch_tiles = t1 - t0;
 #define LFM_STAGE_CFG(NT_, MB_) \
 	{ \
 		auto kern = k_tile_stage<R, D, SCHEME, NT_, MB_>; \
 		if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
 		LAUNCH(h, "tile_stage", h->s_main, \
-		       (kern<<<t1 - t0, NT_, smem, h->s_main>>>(h->mesh<R>(), tview, (const R*)h->q[h->cur], (R*)h->q[1 - h->cur], t0, dt, Ak, Bk, first, res))); \
+		       (kern<<<t1 - t0, NT_, smem, h->s_main>>>(h->mesh<R>(), tview, (const R*)h->q[h->cur], (const R*)h->drv[h->cur], (R*)h->q[1 - h->cur], (R*)h->drv[1 - h->cur], t0, dt, Ak, Bk, \
+		                                              first, res))); \
 	}
 	switch (h->stage_cfg) {
 		case 1: LFM_STAGE_CFG(128, 4) break;
@@ -559,6 +585,10 @@ template <class R, int D, int SCHEME> int tile_stage_s(lfmgpu_ctx* h, int sub, R
 		case 3: LFM_STAGE_CFG(128, 8) break;
 		case 4: LFM_STAGE_CFG(64, 8) break;
 		case 5: LFM_STAGE_CFG(64, 12) break;
+		case 6: LFM_STAGE_CFG(256, 2) break;
+		case 7: LFM_STAGE_CFG(192, 3) break;
+		case 8: LFM_STAGE_CFG(192, 4) break;
+		case 9: LFM_STAGE_CFG(128, 5) break;
 		default: LFM_STAGE_CFG(256, 3) break;
 	}
 #undef LFM_STAGE_CFG
@@ -569,22 +599,41 @@ template <class R, int D> int tile_stage(lfmgpu_ctx* h, int sub, int scheme, R d
 	return scheme == LFMGPU_SCHEME_M1 ? tile_stage_s<R, D, 0>(h, sub, dt, Ak, Bk, first, res) : tile_stage_s<R, D, 1>(h, sub, dt, Ak, Bk, first, res);
 }
 
+// per-mesh-face constants (temporary) -> the plan's tile-ordered face tables
 template <class R, int D> int tile_geo(lfmgpu_ctx* h) {
 	TilePlan& p = h->tiles;
-	TRY(dev_alloc(h, &p.d_gK, (size_t)D * h->nfs * sizeof(R)));
-	TRY(dev_alloc(h, &p.d_delta_mag, h->nfs * sizeof(R)));
-	TRY(dev_alloc(h, &p.d_dmag_inv, h->nfs * sizeof(R)));
-	TRY(dev_alloc(h, &p.d_Smag, h->nfs * sizeof(R)));
-	if (h->n_faces) {
-		k_face_geo<R, D><<<blocks_for(h->n_faces), kBlock>>>(h->mesh<R>(), (R*)p.d_gK, (R*)p.d_delta_mag, (R*)p.d_dmag_inv, (R*)p.d_Smag);
-		CHECK_LAUNCH();
-	}
-	return 0;
+	const size_t T = p.T;
+	R *gK = nullptr, *gdm = nullptr, *gdi = nullptr, *gSm = nullptr;
+	CU(cudaMalloc((void**)&gK, std::max<size_t>(16, (size_t)D * h->nfs * sizeof(R))));
+	CU(cudaMalloc((void**)&gdm, std::max<size_t>(16, h->nfs * sizeof(R))));
+	CU(cudaMalloc((void**)&gdi, std::max<size_t>(16, h->nfs * sizeof(R))));
+	CU(cudaMalloc((void**)&gSm, std::max<size_t>(16, h->nfs * sizeof(R))));
+	int rc = 0;
+	do {
+		if ((rc = dev_alloc(h, &p.d_fS, (size_t)D * T * sizeof(R)))) break;
+		if ((rc = dev_alloc(h, &p.d_fK, (size_t)D * T * sizeof(R)))) break;
+		if ((rc = dev_alloc(h, &p.d_fw, T * sizeof(R)))) break;
+		if ((rc = dev_alloc(h, &p.d_fdm, T * sizeof(R)))) break;
+		if ((rc = dev_alloc(h, &p.d_fdi, T * sizeof(R)))) break;
+		if ((rc = dev_alloc(h, &p.d_fSmag, T * sizeof(R)))) break;
+		if (h->n_faces && p.n_table) {
+			k_face_geo<R, D><<<blocks_for(h->n_faces), kBlock>>>(h->mesh<R>(), gK, gdm, gdi, gSm);
+			const unsigned nb = (unsigned)((p.n_table + kBlock - 1) / kBlock);
+			k_tile_face_tables<R, D><<<nb, kBlock>>>(h->mesh<R>(), gK, gdm, gdi, gSm, p.d_f_gface, p.n_table, T, (R*)p.d_fS, (R*)p.d_fK, (R*)p.d_fw, (R*)p.d_fdm, (R*)p.d_fdi, (R*)p.d_fSmag);
+			if (cudaDeviceSynchronize() != cudaSuccess) rc = fail("tile face tables: %s", cudaGetErrorString(cudaGetLastError()));
+		}
+	} while (0);
+	cudaFree(gK);
+	cudaFree(gdm);
+	cudaFree(gdi);
+	cudaFree(gSm);
+	return rc;
 }
 
-// Cuts every submesh into runs of `tile_cells` consecutive cells and derives, per tile, the halo cells, the
-// incoming faces and the tile-local indices the kernels use.  Returns 0 with plan.ready == false when the mesh
-// does not fit the shared-memory budget even with the smallest tile (the unfused kernels serve it then).
+// Cuts every submesh into runs of about `tile_cells` consecutive cells and derives, per tile, the halo cells, the
+// tile-ordered face list (own faces grouped by rank among the owner's faces, then the incoming faces) and the
+// tile-local indices the kernels use.  Returns 0 with plan.ready == false when the mesh does not fit the
+// shared-memory budget even with the smallest tile (the unfused kernels serve it then).
 int tile_plan_build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
 	TilePlan& p = h->tiles;
 	p.ready = false;
@@ -612,10 +661,16 @@ int tile_plan_build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
 	for (int c = 0; c < nc; c++) cfs[(size_t)c + 1] += cfs[(size_t)c];
 
 	std::vector<TileDesc> tiles;
-	std::vector<int> halo_cell, inc_face;
-	std::vector<uint16_t> inc_lowner, face_lneigh;
+	std::vector<int> halo_cell, f_gface;
+	std::vector<uint32_t> f_idx;
 	std::vector<int16_t> csr_local;
 	std::vector<int> stamp((size_t)h->n_tot, -1), local_of((size_t)h->n_tot, 0);
+	std::vector<int> own_pos, inc_rank((size_t)nc, 0);
+	std::vector<std::pair<int, int>> inc_sorted;   // (mesh face, tile-local index) of the tile's incoming faces
+	struct Inc {
+		int rank, ln, f;
+	};
+	std::vector<Inc> inc;
 	int TCs[LFMGPU_MAX_SUBMESH];
 	for (int s = 0; s < LFMGPU_MAX_SUBMESH; s++) TCs[s] = h->tile_cells;
 	int probe_id = -1;
@@ -623,9 +678,8 @@ int tile_plan_build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
 		int failed_sub = -1;
 		tiles.clear();
 		halo_cell.clear();
-		inc_face.clear();
-		inc_lowner.clear();
-		face_lneigh.assign((size_t)nf, 0);
+		f_gface.clear();
+		f_idx.clear();
 		csr_local.assign((size_t)F * nc, 0);
 		std::fill(stamp.begin(), stamp.end(), -1);
 		bool ok = true;
@@ -686,16 +740,18 @@ int tile_plan_build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
 					}
 				}
 				const int tid = (int)tiles.size();
-				TileDesc td;
+				TileDesc td{};
 				td.c0 = c0;
 				td.nt = c1 - c0;
-				td.fo0 = cfs[(size_t)c0];
-				td.nfo = cfs[(size_t)c1] - cfs[(size_t)c0];
+				const int fo0 = cfs[(size_t)c0];
+				td.nfo = cfs[(size_t)c1] - fo0;
 				td.halo_off = (int)halo_cell.size();
-				td.inc_off = (int)inc_face.size();
+				td.f_off = (int)f_gface.size();
 				// halo cells and incoming faces
+				inc.clear();
 				for (int c = c0; c < c1; c++) {
 					const int* row = &csr[(size_t)c * F];
+					int r = 0;
 					for (int k = 0; k < F && row[k]; k++) {
 						const int e = row[k], f = std::abs(e) - 1;
 						const int other = e > 0 ? ds->face_neigh[f] : ds->face_owner[f];
@@ -704,38 +760,51 @@ int tile_plan_build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
 							stamp[(size_t)other] = tid;
 							halo_cell.push_back(other);
 						}
-						if (e < 0) inc_face.push_back(f);
+						if (e < 0) inc.push_back({r++, c - c0, f});
 					}
 				}
 				std::sort(halo_cell.begin() + td.halo_off, halo_cell.end());
-				std::sort(inc_face.begin() + td.inc_off, inc_face.end());
 				td.nh = (int)halo_cell.size() - td.halo_off;
-				td.ninc = (int)inc_face.size() - td.inc_off;
+				td.ninc = (int)inc.size();
 				for (int i = 0; i < td.nh; i++) local_of[(size_t)halo_cell[(size_t)td.halo_off + i]] = td.nt + i;
-				if (td.nt + td.nh >= 32768 || td.nfo + td.ninc >= 32767) {
+				if (td.nt + td.nh >= 32768 || td.nfo + td.ninc >= 32767 || f_gface.size() + (size_t)td.nfo + td.ninc >= (size_t)0x7fffffff) {
 					ok = false;
 					failed_sub = s;
 					break;
 				}
-				// tile-local indices
-				for (int f = td.fo0; f < td.fo0 + td.nfo; f++) {
-					const int n = ds->face_neigh[f];
-					const int ln = (n >= c0 && n < c1) ? n - c0 : local_of[(size_t)n];
-					const bool ghost = n >= nc && n < nc + h->n_bc;
-					face_lneigh[(size_t)f] = (uint16_t)(ln | (ghost ? 0x8000 : 0));
+				auto staged = [&](int x) { return (x >= c0 && x < c1) ? x - c0 : local_of[(size_t)x]; };
+				// own faces: grouped by rank among the owner's faces, owners ascending inside a group
+				own_pos.assign((size_t)td.nfo, 0);
+				for (int r = 0, placed = 0; placed < td.nfo; r++)
+					for (int c = c0; c < c1; c++) {
+						const int f = cfs[(size_t)c] + r;
+						if (f >= cfs[(size_t)c + 1]) continue;
+						own_pos[(size_t)(f - fo0)] = placed++;
+						const int n = ds->face_neigh[f];
+						const bool ghost = n >= nc && n < nc + h->n_bc;
+						f_gface.push_back(f);
+						f_idx.push_back((uint32_t)(c - c0) | ((uint32_t)staged(n) << 16) | (ghost ? 0x80000000u : 0u));
+					}
+				// incoming faces: grouped by rank among the tile-side cell's incoming faces
+				std::sort(inc.begin(), inc.end(), [](const Inc& a, const Inc& b) { return a.rank != b.rank ? a.rank < b.rank : (a.ln != b.ln ? a.ln < b.ln : a.f < b.f); });
+				inc_sorted.clear();
+				for (int k = 0; k < td.ninc; k++) {
+					const int f = inc[(size_t)k].f;
+					f_gface.push_back(f);
+					f_idx.push_back((uint32_t)staged(ds->face_owner[f]) | ((uint32_t)inc[(size_t)k].ln << 16));
+					inc_sorted.push_back({f, td.nfo + k});
 				}
-				inc_lowner.resize(inc_face.size());
-				for (int k = 0; k < td.ninc; k++) inc_lowner[(size_t)td.inc_off + k] = (uint16_t)local_of[(size_t)ds->face_owner[inc_face[(size_t)td.inc_off + k]]];
+				std::sort(inc_sorted.begin(), inc_sorted.end());
 				for (int c = c0; c < c1; c++) {
 					const int* row = &csr[(size_t)c * F];
 					for (int k = 0; k < F && row[k]; k++) {
 						const int e = row[k], f = std::abs(e) - 1;
 						int lf;
-						if (f >= td.fo0 && f < td.fo0 + td.nfo) {
-							lf = f - td.fo0;
+						if (f >= fo0 && f < fo0 + td.nfo) {
+							lf = own_pos[(size_t)(f - fo0)];
 						} else {
-							const int* b = inc_face.data() + td.inc_off;
-							lf = td.nfo + (int)(std::lower_bound(b, b + td.ninc, f) - b);
+							auto it = std::lower_bound(inc_sorted.begin(), inc_sorted.end(), std::make_pair(f, -1));
+							lf = it->second;
 						}
 						csr_local[(size_t)k * nc + c] = (int16_t)(e > 0 ? lf + 1 : -(lf + 1));
 					}
@@ -747,9 +816,9 @@ int tile_plan_build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
 				tot_halo += td.nh;
 				tiles.push_back(td);
 			}
-			// keep shared-memory rows 16-byte aligned and bank friendly
-			smax = (smax + 3) / 4 * 4 + 1;
-			fmax = (fmax + 3) / 4 * 4 + 1;
+			// keep shared-memory rows 16-byte aligned
+			smax = (smax + 3) / 4 * 4;
+			fmax = (fmax + 3) / 4 * 4;
 			p.sub_smax[s] = smax;
 			p.sub_fmax[s] = fmax;
 			if (ok && ((size_t)NS * smax + (size_t)NQ * fmax) * es > budget) {
@@ -791,11 +860,14 @@ int tile_plan_build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
 		fmax = std::max(fmax, p.sub_fmax[s]);
 	}
 	p.smem_bytes = ((size_t)NS * smax + (size_t)NQ * fmax) * es;
+	p.n_table = f_gface.size();
+	p.T = pad32(p.n_table + 1);
 	TRY(upload<TileDesc>(h, &p.d_tiles, tiles.data(), tiles.size()));
 	TRY(upload<int>(h, &p.d_halo_cell, halo_cell.data(), halo_cell.size()));
-	TRY(upload<int>(h, &p.d_inc_face, inc_face.data(), inc_face.size()));
-	TRY(upload<uint16_t>(h, &p.d_inc_lowner, inc_lowner.data(), inc_lowner.size()));
-	TRY(upload<uint16_t>(h, &p.d_face_lneigh, face_lneigh.data(), face_lneigh.size()));
+	f_gface.resize(p.T, 0);
+	f_idx.resize(p.T, 0);
+	TRY(upload<int>(h, &p.d_f_gface, f_gface.data(), f_gface.size()));
+	TRY(upload<uint32_t>(h, &p.d_f_idx, f_idx.data(), f_idx.size()));
 	TRY(upload<int16_t>(h, &p.d_csr_local, csr_local.data(), csr_local.size()));
 	TRY(h->prec == 8 ? (D == 3 ? tile_geo<double, 3>(h) : tile_geo<double, 2>(h)) : (D == 3 ? tile_geo<float, 3>(h) : tile_geo<float, 2>(h)));
 	p.ready = true;
@@ -1004,8 +1076,10 @@ int lfmgpu_create(const lfmgpu_desc* ds, int device, lfmgpu_t* out) {
 		}
 		rc = h->prec == 8 ? build<double>(h, ds) : build<float>(h, ds);
 	}
+	h->stage_cfg = h->prec == 8 ? 6 : 0;   // fp64: 256 threads x 2 CTAs/SM (128 registers, no spills); fp32: 256 x 3
 	if (const char* e = getenv("LFMGPU_TILE_CELLS")) h->tile_cells = std::max(16, atoi(e));
 	if (const char* e = getenv("LFMGPU_STAGE_CFG")) h->stage_cfg = atoi(e);
+	if (const char* e = getenv("LFMGPU_USE_TILES")) h->use_tiles = atoi(e);
 	if (const char* e = getenv("LFMGPU_PREFETCH")) h->prefetch_distance = atoi(e);
 	if (const char* e = getenv("LFMGPU_TILE_SMEM")) h->tile_smem_budget = std::max(16, atoi(e)) * 1024;
 	if (!rc) rc = tile_plan_build(h, ds);
@@ -1052,6 +1126,7 @@ int lfmgpu_set_option(lfmgpu_t h, const char* name, int value) {
 	TRY(use(h));
 	if (!strcmp(name, "use_tiles")) {
 		h->use_tiles = value;
+		h->drv_valid[0] = h->drv_valid[1] = false;
 		return 0;
 	}
 	return fail("unknown option %s", name);
@@ -1254,6 +1329,7 @@ int lfmgpu_upload_q(lfmgpu_t h, const void* q, size_t bytes) {
 		for (int i = 0; i < h->NQ; i++) memcpy(tmp.data() + ((size_t)i * n + c) * es, (const char*)q + (c * h->NQ + i) * es, es);
 	for (int i = 0; i < h->NQ; i++) CU(cudaMemcpy((char*)h->q[h->cur] + (size_t)i * h->ncs * es, tmp.data() + (size_t)i * n * es, n * es, cudaMemcpyHostToDevice));
 	h->stage_done = false;
+	h->drv_valid[h->cur] = false;
 	return 0;
 }
 
@@ -1264,6 +1340,7 @@ int lfmgpu_upload_q_soa_async(lfmgpu_t h, const void* q, size_t bytes) {
 	const size_t es = (size_t)h->prec, n = (size_t)h->n_cells;
 	if (bytes != n * h->NQ * es) return fail("lfmgpu_upload_q_soa_async: expected %zu bytes", n * h->NQ * es);
 	CU(cudaMemcpy2DAsync(h->q[h->cur], h->ncs * es, q, n * es, n * es, (size_t)h->NQ, cudaMemcpyHostToDevice, h->s_main));
+	h->drv_valid[h->cur] = false;
 	return 0;
 }
 int lfmgpu_download_q_soa_async(lfmgpu_t h, void* q, size_t bytes) {

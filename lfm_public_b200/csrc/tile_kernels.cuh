@@ -1,18 +1,29 @@
-// Fused shared-memory tile kernels ("v2"): the production path of the per-iteration solve.
+// Fused shared-memory tile kernels ("v3"): the production path of the per-iteration solve.
 //
 // A tile is a run of consecutive cells in traversal order (never straddling a submesh).  One CTA owns one
 // tile per launch and
-//   A. stages the state of the tile's cells AND of every cell across one of their faces (the halo) in shared
-//      memory, evaluating the per-cell divisions / square roots once per staged cell,
-//   B. evaluates every face that touches a tile cell exactly once per tile: the tile's own faces (a contiguous
-//      face range, because faces are numbered by owner) plus the "incoming" faces owned by earlier cells outside
-//      the tile -- the only redundant flux evaluations, a surface-to-volume effect of the cell numbering,
+//   A. copies the state of the tile's cells AND of every cell across one of their faces (the halo) into shared
+//      memory with asynchronous copies (cp.async / LDGSTS): no registers are tied up, nothing is computed, every
+//      byte the tile needs from HBM is requested in the first few hundred cycles of the CTA.  The per-cell
+//      divisions / square roots the flux loops need (1/rho, R*psi, c or H) are NOT recomputed here: they travel
+//      with the conservatives as three "derived" values per cell, written by whoever writes the conservatives
+//      (the stage kernel's epilogue, set_boundary_conditions, the halo unpack; k_derive after an upload);
+//   B. evaluates every face that touches a tile cell exactly once per tile, reading both sides from shared
+//      memory and the face constants from the plan's TILE-ORDERED face tables (fully coalesced, no indirection;
+//      the first face's constants are requested before the wait of phase A, the next face's before the current
+//      face is evaluated).  Faces owned by earlier cells outside the tile ("incoming") are the only redundant
+//      flux evaluations, a surface-to-volume effect of the cell numbering;
 //   C. gathers per cell in ascending face id (the reference's summation order, kernels.cuh) from shared memory,
-//      adds the sponge term and applies the low-storage RK update, writing q_new / dq (and RES) coalesced.
+//      adds the sponge term, applies the low-storage RK update and writes q_new, the derived values of q_new and
+//      dq (and RES) coalesced.
 // Nothing but the final cell state goes back to HBM: face fluxes never leave the SM, prepare_for_RKstep's
 // `dq *= A_k` and zeroing passes are folded in.  The conservatives are double-buffered (q -> qn) because other
 // tiles still read the pre-stage state of this tile's cells (the reference's in-place sweep is a Jacobi update,
 // SURVEY.md 3.2).
+//
+// Inside a tile the faces are ordered for conflict-free shared-memory access: the tile's own faces grouped by
+// their rank among the owner's faces (so consecutive threads have consecutive owners and, on a structured
+// numbering, consecutive neighbours), then the incoming faces grouped the same way by their tile-side cell.
 //
 //   calc_VIS (cfd_v0.cpp:1744)                 -> k_tile_grad   (Green-Gauss gather from staged primitives)
 //   one_rk_step_M1/_M2 (cfd_v0.cpp:2530/1897)  -> k_tile_stage  (flux + gather + sponge + RK update)
@@ -28,21 +39,20 @@ namespace lfm {
 struct TileDesc {
 	int c0, nt;          // first cell, number of cells
 	int halo_off, nh;    // halo cells: halo_cell[halo_off .. +nh)
-	int fo0, nfo;        // own faces: [fo0, fo0+nfo)
-	int inc_off, ninc;   // incoming faces: inc_face[inc_off .. +ninc)
+	int f_off, nfo;      // tile faces: tables[f_off .. f_off+nfo+ninc), own faces first
+	int ninc, pad;
 };
 
 template <class R> struct TileView {
 	const TileDesc* tiles;
 	const int* halo_cell;            // global cell id of each halo entry (ascending inside a tile)
-	const int* inc_face;             // global face id of each incoming face (ascending inside a tile)
-	const uint16_t* inc_lowner;      // staged index of the incoming face's owner
-	const uint16_t* face_lneigh;     // [n_faces] staged index of the neighbour inside the owner's tile; bit 15: physical ghost
-	const int16_t* csr_local;        // [F][n_cells] +-(tile-local face index + 1), ascending face id, 0-padded
-	const R *gK, *g_delta_mag, *g_dmag_inv, *g_Smag;   // per-face constants: [D][nfs], [nfs], [nfs], [nfs]
+	const uint32_t* f_idx;           // [T] staged index of the owner | neighbour << 16 | physical-ghost flag << 31
+	const int* f_gface;              // [T] mesh face id (only read for physical-boundary faces: owner->ghost vector)
+	const R *fS, *fK;                // [D][T] area vector, non-orthogonal split K = S - delta
+	const R *fw, *fdm, *fdi, *fSmag; // [T] weight_linear, |delta|, 1/|d|, |S|
+	size_t T;                        // stride of the face tables
+	const int16_t* csr_local;        // [F][n_cells] +-(tile-local face index + 1), ascending mesh face id, 0-padded
 	int smax, fmax;                  // shared-memory strides of this launch (staged cells, faces)
-	int prefetch_distance;           // tiles ahead whose rows are pulled into L2 (0: off)
-	int n_launch_tiles;              // tiles of this launch
 };
 
 // per-face constants (make_geo) computed once on the device with the same expressions the flux loops use
@@ -62,6 +72,24 @@ template <class R, int D> __global__ void __launch_bounds__(kBlock) k_face_geo(D
 	g_delta_mag[f] = g.delta_mag;
 	g_dmag_inv[f] = g.dmag_inv;
 	g_Smag[f] = g.S_mag;
+}
+
+// mesh-face constants -> tile-ordered tables (entry j describes mesh face f_gface[j])
+template <class R, int D>
+__global__ void __launch_bounds__(kBlock) k_tile_face_tables(DevMesh<R> m, const R* gK, const R* g_delta_mag, const R* g_dmag_inv, const R* g_Smag, const int* __restrict__ f_gface, size_t n,
+                                                             size_t T, R* fS, R* fK, R* fw, R* fdm, R* fdi, R* fSmag) {
+	const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n) return;
+	const int f = f_gface[j];
+#pragma unroll
+	for (int i = 0; i < D; i++) {
+		fS[i * T + j] = m.S[i * m.nfs + f];
+		fK[i * T + j] = gK[i * m.nfs + f];
+	}
+	fw[j] = m.w[f];
+	fdm[j] = g_delta_mag[f];
+	fdi[j] = g_dmag_inv[f];
+	fSmag[j] = g_Smag[f];
 }
 
 template <int D> struct StagedLayout {
@@ -86,63 +114,87 @@ template <class R, int D> struct SmemSide {
 
 constexpr int kMaxSlots = 6;   // FACE_CNT of the reference is at most 6 (hexahedra)
 
+// asynchronous global -> shared copy of one element (LDGSTS); completion: cp_async_wait_all()
+template <class T> __device__ __forceinline__ void cp_async_elem(T* dst_smem, const T* src) {
+	const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+	if (sizeof(T) == 8)
+		asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+	else
+		asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+	asm volatile("cp.async.commit_group;" ::: "memory");
+	asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // ---------------------------------------------------------------------------------------------------
 // calc_VIS on one tile: dudx, dTdx, sigmaU of the tile's cells
-//   A. primitives (U, Rpsi) of tile + halo cells and (w, S, owner/neighbour staged index) of the tile's faces
-//      go to shared memory with independent, coalesced loads;
+//   A. (rhoU, 1/rho, Rpsi) of tile + halo cells and (S, w, owner/neighbour staged index) of the tile's faces go
+//      to shared memory with asynchronous copies;
 //   C. per cell, ordered Green-Gauss gather from shared memory, then the tau/sigmaU block of calc_VIS.
 // ---------------------------------------------------------------------------------------------------
-template <class R, int D, int NT> __global__ void __launch_bounds__(NT) k_tile_grad(DevMesh<R> m, TileView<R> tv, const R* __restrict__ q, int tile0) {
+template <class R, int D, int NT>
+__global__ void __launch_bounds__(NT) k_tile_grad(DevMesh<R> m, TileView<R> tv, const R* __restrict__ q, const R* __restrict__ drv, int tile0) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int smax = tv.smax, fmax = tv.fmax;
-	R* pr = reinterpret_cast<R*>(smem_raw);      // [D+1][smax]: U, Rpsi
-	R* fg = pr + (size_t)(D + 1) * smax;         // [D+1][fmax]: S, w
+	R* pr = reinterpret_cast<R*>(smem_raw);      // [D+2][smax]: rhoU, 1/rho, Rpsi
+	R* fg = pr + (size_t)(D + 2) * smax;         // [D+1][fmax]: S, w
 	uint32_t* fi = reinterpret_cast<uint32_t*>(fg + (size_t)(D + 1) * fmax);   // [fmax]: owner | neighbour << 16 (staged indices)
 	const TileDesc td = tv.tiles[tile0 + blockIdx.x];
 	const int ns = td.nt + td.nh;
 	const int nf = td.nfo + td.ninc;
 	for (int i = threadIdx.x; i < ns; i += NT) {
 		const int x = i < td.nt ? td.c0 + i : tv.halo_cell[td.halo_off + i - td.nt];
-		R cq[D + 2], U[D], rho_inv, Rpsi, T;
 #pragma unroll
-		for (int k = 0; k < D + 2; k++) cq[k] = q[k * m.ncs + x];
-		primitives<R, D>(m.k, cq, rho_inv, U, Rpsi, T);
-#pragma unroll
-		for (int k = 0; k < D; k++) pr[k * smax + i] = U[k];
-		pr[D * smax + i] = Rpsi;
+		for (int k = 0; k < D; k++) cp_async_elem(pr + k * smax + i, q + (size_t)(k + 1) * m.ncs + x);
+		cp_async_elem(pr + D * smax + i, drv + x);
+		cp_async_elem(pr + (D + 1) * smax + i, drv + m.ncs + x);
 	}
 	for (int lf = threadIdx.x; lf < nf; lf += NT) {
-		int f;
-		uint32_t lo, ln;
-		if (lf < td.nfo) {
-			f = td.fo0 + lf;
-			lo = (uint32_t)(m.face_owner[f] - td.c0);
-			ln = tv.face_lneigh[f] & 0x7fffu;
-		} else {
-			const int k = td.inc_off + lf - td.nfo;
-			f = tv.inc_face[k];
-			lo = tv.inc_lowner[k];
-			ln = (uint32_t)(m.face_neigh[f] - td.c0);
-		}
+		const size_t j = (size_t)td.f_off + lf;
 #pragma unroll
-		for (int k = 0; k < D; k++) fg[k * fmax + lf] = m.S[k * m.nfs + f];
-		fg[D * fmax + lf] = m.w[f];
-		fi[lf] = lo | (ln << 16);
+		for (int k = 0; k < D; k++) cp_async_elem(fg + k * fmax + lf, tv.fS + k * tv.T + j);
+		cp_async_elem(fg + D * fmax + lf, tv.fw + j);
+		cp_async_elem(fi + lf, tv.f_idx + j);
 	}
+	// what the gather needs from global memory, requested before the wait
+	const int lc0 = threadIdx.x;
+	int e0[kMaxSlots];
+	R vinv0 = R(0), cq0[D + 1];
+	if (lc0 < td.nt) {
+		const int c = td.c0 + lc0;
+#pragma unroll
+		for (int s = 0; s < kMaxSlots; s++) e0[s] = s < m.F ? (int)tv.csr_local[(size_t)s * m.n_cells + c] : 0;
+		vinv0 = m.vol_inv[c];
+#pragma unroll
+		for (int k = 0; k < D + 1; k++) cq0[k] = q[k * m.ncs + c];
+	}
+	cp_async_wait_all();
 	__syncthreads();
 	for (int lc = threadIdx.x; lc < td.nt; lc += NT) {
 		const int c = td.c0 + lc;
 		int e[kMaxSlots];
+		R vinv, cq[D + 1];
+		if (lc == lc0) {
 #pragma unroll
-		for (int s = 0; s < kMaxSlots; s++) e[s] = s < m.F ? (int)tv.csr_local[(size_t)s * m.n_cells + c] : 0;
-		const R vinv = m.vol_inv[c];
-		R cq[D + 2];
+			for (int s = 0; s < kMaxSlots; s++) e[s] = e0[s];
+			vinv = vinv0;
 #pragma unroll
-		for (int k = 0; k < D + 2; k++) cq[k] = q[k * m.ncs + c];
+			for (int k = 0; k < D + 1; k++) cq[k] = cq0[k];
+		} else {
+#pragma unroll
+			for (int s = 0; s < kMaxSlots; s++) e[s] = s < m.F ? (int)tv.csr_local[(size_t)s * m.n_cells + c] : 0;
+			vinv = m.vol_inv[c];
+#pragma unroll
+			for (int k = 0; k < D + 1; k++) cq[k] = q[k * m.ncs + c];
+		}
 		R cU[D];
+		{
+			const R cri = pr[D * smax + lc];
 #pragma unroll
-		for (int k = 0; k < D; k++) cU[k] = pr[k * smax + lc];
-		const R c_Rpsi = pr[D * smax + lc];
+			for (int k = 0; k < D; k++) cU[k] = pr[k * smax + lc] * cri;
+		}
+		const R c_Rpsi = pr[(D + 1) * smax + lc];
 		R dudx[D][D], dTdx[D];
 #pragma unroll
 		for (int i = 0; i < D; i++) {
@@ -156,11 +208,14 @@ template <class R, int D, int NT> __global__ void __launch_bounds__(NT) k_tile_g
 			const bool own = e[s] > 0;
 			const int lf = (own ? e[s] : -e[s]) - 1;
 			const uint32_t idx = fi[lf];
-			const int lo = own ? (int)(idx >> 16) : (int)(idx & 0xffffu);   // the other side
+			const int lo = own ? (int)((idx >> 16) & 0x7fffu) : (int)(idx & 0xffffu);   // the other side
 			R oU[D];
+			{
+				const R ori = pr[D * smax + lo];
 #pragma unroll
-			for (int k = 0; k < D; k++) oU[k] = pr[k * smax + lo];
-			const R o_Rpsi = pr[D * smax + lo];
+				for (int k = 0; k < D; k++) oU[k] = pr[k * smax + lo] * ori;
+			}
+			const R o_Rpsi = pr[(D + 1) * smax + lo];
 			const R w = fg[D * fmax + lf];
 			R face_U[D], face_T, sov[D];
 			if (own) {
@@ -179,8 +234,13 @@ template <class R, int D, int NT> __global__ void __launch_bounds__(NT) k_tile_g
 				dTdx[i] += face_T * sov[i];
 			}
 		}
-		R tauMC[D][D], sigmaU[D];
-		vis_cell_terms<R, D>(m.k, cq, dudx, tauMC, sigmaU);
+		// the tau / sigmaU block of calc_VIS (U = rhoU / rho: a true division, cfd_v0.cpp:1806-1857)
+		R Ud[D], tau[D][D], sigmaU[D];
+#pragma unroll
+		for (int i = 0; i < D; i++) Ud[i] = cq[i + 1] / cq[0];
+		stress<R, D>(m.k, dudx, tau);
+#pragma unroll
+		for (int i = 0; i < D; i++) sigmaU[i] = dotD<R, D>(Ud, tau[i]);
 #pragma unroll
 		for (int i = 0; i < D; i++) {
 #pragma unroll
@@ -194,74 +254,27 @@ template <class R, int D, int NT> __global__ void __launch_bounds__(NT) k_tile_g
 // ---------------------------------------------------------------------------------------------------
 // one_rk_step_M1/_M2 on one tile (flux, gather, sponge, RK update)
 // ---------------------------------------------------------------------------------------------------
-template <class R, int D> __device__ __forceinline__ void staged_store(R* st, int smax, int i, const CellState<R, D>& s) {
-	using L = StagedLayout<D>;
-#pragma unroll
-	for (int k = 0; k < D + 2; k++) st[k * smax + i] = s.q[k];
-	st[L::RHO_INV * smax + i] = s.rho_inv;
-	st[L::RPSI * smax + i] = s.Rpsi;
-	st[L::AUX * smax + i] = s.aux;
-#pragma unroll
-	for (int a = 0; a < D; a++) {
-#pragma unroll
-		for (int b = 0; b < D; b++) st[(L::DUDX + a * D + b) * smax + i] = s.dudx[a][b];
-		st[(L::DTDX + a) * smax + i] = s.dTdx[a];
-		st[(L::SIGMAU + a) * smax + i] = s.sigmaU[a];
-	}
-}
-
-// L2 prefetch of `nrows` rows (row r starts at base + r*stride elements) of `n` elements starting at element `first`:
-// one prefetch instruction per 128-byte line, spread over the CTA.  No registers are tied up and nothing waits.
-template <class T> __device__ __forceinline__ void l2_prefetch_rows(const T* base, size_t stride, int nrows, int first, int n, int tid, int nthreads) {
-	if (n <= 0) return;
-	const int lines = (n * (int)sizeof(T) + 127) / 128 + 1;
-	for (int i = tid; i < nrows * lines; i += nthreads) {
-		const int r = i / lines, l = i - r * lines;
-		const char* p = reinterpret_cast<const char*>(base + (size_t)r * stride + first) + (size_t)l * 128;
-		asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-	}
-}
-
-// everything phase B needs about one face, fetched from global memory ahead of its use
+// everything phase B needs about one face, fetched from the tile-ordered tables ahead of its use
 template <class R, int D> struct FaceIn {
-	int lo, ln;
-	bool ghost;
+	uint32_t idx;
 	FaceGeo<R, D> g;
-	R dv[D];
 };
-template <class R, int D, int SCHEME> __device__ __forceinline__ void fetch_face(const DevMesh<R>& m, const TileView<R>& tv, const TileDesc& td, int lf, FaceIn<R, D>& in) {
-	int f;
-	in.ghost = false;
-	if (lf < td.nfo) {
-		f = td.fo0 + lf;
-		in.lo = m.face_owner[f] - td.c0;
-		const unsigned v = tv.face_lneigh[f];
-		in.ln = (int)(v & 0x7fffu);
-		in.ghost = (v >> 15) != 0;
-	} else {
-		const int k = td.inc_off + lf - td.nfo;
-		f = tv.inc_face[k];
-		in.lo = tv.inc_lowner[k];
-		in.ln = m.face_neigh[f] - td.c0;
-	}
+template <class R, int D, int SCHEME> __device__ __forceinline__ void fetch_face(const TileView<R>& tv, size_t j, FaceIn<R, D>& in) {
+	in.idx = tv.f_idx[j];
 #pragma unroll
 	for (int i = 0; i < D; i++) {
-		in.g.S[i] = m.S[i * m.nfs + f];
-		in.g.K[i] = tv.gK[i * m.nfs + f];
-		in.dv[i] = R(0);
+		in.g.S[i] = tv.fS[i * tv.T + j];
+		in.g.K[i] = tv.fK[i * tv.T + j];
 	}
-	in.g.w = m.w[f];
-	in.g.delta_mag = tv.g_delta_mag[f];
-	in.g.dmag_inv = tv.g_dmag_inv[f];
-	in.g.S_mag = SCHEME == 0 ? tv.g_Smag[f] : R(0);
-	if (in.ghost) {
-#pragma unroll
-		for (int i = 0; i < D; i++) in.dv[i] = m.d[i * m.nfs + f];
-	}
+	in.g.w = tv.fw[j];
+	in.g.delta_mag = tv.fdm[j];
+	in.g.dmag_inv = tv.fdi[j];
+	in.g.S_mag = SCHEME == 0 ? tv.fSmag[j] : R(0);
 }
 
 template <class R, int D, int SCHEME, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) k_tile_stage(DevMesh<R> m, TileView<R> tv, const R* __restrict__ q, R* __restrict__ qn, int tile0, R dt, R Ak, R Bk, int first, int res) {
+__global__ void __launch_bounds__(NT, MINB)
+    k_tile_stage(DevMesh<R> m, TileView<R> tv, const R* __restrict__ q, const R* __restrict__ drv, R* __restrict__ qn, R* __restrict__ drvn, int tile0, R dt, R Ak, R Bk, int first, int res) {
 	using L = StagedLayout<D>;
 	constexpr int NQ = D + 2;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -272,51 +285,56 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_stage(DevMesh<R> m, TileView<
 	const int ns = td.nt + td.nh;
 	const int nf = td.nfo + td.ninc;
 
-	// Pull the streamed rows of a tile that will be scheduled a little later into L2 (its cells' state and its own
-	// faces' constants), so that its staging phase meets L2 latency instead of HBM latency.
-	if (tv.prefetch_distance > 0 && (int)blockIdx.x + tv.prefetch_distance < tv.n_launch_tiles) {
-		const TileDesc pd = tv.tiles[tile0 + blockIdx.x + tv.prefetch_distance];
-		const int t = threadIdx.x;
-		l2_prefetch_rows<R>(q, m.ncs, NQ, pd.c0, pd.nt, t, NT);
-		l2_prefetch_rows<R>(m.dudx, m.ncs, D * D, pd.c0, pd.nt, t, NT);
-		l2_prefetch_rows<R>(m.dTdx, m.ncs, D, pd.c0, pd.nt, t, NT);
-		l2_prefetch_rows<R>(m.sigmaU, m.ncs, D, pd.c0, pd.nt, t, NT);
-		if (!first) l2_prefetch_rows<R>(m.dq, (size_t)m.n_cells, NQ, pd.c0, pd.nt, t, NT);
-		l2_prefetch_rows<R>(m.vol_inv, 0, 1, pd.c0, pd.nt, t, NT);
-		l2_prefetch_rows<R>(m.sigma, 0, 1, pd.c0, pd.nt, t, NT);
-		l2_prefetch_rows<R>(m.S, m.nfs, D, pd.fo0, pd.nfo, t, NT);
-		l2_prefetch_rows<R>(tv.gK, m.nfs, D, pd.fo0, pd.nfo, t, NT);
-		l2_prefetch_rows<R>(m.w, 0, 1, pd.fo0, pd.nfo, t, NT);
-		l2_prefetch_rows<R>(tv.g_delta_mag, 0, 1, pd.fo0, pd.nfo, t, NT);
-		l2_prefetch_rows<R>(tv.g_dmag_inv, 0, 1, pd.fo0, pd.nfo, t, NT);
-	}
-
-	// ---- A: stage cell states ------------------------------------------------------------------------
+	// ---- A: request the cell states (asynchronous copies, no registers) ----------------------------------
 	for (int i = threadIdx.x; i < ns; i += NT) {
 		const int x = i < td.nt ? td.c0 + i : tv.halo_cell[td.halo_off + i - td.nt];
-		CellState<R, D> s;
-		load_state<R, D, SCHEME>(m, q, x, s);
-		staged_store<R, D>(st, smax, i, s);
+#pragma unroll
+		for (int k = 0; k < NQ; k++) cp_async_elem(st + k * smax + i, q + (size_t)k * m.ncs + x);
+#pragma unroll
+		for (int k = 0; k < 3; k++) cp_async_elem(st + (L::RHO_INV + k) * smax + i, drv + (size_t)k * m.ncs + x);
+#pragma unroll
+		for (int k = 0; k < D * D; k++) cp_async_elem(st + (L::DUDX + k) * smax + i, m.dudx + (size_t)k * m.ncs + x);
+#pragma unroll
+		for (int k = 0; k < D; k++) {
+			cp_async_elem(st + (L::DTDX + k) * smax + i, m.dTdx + (size_t)k * m.ncs + x);
+			cp_async_elem(st + (L::SIGMAU + k) * smax + i, m.sigmaU + (size_t)k * m.ncs + x);
+		}
 	}
+	// the first face's constants travel while the copies land
+	FaceIn<R, D> cur;
+	if ((int)threadIdx.x < nf) fetch_face<R, D, SCHEME>(tv, (size_t)td.f_off + threadIdx.x, cur);
+	cp_async_wait_all();
 	__syncthreads();
 
 	// ---- B: every face of the tile once ----------------------------------------------------------------
 	for (int lf = threadIdx.x; lf < nf; lf += NT) {
-		FaceIn<R, D> cur;
-		fetch_face<R, D, SCHEME>(m, tv, td, lf, cur);
+		FaceIn<R, D> nxt;
+		if (lf + NT < nf) fetch_face<R, D, SCHEME>(tv, (size_t)td.f_off + lf + NT, nxt);
+		const int lo = (int)(cur.idx & 0xffffu), ln = (int)((cur.idx >> 16) & 0x7fffu);
+		const bool ghost = (cur.idx >> 31) != 0;
+		R dv[D];
+#pragma unroll
+		for (int i = 0; i < D; i++) dv[i] = R(0);
+		if (ghost) {
+			const int f = tv.f_gface[(size_t)td.f_off + lf];
+#pragma unroll
+			for (int i = 0; i < D; i++) dv[i] = m.d[i * m.nfs + f];
+		}
 		R rhs[NQ];
-		face_flux<R, D, SCHEME>(m.k, SmemSide<R, D>{st, smax, cur.lo}, SmemSide<R, D>{st, smax, cur.ln}, cur.g, cur.ghost, cur.dv, rhs);
+		face_flux<R, D, SCHEME>(m.k, SmemSide<R, D>{st, smax, lo}, SmemSide<R, D>{st, smax, ln}, cur.g, ghost, dv, rhs);
 #pragma unroll
 		for (int i = 0; i < NQ; i++) fl[i * fmax + lf] = rhs[i];
+		if (lf + NT < nf) cur = nxt;
 	}
 
 	// ---- C: ordered gather, sponge, RK update ----------------------------------------------------------
 	// Two threads share a cell when the tile leaves half the CTA idle: the ordered sums are per component, so
-	// splitting the components between threads does not change any result.
+	// splitting the components between threads does not change any result.  The pair sits in adjacent lanes.
 	const int parts = (2 * td.nt <= NT) ? 2 : 1;
 	const int items = td.nt * parts;
-	bool synced = false;
-	for (int it = threadIdx.x; it < items || !synced; it += NT) {
+	const int rounds = items > NT ? (items + NT - 1) / NT : 1;   // the same trip count for every thread of the CTA
+	for (int r = 0; r < rounds; r++) {
+		const int it = threadIdx.x + r * NT;
 		const bool active = it < items;
 		const int lc = active ? (parts == 2 ? (it >> 1) : it) : 0;
 		const int part = parts == 2 ? (it & 1) : 0;
@@ -330,49 +348,62 @@ __global__ void __launch_bounds__(NT, MINB) k_tile_stage(DevMesh<R> m, TileView<
 			for (int s = 0; s < kMaxSlots; s++) e[s] = s < m.F ? (int)tv.csr_local[(size_t)s * m.n_cells + c] : 0;
 #pragma unroll
 			for (int i = 0; i < NQ; i++) {
-				dq[i] = (first || i < i0 || i >= i1) ? R(0) : m.dq[(size_t)i * m.n_cells + c] * Ak;
+				dq[i] = (first || i < i0 || i >= i1) ? R(0) : m.dq[(size_t)i * m.n_cells + c];
 				RES[i] = R(0);
 			}
 			vinv = m.vol_inv[c];
 			sg = m.sigma[c];
 		}
-		if (!synced) {          // the loads above are in flight while the CTA waits for phase B to finish
-			__syncthreads();
-			synced = true;
-		}
-		if (!active) continue;
+		if (r == 0) __syncthreads();   // the loads above are in flight while the CTA waits for phase B to finish
+		if (active) {
 #pragma unroll
-		for (int s = 0; s < kMaxSlots; s++) {
-			if (e[s] == 0) break;
-			const int lfc = (e[s] > 0 ? e[s] : -e[s]) - 1;
-			if (e[s] > 0) {
+			for (int i = 0; i < NQ; i++) dq[i] *= Ak;      // prepare_for_RKstep (0 * Ak == 0 for the components of the partner)
 #pragma unroll
-				for (int i = 0; i < NQ; i++)
-					if (i >= i0 && i < i1) {
-						const R r = fl[i * fmax + lfc];
-						if (res) RES[i] += r;
-						dq[i] += dt * r * vinv;
-					}
-			} else {
+			for (int s = 0; s < kMaxSlots; s++) {
+				if (e[s] == 0) break;
+				const int lfc = (e[s] > 0 ? e[s] : -e[s]) - 1;
+				if (e[s] > 0) {
 #pragma unroll
-				for (int i = 0; i < NQ; i++)
-					if (i >= i0 && i < i1) {
-						const R r = fl[i * fmax + lfc];
-						if (res) RES[i] -= r;
-						dq[i] -= dt * r * vinv;
-					}
+					for (int i = 0; i < NQ; i++)
+						if (i >= i0 && i < i1) {
+							const R r_ = fl[i * fmax + lfc];
+							if (res) RES[i] += r_;
+							dq[i] += dt * r_ * vinv;
+						}
+				} else {
+#pragma unroll
+					for (int i = 0; i < NQ; i++)
+						if (i >= i0 && i < i1) {
+							const R r_ = fl[i * fmax + lfc];
+							if (res) RES[i] -= r_;
+							dq[i] -= dt * r_ * vinv;
+						}
+				}
 			}
-		}
 #pragma unroll
-		for (int i = 0; i < NQ; i++)
-			if (i >= i0 && i < i1) {
-				const R cqi = st[i * smax + lc];
-				const R target = i == 0 ? m.k.rhoInf : (i == NQ - 1 ? m.k.rhoEInf : m.k.rhoUInf[i > 0 && i < NQ - 1 ? i - 1 : 0]);
-				dq[i] += dt * sg * (target - cqi);
-				m.dq[(size_t)i * m.n_cells + c] = dq[i];
-				qn[i * m.ncs + c] = cqi + Bk * dq[i];
-				if (res) m.RES[(size_t)i * m.n_cells + c] = RES[i];
-			}
+			for (int i = 0; i < NQ; i++)
+				if (i >= i0 && i < i1) {
+					const R cqi = st[i * smax + lc];
+					const R target = i == 0 ? m.k.rhoInf : (i == NQ - 1 ? m.k.rhoEInf : m.k.rhoUInf[i > 0 && i < NQ - 1 ? i - 1 : 0]);
+					dq[i] += dt * sg * (target - cqi);
+					m.dq[(size_t)i * m.n_cells + c] = dq[i];
+					const R qi = cqi + Bk * dq[i];
+					qn[i * m.ncs + c] = qi;
+					st[i * smax + lc] = qi;      // only this cell's own threads touch these slots after phase B
+					if (res) m.RES[(size_t)i * m.n_cells + c] = RES[i];
+				}
+		}
+		__syncwarp();   // the partner lane's components of q_new are visible (every lane of the warp gets here)
+		if (active && part == 0) {
+			// derived values of the NEW state travel with it (1/rho, R*psi, c or H): the next stage copies them
+			CellState<R, D> s;
+#pragma unroll
+			for (int i = 0; i < NQ; i++) s.q[i] = st[i * smax + lc];
+			derive_state<R, D, SCHEME>(m.k, s);
+			drvn[c] = s.rho_inv;
+			drvn[m.ncs + c] = s.Rpsi;
+			drvn[2 * m.ncs + c] = s.aux;
+		}
 	}
 }
 
@@ -385,13 +416,13 @@ struct TilePlan {
 	size_t smem_bytes = 0;            // largest k_tile_stage request
 	double halo_face_ratio = 0.0;     // incoming faces / own faces (redundant flux evaluations)
 	double halo_cell_ratio = 0.0;     // halo cells / tile cells
+	size_t T = 0, n_table = 0;        // stride and entries of the tile-ordered face tables
 	TileDesc* d_tiles = nullptr;
 	int* d_halo_cell = nullptr;
-	int* d_inc_face = nullptr;
-	uint16_t* d_inc_lowner = nullptr;
-	uint16_t* d_face_lneigh = nullptr;
+	uint32_t* d_f_idx = nullptr;
+	int* d_f_gface = nullptr;
 	int16_t* d_csr_local = nullptr;
-	void *d_gK = nullptr, *d_delta_mag = nullptr, *d_dmag_inv = nullptr, *d_Smag = nullptr;
+	void *d_fS = nullptr, *d_fK = nullptr, *d_fw = nullptr, *d_fdm = nullptr, *d_fdi = nullptr, *d_fSmag = nullptr;
 };
 
 }  // namespace lfm

@@ -15,7 +15,8 @@ from ._ctypes_defs import (FIELD_DQ, FIELD_DTDX, FIELD_DUDX, FIELD_PAVG, FIELD_P
                            FIELD_SIGMAU, FIELD_TAUMC)
 
 _LIB = None
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liblfmgpu.so")
+# LFMGPU_LIB: alternative build of the same library (tuning experiments: e.g. an --fmad=true build)
+LIB_PATH = os.environ.get("LFMGPU_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "liblfmgpu.so")
 
 # every symbol include/lfmgpu.h declares (tests check that the library exports all of them)
 SYMBOLS = [
