@@ -168,6 +168,12 @@ int lfmgpu_comm_init_local(lfmgpu_t h, int rank, int n_ranks, const lfmgpu_t* pe
 int lfmgpu_halo_send_count(lfmgpu_t h, int comm_step, size_t* n_scalars);
 int lfmgpu_download_send_buffer(lfmgpu_t h, int comm_step, void* dst, size_t dst_bytes);
 
+/* Host-staged halo for callers that keep their own transport (the reference's MPI_env, or more ranks than GPUs):
+ * pack on the device into `dst` (same layout as lfmgpu_download_send_buffer, blocking) / upload a received buffer
+ * (neighbours concatenated in nbr order, the reference's m_RecvBuf*List layout) and unpack it into the MPI ghosts. */
+int lfmgpu_halo_pack_to_host(lfmgpu_t h, int comm_step, void* dst, size_t dst_bytes);
+int lfmgpu_halo_unpack_from_host(lfmgpu_t h, int comm_step, const void* src, size_t bytes);
+
 /* ---- introspection --------------------------------------------------------------------------------- */
 int lfmgpu_launch_count(lfmgpu_t h, uint64_t* n);            /* kernels launched by this handle so far  */
 /* average device time (ms) per launch and launch count of the kernels whose name starts with `prefix`, measured

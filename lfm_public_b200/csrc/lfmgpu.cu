@@ -571,9 +571,9 @@ template <class R, int D, int SCHEME> int tile_stage_s(lfmgpu_ctx* h, int sub, R
 	size_t smem = stage_smem<R, D>(smax, fmax);
 	if (const char* e = getenv("LFMGPU_SMEM_PAD")) smem += (size_t)atoi(e) * 1024;   // experiment knob: fewer resident CTAs
 	TileView<R> tview = tile_view<R>(h, smax, fmax);
-#define LFM_STAGE_CFG(NT_, MB_) \
+#define LFM_STAGE_CFG(NT_, MB_, ...) \
 	{ \
-		auto kern = k_tile_stage<R, D, SCHEME, NT_, MB_>; \
+		auto kern = k_tile_stage<R, D, SCHEME, NT_, MB_, ##__VA_ARGS__>; \
 		if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
 		LAUNCH(h, "tile_stage", h->s_main, \
 		       (kern<<<t1 - t0, NT_, smem, h->s_main>>>(h->mesh<R>(), tview, (const R*)h->q[h->cur], (const R*)h->drv[h->cur], (R*)h->q[1 - h->cur], (R*)h->drv[1 - h->cur], t0, dt, Ak, Bk, \
@@ -589,6 +589,12 @@ template <class R, int D, int SCHEME> int tile_stage_s(lfmgpu_ctx* h, int sub, R
 		case 7: LFM_STAGE_CFG(192, 3) break;
 		case 8: LFM_STAGE_CFG(192, 4) break;
 		case 9: LFM_STAGE_CFG(128, 5) break;
+		case 10: LFM_STAGE_CFG(256, 3, 0) break;
+		case 11: LFM_STAGE_CFG(256, 2, 0) break;
+		case 12: LFM_STAGE_CFG(512, 1) break;
+		case 13: LFM_STAGE_CFG(256, 3, 0, 1) break;
+		case 14: LFM_STAGE_CFG(256, 2, 0, 1) break;
+		case 15: LFM_STAGE_CFG(384, 2, 0, 1) break;
 		default: LFM_STAGE_CFG(256, 3) break;
 	}
 #undef LFM_STAGE_CFG
@@ -1426,6 +1432,33 @@ int lfmgpu_download_send_buffer(lfmgpu_t h, int comm_step, void* dst, size_t dst
 	if (dst_bytes < bytes) return fail("destination too small");
 	CU(cudaStreamSynchronize(h->s_comm));
 	if (bytes) CU(cudaMemcpy(dst, h->send_buf[comm_step], bytes, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+// Host-staged halo (more ranks than GPUs, or a caller that keeps its own transport such as the reference's MPI_env):
+// pack on the device and hand the packed buffer to the host / take a received buffer from the host and unpack it.
+int lfmgpu_halo_pack_to_host(lfmgpu_t h, int comm_step, void* dst, size_t dst_bytes) {
+	TRY(use(h));
+	if (comm_step < 0 || comm_step > 1) return fail("comm_step must be 0 or 1");
+	if (h->n_nbr == 0) return 0;
+	CU(cudaEventRecord(h->ev_ready, h->s_main));
+	CU(cudaStreamWaitEvent(h->s_comm, h->ev_ready, 0));
+	TRY(DISPATCH(h, t_pack, h, comm_step, h->s_comm));
+	const size_t bytes = h->last_send_count[comm_step] * (size_t)h->prec;
+	if (dst_bytes < bytes) return fail("lfmgpu_halo_pack_to_host: destination too small (%zu < %zu)", dst_bytes, bytes);
+	if (bytes) CU(cudaMemcpyAsync(dst, h->send_buf[comm_step], bytes, cudaMemcpyDeviceToHost, h->s_comm));
+	CU(cudaStreamSynchronize(h->s_comm));
+	return 0;
+}
+int lfmgpu_halo_unpack_from_host(lfmgpu_t h, int comm_step, const void* src, size_t bytes) {
+	TRY(use(h));
+	if (comm_step < 0 || comm_step > 1) return fail("comm_step must be 0 or 1");
+	if (h->n_nbr == 0) return 0;
+	const size_t want = (size_t)h->recv_start[(size_t)h->n_nbr] * halo_spc(h, comm_step) * (size_t)h->prec;
+	if (bytes < want) return fail("lfmgpu_halo_unpack_from_host: source too small (%zu < %zu)", bytes, want);
+	if (want) CU(cudaMemcpyAsync(h->recv_buf[comm_step], src, want, cudaMemcpyHostToDevice, h->s_main));
+	TRY(DISPATCH(h, t_unpack, h, comm_step));
+	CU(cudaStreamSynchronize(h->s_main));   // the caller may reuse its buffer as soon as this returns
 	return 0;
 }
 

@@ -272,7 +272,67 @@ template <class R, int D, int SCHEME> __device__ __forceinline__ void fetch_face
 	in.g.S_mag = SCHEME == 0 ? tv.fSmag[j] : R(0);
 }
 
-template <class R, int D, int SCHEME, int NT, int MINB>
+// Phase C of the stage kernel for components [I0, I1) of tile cell lc: dq = A_k dq + sum_faces(+-dt rhs / V) + sponge,
+// q_new = q + B_k dq (prepare_for_RKstep's scaling, the scatter of cfd_v0.cpp:2792-2804 as an ordered gather, sponge
+// 2810-2814, update 2819-2822).  `x -= y` is evaluated as `x += (-y)`: bit-identical, and branch-free on the sign.
+// The global loads are issued before the CTA barrier that closes phase B (sync != 0) so they travel during the wait.
+template <class R, int D, int I0, int I1>
+__device__ __forceinline__ void gather_update(const DevMesh<R>& m, const TileView<R>& tv, const TileDesc& td, R* st, const R* fl, int smax, int fmax, R* __restrict__ qn, int lc, bool active,
+                                              bool sync, R dt, R Ak, R Bk, int first, int res) {
+	constexpr int NQ = D + 2;
+	const int c = td.c0 + (active ? lc : 0);
+	int e[kMaxSlots];
+	R dq[NQ], vinv = R(0), sg = R(0);
+#pragma unroll
+	for (int s = 0; s < kMaxSlots; s++) e[s] = 0;
+#pragma unroll
+	for (int i = 0; i < NQ; i++) dq[i] = R(0);
+	if (active) {
+#pragma unroll
+		for (int s = 0; s < kMaxSlots; s++)
+			if (s < m.F) e[s] = (int)tv.csr_local[(size_t)s * m.n_cells + c];
+		if (!first) {
+#pragma unroll
+			for (int i = I0; i < I1; i++) dq[i] = m.dq[(size_t)i * m.n_cells + c];
+		}
+		vinv = m.vol_inv[c];
+		sg = m.sigma[c];
+	}
+	if (sync) __syncthreads();
+	if (!active) return;
+	R RES[NQ];
+#pragma unroll
+	for (int i = I0; i < I1; i++) {
+		dq[i] *= Ak;
+		RES[i] = R(0);
+	}
+#pragma unroll
+	for (int s = 0; s < kMaxSlots; s++) {
+		if (e[s] == 0) break;
+		const bool own = e[s] > 0;
+		const int lfc = (own ? e[s] : -e[s]) - 1;
+#pragma unroll
+		for (int i = I0; i < I1; i++) {
+			const R v = fl[i * fmax + lfc];
+			const R rr = own ? v : -v;
+			if (res) RES[i] += rr;
+			dq[i] += dt * rr * vinv;
+		}
+	}
+#pragma unroll
+	for (int i = I0; i < I1; i++) {
+		const R cqi = st[i * smax + lc];
+		const R target = i == 0 ? m.k.rhoInf : (i == NQ - 1 ? m.k.rhoEInf : m.k.rhoUInf[i > 0 && i < NQ - 1 ? i - 1 : 0]);
+		dq[i] += dt * sg * (target - cqi);
+		m.dq[(size_t)i * m.n_cells + c] = dq[i];
+		const R qi = cqi + Bk * dq[i];
+		qn[i * m.ncs + c] = qi;
+		st[i * smax + lc] = qi;      // only this cell's own threads touch these slots after phase B
+		if (res) m.RES[(size_t)i * m.n_cells + c] = RES[i];
+	}
+}
+
+template <class R, int D, int SCHEME, int NT, int MINB, int PF = 1, int SPLITB = 0>
 __global__ void __launch_bounds__(NT, MINB)
     k_tile_stage(DevMesh<R> m, TileView<R> tv, const R* __restrict__ q, const R* __restrict__ drv, R* __restrict__ qn, R* __restrict__ drvn, int tile0, R dt, R Ak, R Bk, int first, int res) {
 	using L = StagedLayout<D>;
@@ -307,9 +367,40 @@ __global__ void __launch_bounds__(NT, MINB)
 	__syncthreads();
 
 	// ---- B: every face of the tile once ----------------------------------------------------------------
+	if (SPLITB) {
+		// two lighter passes (fewer live registers, more resident warps): inviscid flux, then the viscous terms
+		for (int lf = threadIdx.x; lf < nf; lf += NT) {
+			const int lo = (int)(cur.idx & 0xffffu), ln = (int)((cur.idx >> 16) & 0x7fffu);
+			R rhs[NQ], dv[D];
+#pragma unroll
+			for (int i = 0; i < D; i++) dv[i] = R(0);
+			face_flux<R, D, SCHEME, SmemSide<R, D>, SmemSide<R, D>, 1>(m.k, SmemSide<R, D>{st, smax, lo}, SmemSide<R, D>{st, smax, ln}, cur.g, false, dv, rhs);
+#pragma unroll
+			for (int i = 0; i < NQ; i++) fl[i * fmax + lf] = rhs[i];
+			if (lf + NT < nf) fetch_face<R, D, SCHEME>(tv, (size_t)td.f_off + lf + NT, cur);
+		}
+		for (int lf = threadIdx.x; lf < nf; lf += NT) {
+			fetch_face<R, D, 1>(tv, (size_t)td.f_off + lf, cur);
+			const int lo = (int)(cur.idx & 0xffffu), ln = (int)((cur.idx >> 16) & 0x7fffu);
+			const bool ghost = (cur.idx >> 31) != 0;
+			R rhs[NQ], dv[D];
+#pragma unroll
+			for (int i = 0; i < D; i++) dv[i] = R(0);
+			if (ghost) {
+				const int f = tv.f_gface[(size_t)td.f_off + lf];
+#pragma unroll
+				for (int i = 0; i < D; i++) dv[i] = m.d[i * m.nfs + f];
+			}
+#pragma unroll
+			for (int i = 0; i < NQ; i++) rhs[i] = fl[i * fmax + lf];
+			face_flux<R, D, SCHEME, SmemSide<R, D>, SmemSide<R, D>, 2>(m.k, SmemSide<R, D>{st, smax, lo}, SmemSide<R, D>{st, smax, ln}, cur.g, ghost, dv, rhs);
+#pragma unroll
+			for (int i = 1; i < NQ; i++) fl[i * fmax + lf] = rhs[i];
+		}
+	} else
 	for (int lf = threadIdx.x; lf < nf; lf += NT) {
 		FaceIn<R, D> nxt;
-		if (lf + NT < nf) fetch_face<R, D, SCHEME>(tv, (size_t)td.f_off + lf + NT, nxt);
+		if (PF && lf + NT < nf) fetch_face<R, D, SCHEME>(tv, (size_t)td.f_off + lf + NT, nxt);
 		const int lo = (int)(cur.idx & 0xffffu), ln = (int)((cur.idx >> 16) & 0x7fffu);
 		const bool ghost = (cur.idx >> 31) != 0;
 		R dv[D];
@@ -324,86 +415,43 @@ __global__ void __launch_bounds__(NT, MINB)
 		face_flux<R, D, SCHEME>(m.k, SmemSide<R, D>{st, smax, lo}, SmemSide<R, D>{st, smax, ln}, cur.g, ghost, dv, rhs);
 #pragma unroll
 		for (int i = 0; i < NQ; i++) fl[i * fmax + lf] = rhs[i];
-		if (lf + NT < nf) cur = nxt;
+		if (lf + NT < nf) {
+			if (PF)
+				cur = nxt;
+			else
+				fetch_face<R, D, SCHEME>(tv, (size_t)td.f_off + lf + NT, cur);
+		}
 	}
 
 	// ---- C: ordered gather, sponge, RK update ----------------------------------------------------------
-	// Two threads share a cell when the tile leaves half the CTA idle: the ordered sums are per component, so
-	// splitting the components between threads does not change any result.  The pair sits in adjacent lanes.
-	const int parts = (2 * td.nt <= NT) ? 2 : 1;
-	const int items = td.nt * parts;
-	const int rounds = items > NT ? (items + NT - 1) / NT : 1;   // the same trip count for every thread of the CTA
+	// When the tile leaves half the CTA idle the components of a cell are split between the two halves of the CTA
+	// (warp-uniform, so neither half pays for the other's components): the ordered sums are per component, so the
+	// split does not change any result.
+	const bool split = 2 * td.nt <= NT;
+	const int rounds = split ? 1 : (td.nt + NT - 1) / NT;   // the same trip count for every thread of the CTA
 	for (int r = 0; r < rounds; r++) {
-		const int it = threadIdx.x + r * NT;
-		const bool active = it < items;
-		const int lc = active ? (parts == 2 ? (it >> 1) : it) : 0;
-		const int part = parts == 2 ? (it & 1) : 0;
-		const int i0 = parts == 2 ? (part == 0 ? 0 : (NQ + 1) / 2) : 0;
-		const int i1 = parts == 2 ? (part == 0 ? (NQ + 1) / 2 : NQ) : NQ;
+		constexpr int H = (NQ + 1) / 2;
+		const int part = split ? (threadIdx.x >= NT / 2 ? 1 : 0) : 2;           // 0: [0,H)  1: [H,NQ)  2: all
+		const int lc = split ? (int)threadIdx.x - (part ? NT / 2 : 0) : (int)threadIdx.x + r * NT;
+		const bool active = lc < td.nt;
+		if (part == 0)
+			gather_update<R, D, 0, H>(m, tv, td, st, fl, smax, fmax, qn, lc, active, r == 0, dt, Ak, Bk, first, res);
+		else if (part == 1)
+			gather_update<R, D, H, NQ>(m, tv, td, st, fl, smax, fmax, qn, lc, active, r == 0, dt, Ak, Bk, first, res);
+		else
+			gather_update<R, D, 0, NQ>(m, tv, td, st, fl, smax, fmax, qn, lc, active, r == 0, dt, Ak, Bk, first, res);
+	}
+	// derived values of the NEW state travel with it (1/rho, R*psi, c or H): the next stage copies them
+	__syncthreads();
+	for (int lc = threadIdx.x; lc < td.nt; lc += NT) {
+		CellState<R, D> s;
+#pragma unroll
+		for (int i = 0; i < NQ; i++) s.q[i] = st[i * smax + lc];
+		derive_state<R, D, SCHEME>(m.k, s);
 		const int c = td.c0 + lc;
-		int e[kMaxSlots];
-		R dq[NQ], RES[NQ], vinv = R(0), sg = R(0);
-		if (active) {
-#pragma unroll
-			for (int s = 0; s < kMaxSlots; s++) e[s] = s < m.F ? (int)tv.csr_local[(size_t)s * m.n_cells + c] : 0;
-#pragma unroll
-			for (int i = 0; i < NQ; i++) {
-				dq[i] = (first || i < i0 || i >= i1) ? R(0) : m.dq[(size_t)i * m.n_cells + c];
-				RES[i] = R(0);
-			}
-			vinv = m.vol_inv[c];
-			sg = m.sigma[c];
-		}
-		if (r == 0) __syncthreads();   // the loads above are in flight while the CTA waits for phase B to finish
-		if (active) {
-#pragma unroll
-			for (int i = 0; i < NQ; i++) dq[i] *= Ak;      // prepare_for_RKstep (0 * Ak == 0 for the components of the partner)
-#pragma unroll
-			for (int s = 0; s < kMaxSlots; s++) {
-				if (e[s] == 0) break;
-				const int lfc = (e[s] > 0 ? e[s] : -e[s]) - 1;
-				if (e[s] > 0) {
-#pragma unroll
-					for (int i = 0; i < NQ; i++)
-						if (i >= i0 && i < i1) {
-							const R r_ = fl[i * fmax + lfc];
-							if (res) RES[i] += r_;
-							dq[i] += dt * r_ * vinv;
-						}
-				} else {
-#pragma unroll
-					for (int i = 0; i < NQ; i++)
-						if (i >= i0 && i < i1) {
-							const R r_ = fl[i * fmax + lfc];
-							if (res) RES[i] -= r_;
-							dq[i] -= dt * r_ * vinv;
-						}
-				}
-			}
-#pragma unroll
-			for (int i = 0; i < NQ; i++)
-				if (i >= i0 && i < i1) {
-					const R cqi = st[i * smax + lc];
-					const R target = i == 0 ? m.k.rhoInf : (i == NQ - 1 ? m.k.rhoEInf : m.k.rhoUInf[i > 0 && i < NQ - 1 ? i - 1 : 0]);
-					dq[i] += dt * sg * (target - cqi);
-					m.dq[(size_t)i * m.n_cells + c] = dq[i];
-					const R qi = cqi + Bk * dq[i];
-					qn[i * m.ncs + c] = qi;
-					st[i * smax + lc] = qi;      // only this cell's own threads touch these slots after phase B
-					if (res) m.RES[(size_t)i * m.n_cells + c] = RES[i];
-				}
-		}
-		__syncwarp();   // the partner lane's components of q_new are visible (every lane of the warp gets here)
-		if (active && part == 0) {
-			// derived values of the NEW state travel with it (1/rho, R*psi, c or H): the next stage copies them
-			CellState<R, D> s;
-#pragma unroll
-			for (int i = 0; i < NQ; i++) s.q[i] = st[i * smax + lc];
-			derive_state<R, D, SCHEME>(m.k, s);
-			drvn[c] = s.rho_inv;
-			drvn[m.ncs + c] = s.Rpsi;
-			drvn[2 * m.ncs + c] = s.aux;
-		}
+		drvn[c] = s.rho_inv;
+		drvn[m.ncs + c] = s.Rpsi;
+		drvn[2 * m.ncs + c] = s.aux;
 	}
 }
 

@@ -26,7 +26,7 @@ SYMBOLS = [
     "lfmgpu_forces", "lfmgpu_residual", "lfmgpu_step", "lfmgpu_warmup", "lfmgpu_step_multi", "lfmgpu_allreduce",
     "lfmgpu_set_option", "lfmgpu_download", "lfmgpu_upload_q", "lfmgpu_upload_q_soa_async", "lfmgpu_download_q_soa_async",
     "lfmgpu_host_alloc", "lfmgpu_host_free", "lfmgpu_nccl_unique_id", "lfmgpu_comm_init_nccl", "lfmgpu_comm_init_local",
-    "lfmgpu_halo_send_count", "lfmgpu_download_send_buffer", "lfmgpu_launch_count", "lfmgpu_enable_kernel_timing",
+    "lfmgpu_halo_send_count", "lfmgpu_download_send_buffer", "lfmgpu_halo_pack_to_host", "lfmgpu_halo_unpack_from_host", "lfmgpu_launch_count", "lfmgpu_enable_kernel_timing",
     "lfmgpu_kernel_time", "lfmgpu_tile_info", "lfmgpu_event_record", "lfmgpu_event_elapsed_ms",
 ]
 
@@ -51,6 +51,7 @@ def lib():
             "lfmgpu_upload_q_soa_async": [vp, vp, sz], "lfmgpu_download_q_soa_async": [vp, vp, sz],
             "lfmgpu_host_alloc": [C.POINTER(vp), sz], "lfmgpu_host_free": [vp], "lfmgpu_nccl_unique_id": [vp],
             "lfmgpu_comm_init_nccl": [vp, vp, i, i], "lfmgpu_comm_init_local": [vp, i, i, vp],
+            "lfmgpu_halo_pack_to_host": [vp, i, vp, sz], "lfmgpu_halo_unpack_from_host": [vp, i, vp, sz],
             "lfmgpu_halo_send_count": [vp, i, C.POINTER(sz)], "lfmgpu_download_send_buffer": [vp, i, vp, sz],
             "lfmgpu_launch_count": [vp, C.POINTER(C.c_uint64)], "lfmgpu_enable_kernel_timing": [vp, i],
             "lfmgpu_kernel_time": [vp, C.c_char_p, C.POINTER(d), C.POINTER(C.c_uint64)],
