@@ -78,8 +78,8 @@ def block_fields(m, n, blocks, rank):
     return dict(p=p, T=T, U=U, alpha=alpha), h
 
 
-def build_rank_case(n, blocks, rank, n_ranks, precision, scheme, tile=None):
-    m = meshgen.hex_block((n, n, n), blocks, rank, tile=tile)
+def build_rank_case(n, blocks, rank, n_ranks, precision, scheme, tile=None, brick_order="morton"):
+    m = meshgen.hex_block((n, n, n), blocks, rank, tile=tile, brick_order=brick_order)
     fields, h = block_fields(m, (n, n, n), blocks, rank)
     if "new_of_old" in m:                                  # fields were built in lexicographic order: renumber them too
         perm = m["new_of_old"]
@@ -225,7 +225,7 @@ def workload_config(args, n_gpus):
     bl = BLOCKS[n_gpus]
     return {"workload": f"synthetic 3D hex polyMesh weak scaling, {n}^3 = {n ** 3} cells per GPU, blocks {bl[0]}x{bl[1]}x{bl[2]} "
                         f"({n ** 3 * n_gpus} cells), {'M2' if args.scheme == 1 else 'M1'} + laminar viscous + sponge, RK5, commType 2",
-            "cell_numbering": f"bricks {args.tile}", "cells_per_gpu": n ** 3, "total_cells": n ** 3 * n_gpus, "rk_stages_per_step": 5,
+            "cell_numbering": f"bricks {args.tile}, {args.brick_order} brick order", "cells_per_gpu": n ** 3, "total_cells": n ** 3 * n_gpus, "rk_stages_per_step": 5,
             "l2_policy": "inputs larger than L2 (about 7 GB of state per GPU at 256^3), no flush"}
 
 
@@ -252,7 +252,7 @@ def run_gpu_arm(args):
     blocks = BLOCKS[world]
     t0 = time.time()
     tile = tuple(int(x) for x in args.tile.split(",")) if args.tile and args.tile != "none" else None
-    case, dt = build_rank_case(args.n, blocks, rank, world, args.precision, args.scheme, tile)
+    case, dt = build_rank_case(args.n, blocks, rank, world, args.precision, args.scheme, tile, args.brick_order)
     if world > 1:
         host_api.exchange_distributed(case, rank)
     else:
@@ -395,6 +395,7 @@ def main():
     ap.add_argument("--scheme", type=int, default=1, choices=[0, 1], help="0 = M1, 1 = M2")
     ap.add_argument("--use-tiles", type=int, default=1)
     ap.add_argument("--tile", default="8,4,4", help="brick numbering of the synthetic mesh (renumberMesh analogue), or 'none'")
+    ap.add_argument("--brick-order", default="morton", choices=["lex", "morton"], help="order of the bricks in the numbering")
     ap.add_argument("--ref-n", type=int, default=64, help="cells per side of the CPU sample")
     ap.add_argument("--ref-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -275,23 +275,41 @@ def tri_prism_box(nx, ny, lengths=(1.0, 1.0), shuffle_seed=None):
 # renumbering (RCM stop-gap for hpathRenumber; reference: examples/*/constant/renumberMeshDict)
 # ------------------------------------------------------------------------------------------------
 
-def blocked_order(ni, nj, nk, tile, offset=(0, 0, 0)):
+def _morton3(x, y, z):
+    """Z-order key of non-negative integer triples (up to 21 bits each)."""
+    def spread(v):
+        v = v.astype(np.uint64) & np.uint64(0x1fffff)
+        v = (v | (v << np.uint64(32))) & np.uint64(0x1f00000000ffff)
+        v = (v | (v << np.uint64(16))) & np.uint64(0x1f0000ff0000ff)
+        v = (v | (v << np.uint64(8))) & np.uint64(0x100f00f00f00f00f)
+        v = (v | (v << np.uint64(4))) & np.uint64(0x10c30c30c30c30c3)
+        v = (v | (v << np.uint64(2))) & np.uint64(0x1249249249249249)
+        return v
+    return spread(x) | (spread(y) << np.uint64(1)) | (spread(z) << np.uint64(2))
+
+
+def blocked_order(ni, nj, nk, tile, offset=(0, 0, 0), brick_order="lex"):
     """Cell permutation new_of_old for a logical (ni,nj,nk) block: cells are numbered tile by tile (tiles of
     tile=(ti,tj,tk) cells, i fastest inside a tile and across tiles), the structured analogue of the reference's
     renumberMesh pre-processing (hpathRenumber / CuthillMcKee): consecutive cell ids form compact 3D bricks, which
     is what the shared-memory tile kernels want.  offset shifts the tile lattice (offset=(1,1,1) aligns the bricks
-    with the interior submesh, whose first cell is (1,1,1))."""
+    with the interior submesh, whose first cell is (1,1,1)).  brick_order: "lex" = bricks in lexicographic order,
+    "morton" = bricks along a Z-order curve, which keeps the bricks across EVERY face of a brick close in the numbering
+    (with "lex" the z-neighbour brick is a whole xy-slab away, beyond the reach of the L2 on large blocks)."""
     ti, tj, tk = tile
     c = np.arange(ni * nj * nk, dtype=np.int64)
     i, j, k = c % ni, (c // ni) % nj, c // (ni * nj)
     io, jo, ko = i + (ti - offset[0]) % ti, j + (tj - offset[1]) % tj, k + (tk - offset[2]) % tk
-    order = np.lexsort((io % ti, jo % tj, ko % tk, io // ti, jo // tj, ko // tk))   # last key is primary
+    if brick_order == "morton":
+        order = np.lexsort((io % ti, jo % tj, ko % tk, _morton3(io // ti, jo // tj, ko // tk)))
+    else:
+        order = np.lexsort((io % ti, jo % tj, ko % tk, io // ti, jo // tj, ko // tk))   # last key is primary
     new_of_old = np.empty(len(c), dtype=np.int64)
     new_of_old[order] = c
     return new_of_old
 
 
-def hex_block(n, blocks=(1, 1, 1), rank=0, cell_size=None, z_cyclic=None, tile=None):
+def hex_block(n, blocks=(1, 1, 1), rank=0, cell_size=None, z_cyclic=None, tile=None, brick_order="lex"):
     """The processor mesh of ONE rank of a block-decomposed hex box, generated without ever building the global
     mesh (weak-scaling runs: 16.8 M cells per rank).  n = (nx,ny,nz) cells of this block, blocks = (bx,by,bz),
     rank = bi + bx*(bj + by*bk) as in block_assignment().  Physically identical to
@@ -353,7 +371,7 @@ def hex_block(n, blocks=(1, 1, 1), rank=0, cell_size=None, z_cyclic=None, tile=N
         patch_id[side == s] = side_patch[s]
     new_of_old = None
     if tile is not None:
-        new_of_old = blocked_order(nx, ny, nz, tile, offset=(1, 1, 1))
+        new_of_old = blocked_order(nx, ny, nz, tile, offset=(1, 1, 1), brick_order=brick_order)
         a = new_of_old[a]
         b = np.where(b >= 0, new_of_old[np.maximum(b, 0)], -1)
     # cyclic twins must share the same offset inside their patches: order the two z planes by (i,j) == gid within a plane

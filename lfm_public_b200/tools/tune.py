@@ -24,13 +24,14 @@ def main():
     ap.add_argument("--scheme", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--tile", default="8,4,4")
+    ap.add_argument("--brick-order", default="morton")
     ap.add_argument("--set", action="append", default=[], help="NAME=v1,v2,... (environment knob and its values)")
     args = ap.parse_args()
     import bench
     from lfm_public_b200 import gpu_api
     tile = tuple(int(x) for x in args.tile.split(",")) if args.tile != "none" else None
     t0 = time.time()
-    case, dt = bench.build_rank_case(args.n, (1, 1, 1), 0, 1, args.precision, args.scheme, tile)
+    case, dt = bench.build_rank_case(args.n, (1, 1, 1), 0, 1, args.precision, args.scheme, tile, args.brick_order)
     case.finish()
     print(f"# setup {time.time() - t0:.1f} s", flush=True)
     names, values = [], []

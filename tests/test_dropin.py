@@ -1,0 +1,100 @@
+"""Drop-in proof: the reference's OWN executable path -- info/lfm_solve.cpp main(), Mesh::initialize / initializeSolver /
+solve (src/mesh_solver.cpp), the reference's init code and output writers, compiled from the sources where they lie --
+with the solver class swapped for CFDv0_solver_gpu (lfm_public_b200/host/gpu_solver.h), against the unmodified
+reference binary on the same case: written fields and every halo message must be identical.
+
+oracle/_ref/lfm_solve_gpu is built by `make -C oracle dropin` where /root/reference exists (it travels to the GPU box
+prebuilt, like oracle/_ref/lfm_solve_ref)."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import common
+from common import CASES, N_STEPS
+
+pytestmark = pytest.mark.gpu
+
+GPU_BIN = os.path.join(common.ROOT, "oracle", "_ref", "lfm_solve_gpu")
+GPU_BIN_SP = os.path.join(common.ROOT, "oracle", "_ref", "lfm_solve_gpu_sp")
+needs_bins = pytest.mark.skipif(not (os.path.exists(GPU_BIN) and common.have_ref()), reason="drop-in / reference binaries not built")
+
+
+def run_gpu_binary(case_dir, o, sp=False, halo=None, timeout=600):
+    env = dict(os.environ)
+    env["LFM_WRITE_PRECISION"] = "17"
+    if halo:
+        env["LFM_GPU_HALO"] = halo
+    args = [GPU_BIN_SP if sp else GPU_BIN]
+    if o["parallel"]:
+        env["LFM_MPI_NP"] = str(o["n_ranks"])
+        args.append("-p")
+        d = os.path.join(case_dir, "dump")
+        os.makedirs(d, exist_ok=True)
+        env["LFM_MPI_DUMP_DIR"] = d
+    out = subprocess.run(args, cwd=case_dir, env=env, capture_output=True, text=True, timeout=timeout)
+    if "Simulation finished successfully" not in out.stdout:
+        raise RuntimeError("drop-in run failed:\n" + out.stdout[-3000:] + out.stderr[-3000:])
+    return out.stdout
+
+
+def _pair(name, tmp_path, sp=False, **override):
+    ref_dir, gpu_dir = str(tmp_path / "ref"), str(tmp_path / "gpu")
+    m, o = common.build_case(name, ref_dir, doublePrecision=not sp, **override)
+    shutil.copytree(ref_dir, gpu_dir)
+    out_ref = common.run_reference(ref_dir, o, sp=sp)
+    out_gpu = run_gpu_binary(gpu_dir, o, sp=sp, halo="host")
+    return o, ref_dir, gpu_dir, out_ref, out_gpu
+
+
+@needs_bins
+@pytest.mark.parametrize("name", ["quad2d_m1", "quad2d_m1_p4", "quad2d_m2_p2_packed", "tri2d_m2", "hex3d_m2_p4", "ogrid3d_m2"])
+def test_dropin_fields_identical_fp64(name, tmp_path):
+    o, ref_dir, gpu_dir, out_ref, out_gpu = _pair(name, tmp_path)
+    D = o["dimension"]
+    t = o["deltaT"] * N_STEPS
+    ref = common.read_reference_q(ref_dir, o, t, D)
+    gpu = common.read_reference_q(gpu_dir, o, t, D)
+    assert len(ref) == len(gpu) == o["n_ranks"]
+    for r in range(o["n_ranks"]):
+        assert ref[r]["rho"].std() > 0
+        for k in ("rho", "U", "E", "p"):
+            assert np.array_equal(ref[r][k], gpu[r][k]), f"{name} rank {r} field {k}: rel max {common.rel_max(ref[r][k], gpu[r][k]):.3e}"
+    # the CFL the time loop prints every step (compute_cfl through the GPU path)
+    cfl = lambda s: [float(l.split("CFL:")[1].split()[0]) for l in s.splitlines() if "CFL:" in l]
+    assert len(cfl(out_ref)) == N_STEPS and np.allclose(cfl(out_ref), cfl(out_gpu), rtol=1e-9, atol=0)
+
+
+@needs_bins
+@pytest.mark.parametrize("name", ["quad2d_m1_p4", "quad2d_m2_p2_packed", "hex3d_m2_p4"])
+def test_dropin_halo_messages_identical(name, tmp_path):
+    """Host-staged halo: what the GPU path hands to the reference's MPI_env equals what the reference packs, message by message."""
+    o, ref_dir, gpu_dir, _, _ = _pair(name, tmp_path)
+    n = 0
+    for src in range(o["n_ranks"]):
+        for dst in range(o["n_ranks"]):
+            p = os.path.join(ref_dir, "dump", f"send_r{src}_to{dst}.bin")
+            if not os.path.exists(p):
+                continue
+            a = common.read_dump(ref_dir, src, dst, np.float64)
+            b = common.read_dump(gpu_dir, src, dst, np.float64)
+            assert len(a) == len(b), f"{src}->{dst}: {len(a)} vs {len(b)} messages"
+            for i, ((ta, xa), (tb, xb)) in enumerate(zip(a, b)):
+                assert ta == tb and xa.tobytes() == xb.tobytes(), f"{name} {src}->{dst} message {i} differs"
+                n += 1
+    assert n > 0
+
+
+@needs_bins
+@pytest.mark.skipif(not (os.path.exists(GPU_BIN_SP) and common.have_ref(sp=True)), reason="single-precision binaries not built")
+def test_dropin_fp32(tmp_path):
+    o, ref_dir, gpu_dir, _, _ = _pair("hex3d_m2_p4", tmp_path, sp=True)
+    D = o["dimension"]
+    t = o["deltaT"] * N_STEPS
+    ref = common.read_reference_q(ref_dir, o, t, D)
+    gpu = common.read_reference_q(gpu_dir, o, t, D)
+    for r in range(o["n_ranks"]):
+        for k in ("rho", "U", "E", "p"):
+            assert common.rel_max(ref[r][k], gpu[r][k]) <= 1e-5, f"rank {r} field {k}"
