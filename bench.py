@@ -340,6 +340,9 @@ def run_gpu_arm(args):
 
     if rank != 0:
         g.close()
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
         return
 
     # ---- roofline of the dominant kernel ------------------------------------------------------------------------------
@@ -382,6 +385,9 @@ def run_gpu_arm(args):
     }
     print(json.dumps(line), flush=True)
     g.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():

@@ -161,3 +161,27 @@ def lockstep_run(oracles, cases, scheme, dt, n_steps, record=None):
                     o.rk_stage(s, scheme, rk, dt, None)
         for r in range(n):
             unpack(r, 0)
+
+
+def drive_rank(orc, exchange, scheme, dt, n_steps):
+    """The same call order for ONE rank of a multi-process job: exchange(step) packs, moves the halo messages over the
+    job's transport and unpacks them (ghost cells are only read by the boundary submesh's next call, so unpacking
+    right after the exchange is equivalent to the reference's later mpi_wait)."""
+    d = orc.case.desc
+    exchange(0)
+    orc.set_bc()
+    exchange(1)
+    orc.vis(0)
+    for _ in range(n_steps):
+        orc.prepare_timestep()
+        for rk in range(d.c.rk_order):
+            orc.prepare_rkstep(rk)
+            orc.set_bc()
+            orc.vis(0)
+            exchange(1)
+            for s in range(1, d.n_sub):
+                orc.vis(s)
+            orc.rk_stage(0, scheme, rk, dt, None)
+            exchange(0)
+            for s in range(1, d.n_sub):
+                orc.rk_stage(s, scheme, rk, dt, None)
