@@ -356,8 +356,15 @@ def run_gpu_arm(args):
         ms, nl = ktimes[dom]
         per_launch_cells = n_cells * (max(1, min(K, 3)) * 5) / nl      # cells one launch covers
         achieved = alg[dom] * per_launch_cells / (ms / nl * 1e-3) / 1e9
+        traffic = None
+        try:                                                          # measured DRAM bytes per launch of the committed ncu capture
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[dom]["f64" if s == 8 else "f32"]
+            if tr["n"] == args.n:
+                traffic = tr["bytes_per_launch"]
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "alg_bytes_per_cell": alg[dom],
+                    "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_cell": alg[dom],
                     "avg_launch_ms": ms / nl, "kernel_ms_per_step": {k: v[0] / max(1, min(K, 3)) for k, v in ktimes.items()},
                     "stage_frac": (Gb + Fb) * n_cells * 5 / (ms_step * 1e-3) / 1e9 / peak}
 

@@ -184,9 +184,7 @@ template <class R, int D> __device__ __forceinline__ void ghost_face_viscous(con
 // One face of one_rk_step_M1 / _M2: rhs[D+2] seen from the owner (c = owner, n = neighbour).
 // ghost: the neighbour is a physical-boundary ghost (is_ghost) -> one-sided gradients; dv (the owner->ghost
 // vector) is only read in that case.
-// PART: 0 = the whole face, 1 = the inviscid flux only (rhs is written), 2 = the viscous terms only (added to rhs, which
-// must hold the inviscid flux) -- the split lets a kernel run two lighter passes with the same sums in the same order.
-template <class R, int D, int SCHEME, class SideC, class SideN, int PART = 0>
+template <class R, int D, int SCHEME, class SideC, class SideN>
 __device__ __forceinline__ void face_flux(const Consts<R>& k, const SideC& c, const SideN& n, const FaceGeo<R, D>& g, bool ghost, const R* dv, R* rhs) {
 	const R ONE = R(1.0), HALF = R(0.5), ZERO = R(0.0);
 	const R weight = g.w;
@@ -200,9 +198,7 @@ __device__ __forceinline__ void face_flux(const Consts<R>& k, const SideC& c, co
 			nU[i] = n.q(i + 1) * nri;
 		}
 	}
-	if (PART == 2) {
-		// inviscid flux already in rhs
-	} else if (SCHEME == 0) {
+	if (SCHEME == 0) {
 		const R S_mag = g.S_mag;
 		const R omw = ONE - weight;
 		const R rhoPos = interp<R>(weight, c.q(0), n.q(0));
@@ -293,7 +289,6 @@ __device__ __forceinline__ void face_flux(const Consts<R>& k, const SideC& c, co
 	}
 
 	// ---- viscosity ----
-	if (PART == 1) return;
 	const R cT = c.Rpsi() * k.Rgas_inv, nT = n.Rpsi() * k.Rgas_inv;
 	if (ghost) {
 		ghost_face_viscous<R, D>(k, cU, nU, cT, nT, S, g.K, weight, g.delta_mag, g.dmag_inv, dv, rhs);

@@ -145,6 +145,7 @@ struct lfmgpu_ctx {
 	int use_tiles = 1;
 	int tile_cells = 128;              // cells per tile requested (halved until the plan fits the budget)
 	int stage_cfg = 0;
+	int fixed_strides = 1;             // compile-time shared-memory strides when the plan fits them
 	int prefetch_distance = 0;
 	int tile_smem_budget = 75 * 1024;  // bytes of shared memory one tile CTA may use
 	// introspection
@@ -552,8 +553,13 @@ template <class R, int D> int tile_grad(lfmgpu_ctx* h, int sub) {
 	int t0, t1, smax, fmax;
 	tile_range(h, sub, t0, t1, smax, fmax);
 	if (t1 <= t0) return 0;
+	const bool fixed = h->fixed_strides && smax <= kFixedSmax && fmax <= kFixedFmax;
+	if (fixed) {
+		smax = kFixedSmax;
+		fmax = kFixedFmax;
+	}
 	const size_t smem = grad_smem<R, D>(smax, fmax);
-	auto kern = k_tile_grad<R, D, kGradThreads>;
+	auto kern = fixed ? k_tile_grad<R, D, kGradThreads, kFixedSmax, kFixedFmax> : k_tile_grad<R, D, kGradThreads, 0, 0>;
 	if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	LAUNCH(h, "tile_grad", h->s_main, (kern<<<t1 - t0, kGradThreads, smem, h->s_main>>>(h->mesh<R>(), tile_view<R>(h, smax, fmax), (const R*)h->q[h->cur], (const R*)h->drv[h->cur], t0)));
 	CHECK_LAUNCH();
@@ -568,36 +574,62 @@ template <class R, int D, int SCHEME> int tile_stage_s(lfmgpu_ctx* h, int sub, R
 	int t0, t1, smax, fmax;
 	tile_range(h, sub, t0, t1, smax, fmax);
 	if (t1 <= t0) return 0;
+	const bool fixed = h->fixed_strides && smax <= kFixedSmax && fmax <= kFixedFmax;
+	if (fixed) {
+		smax = kFixedSmax;
+		fmax = kFixedFmax;
+	}
 	size_t smem = stage_smem<R, D>(smax, fmax);
 	if (const char* e = getenv("LFMGPU_SMEM_PAD")) smem += (size_t)atoi(e) * 1024;   // experiment knob: fewer resident CTAs
 	TileView<R> tview = tile_view<R>(h, smax, fmax);
-#define LFM_STAGE_CFG(NT_, MB_, ...) \
+#define LFM_STAGE_LAUNCH(...) \
 	{ \
-		auto kern = k_tile_stage<R, D, SCHEME, NT_, MB_, ##__VA_ARGS__>; \
+		auto kern = k_tile_stage<R, D, SCHEME, __VA_ARGS__>; \
 		if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
 		LAUNCH(h, "tile_stage", h->s_main, \
-		       (kern<<<t1 - t0, NT_, smem, h->s_main>>>(h->mesh<R>(), tview, (const R*)h->q[h->cur], (const R*)h->drv[h->cur], (R*)h->q[1 - h->cur], (R*)h->drv[1 - h->cur], t0, dt, Ak, Bk, \
+		       (kern<<<t1 - t0, nt_, smem, h->s_main>>>(h->mesh<R>(), tview, (const R*)h->q[h->cur], (const R*)h->drv[h->cur], (R*)h->q[1 - h->cur], (R*)h->drv[1 - h->cur], t0, dt, Ak, Bk, \
 		                                              first, res))); \
 	}
+#define LFM_STAGE_CFG(NT_, MB_) \
+	{ \
+		const int nt_ = NT_; \
+		if (fixed) \
+			LFM_STAGE_LAUNCH(NT_, MB_, kFixedSmax, kFixedFmax) \
+		else \
+			LFM_STAGE_LAUNCH(NT_, MB_, 0, 0) \
+	}
+#define LFM_STAGE_PERSISTENT(NT_, MB_) \
+	{ \
+		auto kern = k_tile_stage_p<R, D, SCHEME, NT_, MB_, kFixedSmax, kFixedFmax>; \
+		const size_t psmem = ((size_t)(StagedLayout<D>::NS + D + 2) * kFixedSmax + (size_t)(D + 2) * kFixedFmax) * sizeof(R) + 3 * sizeof(TileDesc); \
+		CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem)); \
+		int per_sm = 0, sms = 0; \
+		CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT_, psmem)); \
+		CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device)); \
+		const int grid = std::max(1, std::min(t1 - t0, per_sm * sms)); \
+		LAUNCH(h, "tile_stage", h->s_main, \
+		       (kern<<<grid, NT_, psmem, h->s_main>>>(h->mesh<R>(), tview, (const R*)h->q[h->cur], (const R*)h->drv[h->cur], (R*)h->q[1 - h->cur], (R*)h->drv[1 - h->cur], t0, t1 - t0, dt, Ak, \
+		                                              Bk, first, res))); \
+	}
+	if (fixed && h->stage_cfg >= 20) {
+		switch (h->stage_cfg) {
+			case 21: LFM_STAGE_PERSISTENT(128, 4) break;
+			case 22: LFM_STAGE_PERSISTENT(512, 1) break;
+			case 23: LFM_STAGE_PERSISTENT(256, 3) break;
+			default: LFM_STAGE_PERSISTENT(256, 2) break;
+		}
+		CHECK_LAUNCH();
+		return 0;
+	}
+#undef LFM_STAGE_PERSISTENT
 	switch (h->stage_cfg) {
 		case 1: LFM_STAGE_CFG(128, 4) break;
-		case 2: LFM_STAGE_CFG(128, 6) break;
-		case 3: LFM_STAGE_CFG(128, 8) break;
-		case 4: LFM_STAGE_CFG(64, 8) break;
-		case 5: LFM_STAGE_CFG(64, 12) break;
 		case 6: LFM_STAGE_CFG(256, 2) break;
-		case 7: LFM_STAGE_CFG(192, 3) break;
-		case 8: LFM_STAGE_CFG(192, 4) break;
-		case 9: LFM_STAGE_CFG(128, 5) break;
-		case 10: LFM_STAGE_CFG(256, 3, 0) break;
-		case 11: LFM_STAGE_CFG(256, 2, 0) break;
 		case 12: LFM_STAGE_CFG(512, 1) break;
-		case 13: LFM_STAGE_CFG(256, 3, 0, 1) break;
-		case 14: LFM_STAGE_CFG(256, 2, 0, 1) break;
-		case 15: LFM_STAGE_CFG(384, 2, 0, 1) break;
 		default: LFM_STAGE_CFG(256, 3) break;
 	}
 #undef LFM_STAGE_CFG
+#undef LFM_STAGE_LAUNCH
 	CHECK_LAUNCH();
 	return 0;
 }
@@ -693,8 +725,12 @@ int tile_plan_build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
 		for (int s = 0; s < h->n_sub && ok; s++) {
 			const int TC = TCs[s];
 			// shared-memory caps of one tile: faces ~ (F/2 own + 25% incoming) per cell, the rest of the budget for staged cells
-			const int f_cap = std::max(F, (int)(0.625 * F * TC));
-			const int s_cap = (int)(((long long)(budget / es) - (long long)NQ * (f_cap + 4)) / NS) - 4;
+			int f_cap = std::max(F, (int)(0.625 * F * TC));
+			int s_cap = (int)(((long long)(budget / es) - (long long)NQ * (f_cap + 4)) / NS) - 4;
+			if (h->fixed_strides && TC <= 160 && s_cap >= kFixedSmax / 2) {   // keep ordinary tiles inside the compile-time strides
+				f_cap = std::min(f_cap, kFixedFmax);
+				s_cap = std::min(s_cap, kFixedSmax);
+			}
 			if (s_cap < 2 * F) {
 				ok = false;
 				failed_sub = s;
@@ -1082,10 +1118,11 @@ int lfmgpu_create(const lfmgpu_desc* ds, int device, lfmgpu_t* out) {
 		}
 		rc = h->prec == 8 ? build<double>(h, ds) : build<float>(h, ds);
 	}
-	h->stage_cfg = h->prec == 8 ? 6 : 0;   // fp64: 256 threads x 2 CTAs/SM (128 registers, no spills); fp32: 256 x 3
+	h->stage_cfg = h->prec == 8 ? 6 : 23;  // fp64: 256 threads x 2 CTAs/SM (128 registers, no spills); fp32: persistent 256 x 3
 	if (const char* e = getenv("LFMGPU_TILE_CELLS")) h->tile_cells = std::max(16, atoi(e));
 	if (const char* e = getenv("LFMGPU_STAGE_CFG")) h->stage_cfg = atoi(e);
 	if (const char* e = getenv("LFMGPU_USE_TILES")) h->use_tiles = atoi(e);
+	if (const char* e = getenv("LFMGPU_FIXED_STRIDES")) h->fixed_strides = atoi(e);
 	if (const char* e = getenv("LFMGPU_PREFETCH")) h->prefetch_distance = atoi(e);
 	if (const char* e = getenv("LFMGPU_TILE_SMEM")) h->tile_smem_budget = std::max(16, atoi(e)) * 1024;
 	if (!rc) rc = tile_plan_build(h, ds);
