@@ -23,6 +23,9 @@ import common  # noqa: E402
 def main():
     case, tname = sys.argv[1], sys.argv[2]
     src = os.path.join(ROOT, "tmp_cases", case)
+    if not os.path.isdir(src):                      # shipped compressed (the gpurun snapshot is size-limited)
+        subprocess.check_call(["tar", "xzf", src + ".tgz", "-C", "/tmp"])
+        src = os.path.join("/tmp", case)
     dst = os.path.join("/tmp", case + "_gpu")
     if os.path.exists(dst):
         shutil.rmtree(dst)
