@@ -22,6 +22,7 @@ import common  # noqa: E402
 
 def main():
     case, tname = sys.argv[1], sys.argv[2]
+    ranks = int(sys.argv[3]) if len(sys.argv) > 3 else 1
     src = os.path.join(ROOT, "tmp_cases", case)
     if not os.path.isdir(src):                      # shipped compressed (the gpurun snapshot is size-limited)
         subprocess.check_call(["tar", "xzf", src + ".tgz", "-C", "/tmp"])
@@ -31,19 +32,26 @@ def main():
         shutil.rmtree(dst)
     shutil.copytree(src, dst, ignore=shutil.ignore_patterns(tname, "output", "log.*"))
     env = dict(os.environ, LFM_WRITE_PRECISION="17")
+    args = [os.path.join(ROOT, "oracle", "_ref", "lfm_solve_gpu")]
+    if ranks > 1:
+        env["LFM_MPI_NP"] = str(ranks)
+        args.append("-p")
     t0 = time.time()
-    out = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "lfm_solve_gpu")], cwd=dst, env=env, capture_output=True, text=True, timeout=3000)
+    out = subprocess.run(args, cwd=dst, env=env, capture_output=True, text=True, timeout=3000)
     wall = time.time() - t0
     ok = "Simulation finished successfully" in out.stdout
     print(out.stdout[-1500:])
+    print("\n".join(l for l in out.stderr.splitlines() if "lfmgpu" in l)[:2000])
     if not ok:
         print(out.stderr[-3000:])
         raise SystemExit("drop-in run failed")
     rk = re.search(r"\[\s*([0-9.eE+-]+)\]: Rk Loop", out.stdout)
     print(f"# {case}: drop-in run wall {wall:.1f} s, Rk Loop {rk.group(1) if rk else '?'} s")
     worst = 0.0
-    for name in sorted(os.listdir(os.path.join(src, tname))):
-        a_path, b_path = os.path.join(src, tname, name), os.path.join(dst, tname, name)
+    subdirs = [f"processor{r}" for r in range(ranks)] if ranks > 1 else [""]
+    pairs = [(sd, name) for sd in subdirs for name in sorted(os.listdir(os.path.join(src, sd, tname)))]
+    for sd, name in pairs:
+        a_path, b_path = os.path.join(src, sd, tname, name), os.path.join(dst, sd, tname, name)
         if not os.path.isfile(a_path) or not os.path.exists(b_path):
             continue
         try:
@@ -54,7 +62,7 @@ def main():
             continue
         rel = common.rel_max(a, b)
         worst = max(worst, rel)
-        print(f"  field {name:8s} n={a.shape[0]:8d} identical={bool(np.array_equal(a, b))} rel_max={rel:.3e} (max |ref| {np.abs(a).max():.6g})")
+        print(f"  {sd:11s} field {name:8s} n={a.shape[0]:8d} identical={bool(np.array_equal(a, b))} rel_max={rel:.3e} (max |ref| {np.abs(a).max():.6g})")
     print(f"# worst relative max-norm difference: {worst:.3e} (bar 1e-12)")
     if worst > 1e-12:
         raise SystemExit(1)
