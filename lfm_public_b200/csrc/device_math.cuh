@@ -304,29 +304,37 @@ __device__ __forceinline__ void face_flux(const Consts<R>& k, const SideC& c, co
 	}
 	cdiag *= k.c_diag;
 	ndiag *= k.c_diag;
+	// divTauMC[i] = sum_j interp(w, tauMC_c[i][j], tauMC_n[i][j]) * S[j],  tauMC[i][j] = mu*dudx[j][i] (+ diag on i == j)
+	// Kdudx[i]    = sum_j K[j] * interp(w, dudx_c[i][j], dudx_n[i][j])
+	// One pass over the elements (a, b) of dudx in row-major order feeds both sums -- element (a, b) is term j = a of
+	// divTauMC[b] and term j = b of Kdudx[a] -- so every element is read once and each sum still runs over ascending j.
+	R divTauMC[D], Kdudx[D];
 #pragma unroll
-	for (int i = 0; i < D; i++) {
-		// divTauMC[i] = sum_j interp(w, tauMC_c[i][j], tauMC_n[i][j]) * S[j],  tauMC[i][j] = mu*dudx[j][i] (+ diag on i == j)
-		R divTauMC = ZERO, Kdudx = ZERO;
+	for (int a = 0; a < D; a++) {
 #pragma unroll
-		for (int j = 0; j < D; j++) {
-			R ct = k.mu * c.dudx(j, i), nt = k.mu * n.dudx(j, i);
-			if (j == i) {
+		for (int b = 0; b < D; b++) {
+			const R cab = c.dudx(a, b), nab = n.dudx(a, b);
+			R ct = k.mu * cab, nt = k.mu * nab;
+			if (a == b) {
 				ct += cdiag;
 				nt += ndiag;
 			}
-			const R t = interp<R>(weight, ct, nt) * S[j];
-			const R d = g.K[j] * interp<R>(weight, c.dudx(i, j), n.dudx(i, j));
-			if (j == 0) {
-				divTauMC = t;
-				Kdudx = d;
-			} else {
-				divTauMC += t;
-				Kdudx += d;
-			}
+			const R t = interp<R>(weight, ct, nt) * S[a];
+			const R d = g.K[b] * interp<R>(weight, cab, nab);
+			if (a == 0)
+				divTauMC[b] = t;
+			else
+				divTauMC[b] += t;
+			if (b == 0)
+				Kdudx[a] = d;
+			else
+				Kdudx[a] += d;
 		}
-		const R lapU = k.mu * (g.delta_mag * (nU[i] - cU[i]) * dmag_inv + Kdudx);
-		rhs[i + 1] += divTauMC + lapU;
+	}
+#pragma unroll
+	for (int i = 0; i < D; i++) {
+		const R lapU = k.mu * (g.delta_mag * (nU[i] - cU[i]) * dmag_inv + Kdudx[i]);
+		rhs[i + 1] += divTauMC[i] + lapU;
 	}
 	R KdTdx = ZERO, divSigmaU = ZERO;
 #pragma unroll
