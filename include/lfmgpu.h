@@ -152,6 +152,15 @@ int lfmgpu_upload_q(lfmgpu_t h, const void* q, size_t bytes);              /* [n
 /* component-major host arrays [D+2][n_cells] (what a time-directory writer wants), asynchronous on the compute stream */
 int lfmgpu_upload_q_soa_async(lfmgpu_t h, const void* q, size_t bytes);
 int lfmgpu_download_q_soa_async(lfmgpu_t h, void* q, size_t bytes);
+/* Pipelined host I/O for back-to-back batches (each batch: upload q, advance, download q): the upload of the next batch
+ * and the download of the previous result run on their own copy streams through device staging buffers while the compute
+ * stream advances the current batch.  Order per batch: pipe_in_start(host_in) [may be issued one batch ahead] ->
+ * pipe_in_commit -> lfmgpu_step -> pipe_out_start -> pipe_out_fetch(host_out).  Host arrays are [D+2][n_cells] as in
+ * lfmgpu_upload_q_soa_async and must stay valid (pinned for true overlap) until lfmgpu_sync / a later event. */
+int lfmgpu_pipe_in_start(lfmgpu_t h, const void* q, size_t bytes);
+int lfmgpu_pipe_in_commit(lfmgpu_t h);
+int lfmgpu_pipe_out_start(lfmgpu_t h);
+int lfmgpu_pipe_out_fetch(lfmgpu_t h, void* q, size_t bytes);
 /* pinned host staging for the end-to-end path */
 int lfmgpu_host_alloc(void** p, size_t bytes);
 int lfmgpu_host_free(void* p);

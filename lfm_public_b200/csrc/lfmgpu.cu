@@ -126,6 +126,10 @@ struct lfmgpu_ctx {
 	int* d_force_used = nullptr;
 	void* d_force_out = nullptr;
 	cudaStream_t s_main = nullptr, s_comm = nullptr;
+	// pipelined host I/O (lfmgpu_pipe_*): staging buffers and copy streams, created on first use
+	cudaStream_t s_in = nullptr, s_out = nullptr;
+	void *stage_in = nullptr, *stage_out = nullptr;
+	cudaEvent_t ev_in_ready = nullptr, ev_in_free = nullptr, ev_out_ready = nullptr, ev_out_free = nullptr;
 	cudaEvent_t ev_ready = nullptr;
 	cudaEvent_t ev_user[8] = {nullptr};
 	cudaEvent_t ev_packed[2] = {nullptr, nullptr}, ev_arrived[2] = {nullptr, nullptr};
@@ -1152,6 +1156,10 @@ int lfmgpu_destroy(lfmgpu_t h) {
 		if (h->ev_packed[s]) cudaEventDestroy(h->ev_packed[s]);
 		if (h->ev_arrived[s]) cudaEventDestroy(h->ev_arrived[s]);
 	}
+	if (h->s_in) cudaStreamDestroy(h->s_in);
+	if (h->s_out) cudaStreamDestroy(h->s_out);
+	for (cudaEvent_t e : {h->ev_in_ready, h->ev_in_free, h->ev_out_ready, h->ev_out_free})
+		if (e) cudaEventDestroy(e);
 	if (h->s_main) cudaStreamDestroy(h->s_main);
 	if (h->s_comm) cudaStreamDestroy(h->s_comm);
 	delete h;
@@ -1160,6 +1168,8 @@ int lfmgpu_destroy(lfmgpu_t h) {
 
 int lfmgpu_sync(lfmgpu_t h) {
 	TRY(use(h));
+	if (h->s_in) CU(cudaStreamSynchronize(h->s_in));
+	if (h->s_out) CU(cudaStreamSynchronize(h->s_out));
 	CU(cudaStreamSynchronize(h->s_comm));
 	CU(cudaStreamSynchronize(h->s_main));
 	return 0;
@@ -1394,6 +1404,67 @@ int lfmgpu_download_q_soa_async(lfmgpu_t h, void* q, size_t bytes) {
 	return 0;
 }
 
+// Pipelined host I/O for back-to-back batches: the upload of the next batch and the download of the previous result run
+// on their own streams, through device staging buffers, while the compute stream advances the current batch.
+//   pipe_in_start(host)  : H2D host -> staging (copy-in stream), once the previous commit has drained the staging buffer
+//   pipe_in_commit()     : compute stream waits for that upload, then staging -> q (device copy)
+//   pipe_out_start()     : compute stream copies q -> out staging, once the previous fetch has drained it
+//   pipe_out_fetch(host) : D2H out staging -> host (copy-out stream)
+namespace {
+int pipe_init(lfmgpu_ctx* h) {
+	if (h->s_in) return 0;
+	const size_t bytes = (size_t)h->NQ * h->n_cells * (size_t)h->prec;
+	CU(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+	CU(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+	TRY(dev_alloc(h, &h->stage_in, bytes, false));
+	TRY(dev_alloc(h, &h->stage_out, bytes, false));
+	cudaEvent_t* evs[4] = {&h->ev_in_ready, &h->ev_in_free, &h->ev_out_ready, &h->ev_out_free};
+	for (auto* e : evs) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+	CU(cudaEventRecord(h->ev_in_free, h->s_main));
+	CU(cudaEventRecord(h->ev_out_free, h->s_out));
+	return 0;
+}
+}  // namespace
+int lfmgpu_pipe_in_start(lfmgpu_t h, const void* q, size_t bytes) {
+	TRY(use(h));
+	TRY(pipe_init(h));
+	const size_t es = (size_t)h->prec, n = (size_t)h->n_cells;
+	if (bytes != n * h->NQ * es) return fail("lfmgpu_pipe_in_start: expected %zu bytes", n * h->NQ * es);
+	CU(cudaStreamWaitEvent(h->s_in, h->ev_in_free, 0));
+	CU(cudaMemcpyAsync(h->stage_in, q, bytes, cudaMemcpyHostToDevice, h->s_in));
+	CU(cudaEventRecord(h->ev_in_ready, h->s_in));
+	return 0;
+}
+int lfmgpu_pipe_in_commit(lfmgpu_t h) {
+	TRY(use(h));
+	TRY(pipe_init(h));
+	const size_t es = (size_t)h->prec, n = (size_t)h->n_cells;
+	CU(cudaStreamWaitEvent(h->s_main, h->ev_in_ready, 0));
+	CU(cudaMemcpy2DAsync(h->q[h->cur], h->ncs * es, h->stage_in, n * es, n * es, (size_t)h->NQ, cudaMemcpyDeviceToDevice, h->s_main));
+	CU(cudaEventRecord(h->ev_in_free, h->s_main));
+	h->drv_valid[h->cur] = false;
+	return 0;
+}
+int lfmgpu_pipe_out_start(lfmgpu_t h) {
+	TRY(use(h));
+	TRY(pipe_init(h));
+	const size_t es = (size_t)h->prec, n = (size_t)h->n_cells;
+	CU(cudaStreamWaitEvent(h->s_main, h->ev_out_free, 0));
+	CU(cudaMemcpy2DAsync(h->stage_out, n * es, h->q[h->cur], h->ncs * es, n * es, (size_t)h->NQ, cudaMemcpyDeviceToDevice, h->s_main));
+	CU(cudaEventRecord(h->ev_out_ready, h->s_main));
+	return 0;
+}
+int lfmgpu_pipe_out_fetch(lfmgpu_t h, void* q, size_t bytes) {
+	TRY(use(h));
+	TRY(pipe_init(h));
+	const size_t es = (size_t)h->prec, n = (size_t)h->n_cells;
+	if (bytes != n * h->NQ * es) return fail("lfmgpu_pipe_out_fetch: expected %zu bytes", n * h->NQ * es);
+	CU(cudaStreamWaitEvent(h->s_out, h->ev_out_ready, 0));
+	CU(cudaMemcpyAsync(q, h->stage_out, bytes, cudaMemcpyDeviceToHost, h->s_out));
+	CU(cudaEventRecord(h->ev_out_free, h->s_out));
+	return 0;
+}
+
 int lfmgpu_host_alloc(void** p, size_t bytes) {
 	CU(cudaMallocHost(p, bytes));
 	return 0;
@@ -1540,6 +1611,12 @@ int lfmgpu_event_record(lfmgpu_t h, int slot) {
 	// the compute stream waits for the halo stream first so that the event closes everything enqueued so far
 	CU(cudaEventRecord(h->ev_ready, h->s_comm));
 	CU(cudaStreamWaitEvent(h->s_main, h->ev_ready, 0));
+	if (h->s_in) {   // pipelined host I/O in flight: the event closes the copy streams too
+		CU(cudaEventRecord(h->ev_ready, h->s_in));
+		CU(cudaStreamWaitEvent(h->s_main, h->ev_ready, 0));
+		CU(cudaEventRecord(h->ev_ready, h->s_out));
+		CU(cudaStreamWaitEvent(h->s_main, h->ev_ready, 0));
+	}
 	CU(cudaEventRecord(h->ev_user[slot], h->s_main));
 	return 0;
 }

@@ -25,6 +25,7 @@ SYMBOLS = [
     "lfmgpu_rk_stage", "lfmgpu_halo_start", "lfmgpu_halo_wait", "lfmgpu_cfl", "lfmgpu_dt", "lfmgpu_average",
     "lfmgpu_forces", "lfmgpu_residual", "lfmgpu_step", "lfmgpu_warmup", "lfmgpu_step_multi", "lfmgpu_allreduce",
     "lfmgpu_set_option", "lfmgpu_download", "lfmgpu_upload_q", "lfmgpu_upload_q_soa_async", "lfmgpu_download_q_soa_async",
+    "lfmgpu_pipe_in_start", "lfmgpu_pipe_in_commit", "lfmgpu_pipe_out_start", "lfmgpu_pipe_out_fetch",
     "lfmgpu_host_alloc", "lfmgpu_host_free", "lfmgpu_nccl_unique_id", "lfmgpu_comm_init_nccl", "lfmgpu_comm_init_local",
     "lfmgpu_halo_send_count", "lfmgpu_download_send_buffer", "lfmgpu_halo_pack_to_host", "lfmgpu_halo_unpack_from_host", "lfmgpu_launch_count", "lfmgpu_enable_kernel_timing",
     "lfmgpu_kernel_time", "lfmgpu_tile_info", "lfmgpu_event_record", "lfmgpu_event_elapsed_ms",
@@ -49,6 +50,8 @@ def lib():
             "lfmgpu_step_multi": [vp, i, i, d, i, i, i], "lfmgpu_allreduce": [vp, vp, i, i],
             "lfmgpu_set_option": [vp, C.c_char_p, i], "lfmgpu_download": [vp, i, vp, sz], "lfmgpu_upload_q": [vp, vp, sz],
             "lfmgpu_upload_q_soa_async": [vp, vp, sz], "lfmgpu_download_q_soa_async": [vp, vp, sz],
+            "lfmgpu_pipe_in_start": [vp, vp, sz], "lfmgpu_pipe_in_commit": [vp], "lfmgpu_pipe_out_start": [vp],
+            "lfmgpu_pipe_out_fetch": [vp, vp, sz],
             "lfmgpu_host_alloc": [C.POINTER(vp), sz], "lfmgpu_host_free": [vp], "lfmgpu_nccl_unique_id": [vp],
             "lfmgpu_comm_init_nccl": [vp, vp, i, i], "lfmgpu_comm_init_local": [vp, i, i, vp],
             "lfmgpu_halo_pack_to_host": [vp, i, vp, sz], "lfmgpu_halo_unpack_from_host": [vp, i, vp, sz],
@@ -191,6 +194,18 @@ class GpuSolver:
 
     def download_q_soa_async(self, ptr, nbytes):
         _check(lib().lfmgpu_download_q_soa_async(self.h, ptr, nbytes))
+
+    def pipe_in_start(self, ptr, nbytes):
+        _check(lib().lfmgpu_pipe_in_start(self.h, ptr, nbytes))
+
+    def pipe_in_commit(self):
+        _check(lib().lfmgpu_pipe_in_commit(self.h))
+
+    def pipe_out_start(self):
+        _check(lib().lfmgpu_pipe_out_start(self.h))
+
+    def pipe_out_fetch(self, ptr, nbytes):
+        _check(lib().lfmgpu_pipe_out_fetch(self.h, ptr, nbytes))
 
     def send_buffer(self, step):
         n = C.c_size_t()
