@@ -121,6 +121,7 @@ int lfmgpu_prepare_rkstep(lfmgpu_t h, int rk_step);          /* cfd_v0.cpp:1339 
 int lfmgpu_set_bc(lfmgpu_t h);                               /* cfd_v0.cpp:1010  set_boundary_conditions*/
 int lfmgpu_gradients(lfmgpu_t h, int submesh);               /* cfd_v0.cpp:1501  calc_gradients (minmod)*/
 int lfmgpu_vis(lfmgpu_t h, int submesh);                     /* cfd_v0.cpp:1744  calc_VIS (laminar)     */
+int lfmgpu_vis_smagorinsky(lfmgpu_t h, int submesh);         /* cfd_v0.cpp:1574  calc_VIS_Smagorinsky   */
 int lfmgpu_rk_stage(lfmgpu_t h, int submesh, int scheme, int rk_step, double dt, int want_res);
                                                              /* cfd_v0.cpp:2530 / 1897 one_rk_step_M1/M2 */
 int lfmgpu_halo_start(lfmgpu_t h, int comm_step);            /* cfd_v0.cpp:3547  mpi_communication      */
@@ -143,7 +144,9 @@ int lfmgpu_step_multi(const lfmgpu_t* hs, int n_ranks, int scheme, double dt, in
 /* The scalar reductions Mesh::solve does with MPI_Allreduce / MPI_Reduce (mesh_solver.cpp:715, 763-779,
  * cfd_v0.cpp:3242-3243): op 0 = sum, 1 = min, 2 = max over the NCCL ranks, in place, n <= 8; blocking. */
 int lfmgpu_allreduce(lfmgpu_t h, double* values, int n, int op);
-/* Tuning knobs: "use_tiles" 1 (default) = fused shared-memory tile kernels, 0 = face kernel + gather kernels. */
+/* Options: "use_tiles" 1 (default) = fused shared-memory tile kernels, 0 = face kernel + gather kernels (tuning);
+ * "laminar" 1 (default) / 0 = lfmgpu_step and lfmgpu_step_multi call calc_VIS / calc_VIS_Smagorinsky
+ * (CInputReader::m_bLaminar, reference: src/inputReader.cpp:60, src/mesh_solver.cpp:556-560). */
 int lfmgpu_set_option(lfmgpu_t h, const char* name, int value);
 
 /* ---- data movement --------------------------------------------------------------------------------- */

@@ -95,6 +95,33 @@ template <class R, int D> __device__ __forceinline__ void tauMC_from(const Const
 	}
 }
 
+// tauMC of calc_VIS_Smagorinsky (cfd_v0.cpp:1660-1690): the laminar tauMC plus the eddy-viscosity contribution,
+// smag = -2 (Cs Delta)^2 of the visiting cell (cfd_v0.cpp:1601-1602; computed on the host with the C library's pow)
+template <class R, int D> __device__ __forceinline__ void tauMC_smagorinsky(const Consts<R>& k, R smag, const R (*dudx)[D], R (*tauMC)[D]) {
+	tauMC_from<R, D>(k, dudx, tauMC);
+	const R HALF = R(0.5);
+	R Strain_Mag = R(0), divu = R(0);
+#pragma unroll
+	for (int i = 0; i < D; i++) {
+#pragma unroll
+		for (int j = 0; j < D; j++) {
+			const R S_ij = HALF * (dudx[i][j] + dudx[j][i]);
+			Strain_Mag += S_ij * S_ij;
+		}
+		divu += dudx[i][i];
+	}
+	Strain_Mag = LFM_SQRT(R(2.0) * Strain_Mag);
+#pragma unroll
+	for (int i = 0; i < D; i++) {
+#pragma unroll
+		for (int j = 0; j < D; j++) {
+			const R S_ij = HALF * (dudx[i][j] + dudx[j][i]);
+			tauMC[i][j] -= smag * Strain_Mag * S_ij;
+		}
+		tauMC[i][i] += smag * Strain_Mag * divu / R(3.0);
+	}
+}
+
 // the per-cell block of calc_VIS (cfd_v0.cpp:1806-1857): sigmaU and tauMC from the finished dudx
 template <class R, int D> __device__ __forceinline__ void vis_cell_terms(const Consts<R>& k, const R* q, const R (*dudx)[D], R (*tauMC)[D], R* sigmaU) {
 	R Ud[D], tau[D][D];
@@ -150,6 +177,7 @@ template <class R, int D> struct RegSide {
 	__device__ __forceinline__ R dudx(int i, int j) const { return s.dudx[i][j]; }
 	__device__ __forceinline__ R dTdx(int i) const { return s.dTdx[i]; }
 	__device__ __forceinline__ R sigmaU(int i) const { return s.sigmaU[i]; }
+	__device__ __forceinline__ R tauMC(int, int) const { return R(0); }   // the unfused kernels serve the laminar closure only
 };
 
 // one-sided viscous terms of a physical-boundary face (cfd_v0.cpp:2701-2707, 2732-2745, 2774-2782); rare, kept out of line
@@ -184,7 +212,9 @@ template <class R, int D> __device__ __forceinline__ void ghost_face_viscous(con
 // One face of one_rk_step_M1 / _M2: rhs[D+2] seen from the owner (c = owner, n = neighbour).
 // ghost: the neighbour is a physical-boundary ghost (is_ghost) -> one-sided gradients; dv (the owner->ghost
 // vector) is only read in that case.
-template <class R, int D, int SCHEME, class SideC, class SideN>
+// LES != 0: tauMC of both sides is read from the sides (c.tauMC(i, j), stored by the Smagorinsky gradient pass) instead of
+// being rebuilt from dudx.
+template <class R, int D, int SCHEME, class SideC, class SideN, int LES = 0>
 __device__ __forceinline__ void face_flux(const Consts<R>& k, const SideC& c, const SideN& n, const FaceGeo<R, D>& g, bool ghost, const R* dv, R* rhs) {
 	const R ONE = R(1.0), HALF = R(0.5), ZERO = R(0.0);
 	const R weight = g.w;
@@ -314,10 +344,17 @@ __device__ __forceinline__ void face_flux(const Consts<R>& k, const SideC& c, co
 #pragma unroll
 		for (int b = 0; b < D; b++) {
 			const R cab = c.dudx(a, b), nab = n.dudx(a, b);
-			R ct = k.mu * cab, nt = k.mu * nab;
-			if (a == b) {
-				ct += cdiag;
-				nt += ndiag;
+			R ct, nt;
+			if (LES) {
+				ct = c.tauMC(b, a);
+				nt = n.tauMC(b, a);
+			} else {
+				ct = k.mu * cab;
+				nt = k.mu * nab;
+				if (a == b) {
+					ct += cdiag;
+					nt += ndiag;
+				}
 			}
 			const R t = interp<R>(weight, ct, nt) * S[a];
 			const R d = g.K[b] * interp<R>(weight, cab, nab);

@@ -34,6 +34,9 @@ template <class R> struct DevMesh {
 	R* dudx;                           // [D*D][ncs]
 	R* dTdx;                           // [D][ncs]
 	R* sigmaU;                         // [D][ncs]    U.tau of calc_VIS (real cells: k_*grad*; MPI ghosts: as received)
+	R* tauMC;                          // [D*D][ncs]  only with the Smagorinsky closure (laminar: rebuilt from dudx where needed)
+	const R* smag_c;                   // [n_cells]   -2 (Cs Delta)^2 of the cell whose face loop leaves the cell's final tauMC
+	int les;                           // calc_VIS_Smagorinsky instead of calc_VIS
 	R* flux;                           // [NQ][nfs]   materialised face fluxes (v1 path)
 	R *pAVG, *pRMS;
 	const int *bc_cell, *bc_kind, *bc_face, *bc_patch;
@@ -315,7 +318,14 @@ template <class R, int D> __global__ void __launch_bounds__(kBlock) k_pack(DevMe
 			for (int b = 0; b < D; b++) dudx[a][b] = m.dudx[(size_t)(a * D + b) * m.ncs + c];
 			dTdx[a] = m.dTdx[(size_t)a * m.ncs + c];
 		}
-		tauMC_from<R, D>(m.k, dudx, tauMC);
+		if (m.les) {
+#pragma unroll
+			for (int a = 0; a < D; a++)
+#pragma unroll
+				for (int b = 0; b < D; b++) tauMC[a][b] = m.tauMC[(size_t)(a * D + b) * m.ncs + c];
+		} else {
+			tauMC_from<R, D>(m.k, dudx, tauMC);
+		}
 #pragma unroll
 		for (int a = 0; a < D; a++) sigmaU[a] = m.sigmaU[(size_t)a * m.ncs + c];
 #pragma unroll
@@ -354,7 +364,11 @@ template <class R, int D> __global__ void __launch_bounds__(kBlock) k_unpack(Dev
 		for (int a = 0; a < D * D; a++) m.dudx[(size_t)a * m.ncs + g] = *o++;
 #pragma unroll
 		for (int a = 0; a < D; a++) m.dTdx[(size_t)a * m.ncs + g] = *o++;
-		o += D * D;   // tauMC is a function of the dudx just stored (same expression on both ranks): not kept
+		if (m.les) {   // with the Smagorinsky closure tauMC is not a function of dudx alone: keep what the neighbour computed
+#pragma unroll
+			for (int a = 0; a < D * D; a++) m.tauMC[(size_t)a * m.ncs + g] = o[a];
+		}
+		o += D * D;   // laminar: tauMC is a function of the dudx just stored (same expression on both ranks): not kept
 #pragma unroll
 		for (int a = 0; a < D; a++) m.sigmaU[(size_t)a * m.ncs + g] = *o++;
 	}

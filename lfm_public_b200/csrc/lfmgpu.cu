@@ -150,6 +150,9 @@ struct lfmgpu_ctx {
 	int tile_cells = 128;              // cells per tile requested (halved until the plan fits the budget)
 	int stage_cfg = 0;
 	int fixed_strides = 1;             // compile-time shared-memory strides when the plan fits them
+	int les_opt = 0;                   // option "laminar" == 0: lfmgpu_step / _step_multi use calc_VIS_Smagorinsky
+	int les = 0;                       // closure of the latest calc_VIS call (what the stage kernels and the halo pack see)
+	std::vector<int> smag_owner;       // cell whose face loop leaves each cell's final tauMC (Smagorinsky constant)
 	int prefetch_distance = 0;
 	int tile_smem_budget = 75 * 1024;  // bytes of shared memory one tile CTA may use
 	// introspection
@@ -284,6 +287,28 @@ template <class R> int build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
 	TRY(dev_alloc(h, (void**)&m.dudx, (size_t)D * D * h->ncs * sizeof(R)));
 	TRY(dev_alloc(h, (void**)&m.dTdx, (size_t)D * h->ncs * sizeof(R)));
 	TRY(dev_alloc(h, (void**)&m.sigmaU, (size_t)D * h->ncs * sizeof(R)));
+	m.tauMC = nullptr;   // allocated when the Smagorinsky closure is first used
+	m.les = 0;
+	{
+		// Smagorinsky constant -2 (Cs Delta)^2 per cell (cfd_v0.cpp:1601-1602), evaluated here with the C library's pow so that
+		// it equals the reference's value bit for bit.  The reference recomputes a cell's tauMC at every face visit with the
+		// constant of the VISITING cell: the final value comes from the cell's own loop if it owns a face, else from the owner
+		// of its last incoming face.
+		std::vector<R> sc((size_t)h->n_cells, R(0));
+		const R* vol_inv = (const R*)ds->vol_inv;
+		for (int c = 0; c < h->n_cells; c++) {
+			int owner = -1, last_inc = 0;
+			for (int s = 0; s < F; s++) {
+				const int e = ds->cell_slot_face[(size_t)c * F + s];
+				if (e > 0) owner = c;
+				if (e < 0 && -e > last_inc) last_inc = -e;
+			}
+			if (owner < 0 && last_inc > 0) owner = ds->face_owner[last_inc - 1];
+			if (owner >= 0) sc[(size_t)c] = -(R)2.0 * pow((R)0.16 * pow(1.0 / vol_inv[owner], 1. / 3.), 2);
+		}
+		TRY(upload<R>(h, &r, sc.data(), sc.size()));
+		m.smag_c = r;
+	}
 	m.flux = nullptr;   // allocated on first use of the materialised path
 	TRY(dev_alloc(h, (void**)&m.pAVG, (size_t)h->n_cells * sizeof(R)));
 	TRY(dev_alloc(h, (void**)&m.pRMS, (size_t)h->n_cells * sizeof(R)));
@@ -389,10 +414,15 @@ template <class R, int D> int ensure_drv(lfmgpu_ctx* h, int scheme) {
 	return 0;
 }
 
-template <class R, int D> int t_vis(lfmgpu_ctx* h, int sub) {
+template <class R, int D> int t_vis(lfmgpu_ctx* h, int sub, int les) {
 	int c0, c1, f0, f1;
 	sub_range(h, sub, c0, c1, f0, f1);
 	h->vis_on_cur = true;
+	DevMesh<R>& m = h->mesh<R>();
+	if (les && !(h->use_tiles && h->tiles.ready)) return fail("the Smagorinsky closure is served by the tile kernels only (use_tiles=1 and a tileable mesh)");
+	if (les && !m.tauMC) TRY(dev_alloc(h, (void**)&m.tauMC, (size_t)D * D * h->ncs * sizeof(R)));
+	h->les = les;
+	m.les = les;
 	if (c1 <= c0) return 0;
 	if (h->use_tiles && h->tiles.ready) {
 		TRY((ensure_drv<R, D>(h, -1)));
@@ -417,6 +447,7 @@ template <class R, int D> int t_rk_stage(lfmgpu_ctx* h, int sub, int scheme, int
 			TRY((ensure_drv<R, D>(h, scheme)));
 			TRY((tile_stage<R, D>(h, sub, scheme, (R)dt, Ak, Bk, first, res)));
 		} else {
+			if (h->les) return fail("the Smagorinsky closure is served by the tile kernels only");
 			h->drv_dirty_next = true;
 			if (!m.flux) TRY(dev_alloc(h, (void**)&m.flux, (size_t)h->NQ * h->nfs * sizeof(R)));
 			if (f1 > f0) {
@@ -563,7 +594,8 @@ template <class R, int D> int tile_grad(lfmgpu_ctx* h, int sub) {
 		fmax = kFixedFmax;
 	}
 	const size_t smem = grad_smem<R, D>(smax, fmax);
-	auto kern = fixed ? k_tile_grad<R, D, kGradThreads, kFixedSmax, kFixedFmax> : k_tile_grad<R, D, kGradThreads, 0, 0>;
+	auto kern = h->les ? (fixed ? k_tile_grad<R, D, kGradThreads, kFixedSmax, kFixedFmax, 1> : k_tile_grad<R, D, kGradThreads, 0, 0, 1>)
+	                   : (fixed ? k_tile_grad<R, D, kGradThreads, kFixedSmax, kFixedFmax, 0> : k_tile_grad<R, D, kGradThreads, 0, 0, 0>);
 	if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	LAUNCH(h, "tile_grad", h->s_main, (kern<<<t1 - t0, kGradThreads, smem, h->s_main>>>(h->mesh<R>(), tile_view<R>(h, smax, fmax), (const R*)h->q[h->cur], (const R*)h->drv[h->cur], t0)));
 	CHECK_LAUNCH();
@@ -583,9 +615,30 @@ template <class R, int D, int SCHEME> int tile_stage_s(lfmgpu_ctx* h, int sub, R
 		smax = kFixedSmax;
 		fmax = kFixedFmax;
 	}
-	size_t smem = stage_smem<R, D>(smax, fmax);
+	size_t smem = stage_smem<R, D>(smax, fmax) + (h->les ? (size_t)D * D * smax * sizeof(R) : 0);
 	if (const char* e = getenv("LFMGPU_SMEM_PAD")) smem += (size_t)atoi(e) * 1024;   // experiment knob: fewer resident CTAs
 	TileView<R> tview = tile_view<R>(h, smax, fmax);
+	if (h->les) {   // Smagorinsky closure: tauMC is staged too (one configuration: 256 threads, 2 CTAs/SM)
+		const int nt_ = 256;
+		int dev_smem = 0;
+		CU(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+		if (smem > (size_t)dev_smem) return fail("Smagorinsky closure: a tile needs %zu bytes of shared memory (limit %d): lower LFMGPU_TILE_CELLS", smem, dev_smem);
+#define LFM_STAGE_LES(SM_, FM_) \
+		{ \
+			auto kern = k_tile_stage<R, D, SCHEME, 256, 2, SM_, FM_, 1>; \
+			if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+			LAUNCH(h, "tile_stage", h->s_main, \
+			       (kern<<<t1 - t0, nt_, smem, h->s_main>>>(h->mesh<R>(), tview, (const R*)h->q[h->cur], (const R*)h->drv[h->cur], (R*)h->q[1 - h->cur], (R*)h->drv[1 - h->cur], t0, dt, Ak, \
+			                                              Bk, first, res))); \
+		}
+		if (fixed)
+			LFM_STAGE_LES(kFixedSmax, kFixedFmax)
+		else
+			LFM_STAGE_LES(0, 0)
+#undef LFM_STAGE_LES
+		CHECK_LAUNCH();
+		return 0;
+	}
 #define LFM_STAGE_LAUNCH(...) \
 	{ \
 		auto kern = k_tile_stage<R, D, SCHEME, __VA_ARGS__>; \
@@ -1000,14 +1053,14 @@ int stage_all(lfmgpu_ctx** hs, int n, int scheme, int rk, double dt, int want_re
 		h->rk_pending = rk;
 		TRY(halo_wait_impl(h, 0));
 		TRY(DISPATCH(h, t_set_bc, h));
-		TRY(DISPATCH(h, t_vis, h, h->n_nbr ? 0 : -1));
+		TRY(DISPATCH(h, t_vis, h, h->n_nbr ? 0 : -1, h->les_opt));
 		TRY(halo_start_impl(h, 1));
 	}
 	for (int r = 0; r < n; r++) {
 		lfmgpu_ctx* h = hs[r];
 		TRY(use(h));
 		if (h->n_nbr)
-			for (int s = 1; s < h->n_sub; s++) TRY(DISPATCH(h, t_vis, h, s));
+			for (int s = 1; s < h->n_sub; s++) TRY(DISPATCH(h, t_vis, h, s, h->les_opt));
 	}
 	for (int r = 0; r < n; r++) {
 		lfmgpu_ctx* h = hs[r];
@@ -1177,6 +1230,10 @@ int lfmgpu_sync(lfmgpu_t h) {
 
 int lfmgpu_set_option(lfmgpu_t h, const char* name, int value) {
 	TRY(use(h));
+	if (!strcmp(name, "laminar")) {   // 0: the time loops of lfmgpu_step / _step_multi call calc_VIS_Smagorinsky
+		h->les_opt = value ? 0 : 1;
+		return 0;
+	}
 	if (!strcmp(name, "use_tiles")) {
 		h->use_tiles = value;
 		h->drv_valid[0] = h->drv_valid[1] = false;
@@ -1210,7 +1267,12 @@ int lfmgpu_gradients(lfmgpu_t h, int submesh) {
 int lfmgpu_vis(lfmgpu_t h, int submesh) {
 	TRY(use(h));
 	if (submesh >= h->n_sub) return fail("submesh out of range");
-	return DISPATCH(h, t_vis, h, submesh);
+	return DISPATCH(h, t_vis, h, submesh, 0);
+}
+int lfmgpu_vis_smagorinsky(lfmgpu_t h, int submesh) {
+	TRY(use(h));
+	if (submesh >= h->n_sub) return fail("submesh out of range");
+	return DISPATCH(h, t_vis, h, submesh, 1);
 }
 int lfmgpu_rk_stage(lfmgpu_t h, int submesh, int scheme, int rk_step, double dt, int want_res) {
 	TRY(use(h));
@@ -1299,7 +1361,15 @@ int lfmgpu_download(lfmgpu_t h, int field, void* dst, size_t dst_bytes) {
 		case LFMGPU_FIELD_PAVG: base = h->prec == 8 ? (const char*)h->md.pAVG : (const char*)h->mf.pAVG; stride = (size_t)nc; break;
 		case LFMGPU_FIELD_PRMS: base = h->prec == 8 ? (const char*)h->md.pRMS : (const char*)h->mf.pRMS; stride = (size_t)nc; break;
 		case LFMGPU_FIELD_QGHOST: base = (const char*)h->q[h->cur]; stride = h->ncs; comps = NQ; off = (size_t)nc; n = (size_t)(h->n_bc + h->n_mpi); break;
-		case LFMGPU_FIELD_TAUMC: comps = D * D; derived = true; break;
+		case LFMGPU_FIELD_TAUMC:
+			comps = D * D;
+			if (h->les) {
+				base = h->prec == 8 ? (const char*)h->md.tauMC : (const char*)h->mf.tauMC;
+				stride = h->ncs;
+			} else {
+				derived = true;
+			}
+			break;
 		case LFMGPU_FIELD_SIGMAU: base = h->prec == 8 ? (const char*)h->md.sigmaU : (const char*)h->mf.sigmaU; stride = h->ncs; comps = D; break;
 		default: return fail("unknown field %d", field);
 	}

@@ -96,6 +96,8 @@ template <int D> struct StagedLayout {
 	static constexpr int NQ = D + 2;
 	static constexpr int RHO_INV = NQ, RPSI = NQ + 1, AUX = NQ + 2, DUDX = NQ + 3, DTDX = DUDX + D * D, SIGMAU = DTDX + D;
 	static constexpr int NS = SIGMAU + D;
+	static constexpr int TAUMC = NS;             // staged only with the Smagorinsky closure
+	static constexpr int NS_LES = NS + D * D;
 };
 
 // a side of a face staged in shared memory (SoA rows of stride smax); values are loaded where they are used
@@ -110,6 +112,7 @@ template <class R, int D> struct SmemSide {
 	__device__ __forceinline__ R dudx(int a, int b) const { return st[(L::DUDX + a * D + b) * smax + i]; }
 	__device__ __forceinline__ R dTdx(int a) const { return st[(L::DTDX + a) * smax + i]; }
 	__device__ __forceinline__ R sigmaU(int a) const { return st[(L::SIGMAU + a) * smax + i]; }
+	__device__ __forceinline__ R tauMC(int a, int b) const { return st[(L::TAUMC + a * D + b) * smax + i]; }
 };
 
 constexpr int kMaxSlots = 6;   // FACE_CNT of the reference is at most 6 (hexahedra)
@@ -137,7 +140,7 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // instead of one address computation per access); 0: the strides of the launch (tv.smax / tv.fmax).
 constexpr int kFixedSmax = 320, kFixedFmax = 480;
 
-template <class R, int D, int NT, int SMAX = 0, int FMAX = 0>
+template <class R, int D, int NT, int SMAX = 0, int FMAX = 0, int LES = 0>
 __global__ void __launch_bounds__(NT) k_tile_grad(DevMesh<R> m, TileView<R> tv, const R* __restrict__ q, const R* __restrict__ drv, int tile0) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int smax = SMAX ? SMAX : tv.smax, fmax = FMAX ? FMAX : tv.fmax;
@@ -252,6 +255,14 @@ __global__ void __launch_bounds__(NT) k_tile_grad(DevMesh<R> m, TileView<R> tv, 
 			m.dTdx[(size_t)i * m.ncs + c] = dTdx[i];
 			m.sigmaU[(size_t)i * m.ncs + c] = sigmaU[i];
 		}
+		if (LES) {
+			R tauMC[D][D];
+			tauMC_smagorinsky<R, D>(m.k, m.smag_c[c], dudx, tauMC);
+#pragma unroll
+			for (int i = 0; i < D; i++)
+#pragma unroll
+				for (int j = 0; j < D; j++) m.tauMC[(size_t)(i * D + j) * m.ncs + c] = tauMC[i][j];
+		}
 	}
 }
 
@@ -336,15 +347,15 @@ __device__ __forceinline__ void gather_update(const DevMesh<R>& m, const TileVie
 	}
 }
 
-template <class R, int D, int SCHEME, int NT, int MINB, int SMAX = 0, int FMAX = 0>
+template <class R, int D, int SCHEME, int NT, int MINB, int SMAX = 0, int FMAX = 0, int LES = 0>
 __global__ void __launch_bounds__(NT, MINB)
     k_tile_stage(DevMesh<R> m, TileView<R> tv, const R* __restrict__ q, const R* __restrict__ drv, R* __restrict__ qn, R* __restrict__ drvn, int tile0, R dt, R Ak, R Bk, int first, int res) {
 	using L = StagedLayout<D>;
 	constexpr int NQ = D + 2;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int smax = SMAX ? SMAX : tv.smax, fmax = FMAX ? FMAX : tv.fmax;
-	R* st = reinterpret_cast<R*>(smem_raw);      // [NS][smax]
-	R* fl = st + (size_t)L::NS * smax;           // [NQ][fmax]
+	R* st = reinterpret_cast<R*>(smem_raw);      // [NS (+D*D)][smax]
+	R* fl = st + (size_t)(LES ? L::NS_LES : L::NS) * smax;   // [NQ][fmax]
 	const TileDesc td = tv.tiles[tile0 + blockIdx.x];
 	const int ns = td.nt + td.nh;
 	const int nf = td.nfo + td.ninc;
@@ -362,6 +373,10 @@ __global__ void __launch_bounds__(NT, MINB)
 		for (int k = 0; k < D; k++) {
 			cp_async_elem(st + (L::DTDX + k) * smax + i, m.dTdx + (size_t)k * m.ncs + x);
 			cp_async_elem(st + (L::SIGMAU + k) * smax + i, m.sigmaU + (size_t)k * m.ncs + x);
+		}
+		if (LES) {
+#pragma unroll
+			for (int k = 0; k < D * D; k++) cp_async_elem(st + (L::TAUMC + k) * smax + i, m.tauMC + (size_t)k * m.ncs + x);
 		}
 	}
 	// the first face's constants travel while the copies land
@@ -385,7 +400,7 @@ __global__ void __launch_bounds__(NT, MINB)
 			for (int i = 0; i < D; i++) dv[i] = m.d[i * m.nfs + f];
 		}
 		R rhs[NQ];
-		face_flux<R, D, SCHEME>(m.k, SmemSide<R, D>{st, smax, lo}, SmemSide<R, D>{st, smax, ln}, cur.g, ghost, dv, rhs);
+		face_flux<R, D, SCHEME, SmemSide<R, D>, SmemSide<R, D>, LES>(m.k, SmemSide<R, D>{st, smax, lo}, SmemSide<R, D>{st, smax, ln}, cur.g, ghost, dv, rhs);
 #pragma unroll
 		for (int i = 0; i < NQ; i++) fl[i * fmax + lf] = rhs[i];
 		if (lf + NT < nf) cur = nxt;
@@ -505,6 +520,7 @@ template <class R, int D, int SMAX> struct SmemSide2 {
 	__device__ __forceinline__ R dudx(int a, int b) const { return sv[(L::DUDX - L::NQ + a * D + b) * SMAX + i]; }
 	__device__ __forceinline__ R dTdx(int a) const { return sv[(L::DTDX - L::NQ + a) * SMAX + i]; }
 	__device__ __forceinline__ R sigmaU(int a) const { return sv[(L::SIGMAU - L::NQ + a) * SMAX + i]; }
+	__device__ __forceinline__ R tauMC(int, int) const { return R(0); }   // the persistent kernel serves the laminar closure only
 };
 
 template <class R, int D, int SCHEME, int NT, int MINB, int SMAX, int FMAX>

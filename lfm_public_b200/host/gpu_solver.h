@@ -132,7 +132,7 @@ public:
 	void calc_gradients(MPI_env&) override { LFMGPU_OK(lfmgpu_gradients(handle(), this->m_nSubmeshIndex)); }
 	void calc_gradients_M2AUSM(MPI_env&) override { unsupported("calc_gradients_M2AUSM (solver 2)"); }
 	void calc_VIS(MPI_env&) override { LFMGPU_OK(lfmgpu_vis(handle(), this->m_nSubmeshIndex)); }
-	void calc_VIS_Smagorinsky(MPI_env&) override { unsupported("calc_VIS_Smagorinsky"); }
+	void calc_VIS_Smagorinsky(MPI_env&) override { LFMGPU_OK(lfmgpu_vis_smagorinsky(handle(), this->m_nSubmeshIndex)); }
 	void one_rk_step_M1(int rk_step, P dt, MPI_env&, P* RES) override { stage(LFMGPU_SCHEME_M1, rk_step, dt, RES); }
 	void one_rk_step_M2(int rk_step, P dt, MPI_env&, P* RES) override { stage(LFMGPU_SCHEME_M2, rk_step, dt, RES); }
 	void one_rk_step_M2AUSM(int, P, MPI_env&, P*) override { unsupported("one_rk_step_M2AUSM (solver 2)"); }

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--tile", default="8,4,4")
     ap.add_argument("--brick-order", default="morton")
+    ap.add_argument("--les", action="store_true", help="Smagorinsky closure (calc_VIS_Smagorinsky) instead of laminar")
     ap.add_argument("--set", action="append", default=[], help="NAME=v1,v2,... (environment knob and its values)")
     args = ap.parse_args()
     import bench
@@ -50,6 +51,8 @@ def main():
         except Exception as e:   # a knob combination the library rejects
             print(json.dumps({"knobs": dict(zip(names, combo)), "error": str(e)[:200]}), flush=True)
             continue
+        if args.les:
+            g.set_option("laminar", 0)
         g.warmup()
         g.step(args.scheme, dt, 2)
         g.sync()

@@ -25,6 +25,7 @@ typedef struct NAME(ctx) {
 	REAL gamma, gm1, Rgas_inv, mu, Cp, Pr_inv, rhoInf, UInf[3], EInf, pInf, TInf;
 	REAL Ak[LFMGPU_MAX_RK], Bk[LFMGPU_MAX_RK];
 	int comm_type;
+	int les;                        /* 0: calc_VIS, 1: calc_VIS_Smagorinsky */
 } NAME(ctx);
 
 static void* NAME(xcalloc)(size_t n, size_t sz) {
@@ -253,8 +254,10 @@ static void NAME(set_bc)(NAME(ctx)* c) {
 	}
 }
 
-/* the tau / sigmaU / tauMC block of calc_VIS (src/cfd_v0.cpp:1806-1857) for one cell record */
-static void NAME(vis_cell_terms)(NAME(ctx)* c, int x) {
+/* the tau / sigmaU / tauMC block of calc_VIS (src/cfd_v0.cpp:1806-1857) for one cell record; with les != 0 the block of
+ * calc_VIS_Smagorinsky (src/cfd_v0.cpp:1649-1690): the same plus the eddy-viscosity contribution to tauMC, with the
+ * smag_constant of the cell whose face loop is running (:1601-1602) */
+static void NAME(vis_cell_terms)(NAME(ctx)* c, int x, REAL smag_constant) {
 	const int D = c->D;
 	REAL mu = c->mu, diagSum;
 	REAL U[3], tau[3][3];
@@ -278,6 +281,25 @@ static void NAME(vis_cell_terms)(NAME(ctx)* c, int x) {
 		for (int j = 0; j < D; j++) c->tauMC[x * 9 + i * 3 + j] = mu * dudx[j * 3 + i];
 		c->tauMC[x * 9 + i * 3 + i] += diagSum;
 	}
+	if (c->les) {
+		const REAL HALF = 0.5;
+		REAL Strain_Mag = 0.0, S_ij = 0.0, divu = 0.0;
+		for (int i = 0; i < D; i++) {
+			for (int j = 0; j < D; j++) {
+				S_ij = HALF * (dudx[i * 3 + j] + dudx[j * 3 + i]);
+				Strain_Mag += pow(S_ij, 2);
+			}
+			divu += dudx[i * 3 + i];
+		}
+		Strain_Mag = sqrt(2.0 * Strain_Mag);
+		for (int i = 0; i < D; i++) {
+			for (int j = 0; j < D; j++) {
+				S_ij = HALF * (dudx[i * 3 + j] + dudx[j * 3 + i]);
+				c->tauMC[x * 9 + i * 3 + j] -= smag_constant * Strain_Mag * S_ij;
+			}
+			c->tauMC[x * 9 + i * 3 + i] += smag_constant * Strain_Mag * divu / (REAL)3.0;
+		}
+	}
 }
 
 /* src/cfd_v0.cpp:1744-1860 calc_VIS over one submesh */
@@ -289,6 +311,8 @@ static void NAME(vis)(NAME(ctx)* c, int sub) {
 	for (int t = c->sub_cell_start[sub]; t < c->sub_cell_start[sub + 1]; t++) {
 		const REAL* vq = &c->q[t * 5];
 		cell_Rpsi = NAME(compute_Rpsi)(c, vq);
+		/* Smagorinsky, non dynamic: -2*(Cs*Delta)^2 (src/cfd_v0.cpp:1601-1602) */
+		const REAL smag_constant = c->les ? -(REAL)2.0 * pow((REAL)0.16 * pow(1.0 / c->vol_inv[t], 1. / 3.), 2) : (REAL)0.0;
 		for (int f = c->cell_face_start[t]; f < c->cell_face_start[t + 1]; f++) {
 			const int n = c->face_neigh[f];
 			const REAL* nq = &c->q[n * 5];
@@ -313,8 +337,8 @@ static void NAME(vis)(NAME(ctx)* c, int sub) {
 				c->dTdx[t * 3 + i] += face_T * cell_sov[i];
 				c->dTdx[n * 3 + i] += face_T * adjc_sov[i];
 			}
-			NAME(vis_cell_terms)(c, t);
-			NAME(vis_cell_terms)(c, n);
+			NAME(vis_cell_terms)(c, t, smag_constant);
+			NAME(vis_cell_terms)(c, n, smag_constant);
 		}
 	}
 }

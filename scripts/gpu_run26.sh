@@ -1,0 +1,3 @@
+set -x
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/r26_pytest_gpu.log 2>&1; tail -15 gpurun_out/r26_pytest_gpu.log

@@ -61,6 +61,11 @@ CASES = {
     # O-grid cylinder with wall + inlet/outlet + cyclic span, 3D M2 (3D_Cylinder_Re3900 analogue)
     "ogrid3d_m2": dict(mesh=lambda: meshgen.ogrid_cylinder(8, 16, 4, r_in=0.5, r_out=6.0, span=1.0, stretch=4.0), two_d=False,
                        blocks=None, opts=dict(solver=1, dimension=3, deltaT=1e-3, Ls=2.0, mu=7.17948717948718e-05, haveForces=True)),
+    # LES closure: calc_VIS_Smagorinsky instead of calc_VIS (turbulenceProperties simulationType LES)
+    "hex3d_m2_les_p4": dict(mesh=_hex3d, two_d=False, blocks=(2, 2, 1),
+                            opts=dict(solver=1, dimension=3, deltaT=2e-3, Ls=0.4, commType=2, mu=7.17948717948718e-05, simulationType="LES")),
+    "ogrid3d_m1_les": dict(mesh=lambda: meshgen.ogrid_cylinder(8, 16, 4, r_in=0.5, r_out=6.0, span=1.0, stretch=4.0), two_d=False,
+                           blocks=None, opts=dict(solver=0, dimension=3, deltaT=1e-3, Ls=2.0, mu=7.17948717948718e-05, simulationType="LES")),
     "ogrid2d_m1": dict(mesh=lambda: meshgen.ogrid_cylinder(8, 16, 1, r_in=0.5, r_out=6.0, two_d=True, stretch=4.0), two_d=True,
                        blocks=None, opts=dict(solver=0, dimension=2, deltaT=1e-3, Ls=2.0, haveForces=True, haveAverage=True)),
 }

@@ -18,7 +18,7 @@ sys.path.insert(0, os.path.dirname(HERE))
 import common  # noqa: E402
 
 GOLDEN_CASES = ["quad2d_m1", "quad2d_m1_p4", "quad2d_m2_p2_packed", "tri2d_m2", "hex3d_m2", "hex3d_m2_p4", "hex3d_m1_p8",
-                "ogrid3d_m2", "ogrid2d_m1"]
+                "ogrid3d_m2", "ogrid2d_m1", "hex3d_m2_les_p4", "ogrid3d_m1_les"]
 GOLDEN_SP = ["quad2d_m1", "hex3d_m2_p4", "tri2d_m2"]
 
 
@@ -48,7 +48,10 @@ def make(name, sp=False):
 
 if __name__ == "__main__":
     assert common.have_ref() and common.have_ref(sp=True), "build oracle/_ref first (make -C oracle ref)"
+    only = sys.argv[1:]
     for n in GOLDEN_CASES:
-        make(n)
+        if not only or n in only:
+            make(n)
     for n in GOLDEN_SP:
-        make(n, sp=True)
+        if not only or n in only:
+            make(n, sp=True)

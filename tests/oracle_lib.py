@@ -24,6 +24,7 @@ def lib():
             getattr(L, f).argtypes = [C.c_void_p]
         L.lfmo_prepare_rkstep.argtypes = [C.c_void_p, C.c_int]
         L.lfmo_vis.argtypes = [C.c_void_p, C.c_int]
+        L.lfmo_set_les.argtypes = [C.c_void_p, C.c_int]
         L.lfmo_rk_stage.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p]
         L.lfmo_halo_count.restype = C.c_size_t
         L.lfmo_halo_count.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -55,6 +56,8 @@ class Oracle:
         self.n_ghost = d.n_bc_ghosts + d.n_mpi_ghosts
         self.real = np.float64 if d.precision == 8 else np.float32
         self.h = lib().lfmo_create(C.cast(case.desc_ptr, C.c_void_p))
+        if not case.opts.laminar:          # turbulenceProperties simulationType != laminar: calc_VIS_Smagorinsky
+            lib().lfmo_set_les(self.h, 1)
 
     def download(self, field):
         kind = FIELD_SHAPES[field]
