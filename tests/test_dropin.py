@@ -123,3 +123,30 @@ def test_dropin_mpi_env_modes(halo, comm, tmp_path):
     for r in range(o["n_ranks"]):
         for k in ("rho", "U", "E", "p"):
             assert np.array_equal(ref[r][k], gpu[r][k]), f"halo {halo} comm {comm} rank {r} field {k}: rel max {common.rel_max(ref[r][k], gpu[r][k]):.3e}"
+
+
+def _last_time_dir(d):
+    ts = [x for x in os.listdir(d) if x.replace(".", "", 1).replace("e-", "", 1).isdigit() and float(x) > 0]
+    return max(ts, key=float)
+
+
+@needs_bins
+def test_dropin_adjustable_time_step(tmp_path):
+    """adjustTimeStep yes: Mesh::solve takes dt = min over ranks of compute_dt(maxCo) every step (mesh_solver.cpp:705-717):
+    compute_dt runs on the device, the MPI_Allreduce(MIN) stays the reference's; same time levels, same fields."""
+    name = "quad2d_m1_p4"
+    ref_dir, gpu_dir = str(tmp_path / "ref"), str(tmp_path / "gpu")
+    m, o = common.build_case(name, ref_dir, adjustTimeStep=True, maxCo=0.4, endTime=0.2, writeInterval=N_STEPS)
+    shutil.copytree(ref_dir, gpu_dir)
+    out_ref = common.run_reference(ref_dir, o)
+    out_gpu = run_gpu_binary(gpu_dir, o, halo="host")
+    dts = lambda s: [l.split("dt:")[1].split()[0] for l in s.splitlines() if "dt:" in l]
+    assert len(dts(out_ref)) > N_STEPS and len(set(dts(out_ref))) > 1 and dts(out_ref) == dts(out_gpu)
+    ta = _last_time_dir(os.path.join(ref_dir, "processor0"))
+    tb = _last_time_dir(os.path.join(gpu_dir, "processor0"))
+    assert ta == tb
+    for r in range(o["n_ranks"]):
+        for k, nc in (("rho", 1), ("U", 3), ("E", 1), ("p", 1)):
+            a = common.read_field(os.path.join(ref_dir, f"processor{r}", ta, k), nc)
+            b = common.read_field(os.path.join(gpu_dir, f"processor{r}", tb, k), nc)
+            assert np.array_equal(a, b), f"rank {r} field {k}"
