@@ -1,5 +1,5 @@
 # Builds everything in-tree (the .so files travel with the gpurun snapshot; they are git-ignored).
-#   make            host library, CUDA library (sm_100a), host driver, oracle port (+ oracle/_ref when /root/reference exists)
+#   make            host library, CUDA library (sm_100a), oracle port (+ oracle/_ref: reference and drop-in binaries, when /root/reference exists)
 ROOT   := $(abspath .)
 PKG    := $(ROOT)/lfm_public_b200
 HOST   := $(PKG)/host
@@ -20,7 +20,7 @@ HOST_SRC := $(HOST)/foam_io.cpp $(HOST)/flatten.cpp $(HOST)/hostapi.cpp
 GPU_SRC  := $(CSRC)/lfmgpu.cu
 GPU_HDR  := $(wildcard $(CSRC)/*.cuh) $(INC)/lfmgpu.h
 
-.PHONY: all host gpu driver oracle ref clean
+.PHONY: all host gpu oracle clean
 all: host gpu oracle
 
 host: $(PKG)/liblfmhost.so
@@ -31,14 +31,10 @@ gpu: $(PKG)/liblfmgpu.so
 $(PKG)/liblfmgpu.so: $(GPU_SRC) $(GPU_HDR)
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(GPU_SRC) -Xlinker -rpath -Xlinker '$$ORIGIN' -lcudart -ldl
 
-driver: $(PKG)/lfm_solve_gpu
-$(PKG)/lfm_solve_gpu: $(HOST)/lfm_solve_gpu.cpp $(HOST)/gpu_solver.h $(PKG)/liblfmhost.so $(PKG)/liblfmgpu.so
-	$(CXX) -std=c++17 -O2 -I$(INC) -I$(HOST) -o $@ $(HOST)/lfm_solve_gpu.cpp -L$(PKG) -llfmhost -llfmgpu -Wl,-rpath,'$$ORIGIN'
-
 oracle:
 	$(MAKE) -C oracle port
 	@if [ -d $(REF)/src ]; then $(MAKE) -C oracle ref REF=$(REF); else echo "no $(REF): keeping prebuilt oracle/_ref"; fi
 
 clean:
-	rm -f $(PKG)/liblfmhost.so $(PKG)/liblfmgpu.so $(PKG)/lfm_solve_gpu
+	rm -f $(PKG)/liblfmhost.so $(PKG)/liblfmgpu.so
 	$(MAKE) -C oracle clean

@@ -2,10 +2,11 @@
 
 Only what the hot path needs lives here:
   csrc/       CUDA kernels + the C ABI (include/lfmgpu.h)            -> liblfmgpu.so
-  host/       C++ host: OpenFOAM-free case I/O, the reference's pre-loop setup restated, ISolver/Mesh mirror
-              (include/lfmhost.h)                                     -> liblfmhost.so, lfm_solve_gpu
+  host/       C++ host: gpu_solver.h = CFDv0_solver_gpu, the reference-side binding (INTEGRATION.md);
+              OpenFOAM-free case I/O and the reference's pre-loop setup restated (include/lfmhost.h) -> liblfmhost.so
   host_api.py / gpu_api.py   thin ctypes views of the two libraries (tests, bench)
-  tools/      synthetic polyMesh generators / decomposer / case writer (test + bench tooling)
+  tools/      synthetic polyMesh generators / decomposer / case writer, OpenFOAM case reader, renumbering tool,
+              tuning sweep (test + bench tooling)
 """
 from . import _ctypes_defs as defs  # noqa: F401
 

@@ -1,4 +1,5 @@
-// Baseline ("v1") kernels of the per-iteration solve on SoA state.
+// Unfused kernels of the per-iteration solve on SoA state (the fallback of the tile kernels, tile_kernels.cuh) and the
+// small per-step kernels (boundary ghosts, halo pack/unpack, reductions, post-processing).
 //
 // Determinism: every accumulated cell quantity (dudx, dTdx, dq, RES) is produced by ONE thread that
 // walks the cell's faces in ascending face id.  Faces are numbered in the order the reference's stage
@@ -37,7 +38,7 @@ template <class R> struct DevMesh {
 	R* tauMC;                          // [D*D][ncs]  only with the Smagorinsky closure (laminar: rebuilt from dudx where needed)
 	const R* smag_c;                   // [n_cells]   -2 (Cs Delta)^2 of the cell whose face loop leaves the cell's final tauMC
 	int les;                           // calc_VIS_Smagorinsky instead of calc_VIS
-	R* flux;                           // [NQ][nfs]   materialised face fluxes (v1 path)
+	R* flux;                           // [NQ][nfs]   materialised face fluxes (unfused path)
 	R *pAVG, *pRMS;
 	const int *bc_cell, *bc_kind, *bc_face, *bc_patch;
 	Consts<R> k;

@@ -153,7 +153,6 @@ struct lfmgpu_ctx {
 	int les_opt = 0;                   // option "laminar" == 0: lfmgpu_step / _step_multi use calc_VIS_Smagorinsky
 	int les = 0;                       // closure of the latest calc_VIS call (what the stage kernels and the halo pack see)
 	std::vector<int> smag_owner;       // cell whose face loop leaves each cell's final tauMC (Smagorinsky constant)
-	int prefetch_distance = 0;
 	int tile_smem_budget = 75 * 1024;  // bytes of shared memory one tile CTA may use
 	// introspection
 	uint64_t launches = 0;
@@ -1180,7 +1179,6 @@ int lfmgpu_create(const lfmgpu_desc* ds, int device, lfmgpu_t* out) {
 	if (const char* e = getenv("LFMGPU_STAGE_CFG")) h->stage_cfg = atoi(e);
 	if (const char* e = getenv("LFMGPU_USE_TILES")) h->use_tiles = atoi(e);
 	if (const char* e = getenv("LFMGPU_FIXED_STRIDES")) h->fixed_strides = atoi(e);
-	if (const char* e = getenv("LFMGPU_PREFETCH")) h->prefetch_distance = atoi(e);
 	if (const char* e = getenv("LFMGPU_TILE_SMEM")) h->tile_smem_budget = std::max(16, atoi(e)) * 1024;
 	if (!rc) rc = tile_plan_build(h, ds);
 	if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = fail("upload failed: %s", cudaGetErrorString(cudaGetLastError()));

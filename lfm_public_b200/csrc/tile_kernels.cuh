@@ -654,7 +654,7 @@ __global__ void __launch_bounds__(NT, MINB)
 // host-side description of the plan (device arrays are owned by the handle's allocation list)
 struct TilePlan {
 	bool ready = false;
-	int n_tiles = 0, tile_cells = 0, threads = 128;
+	int n_tiles = 0, tile_cells = 0;
 	int sub_tile_start[LFMGPU_MAX_SUBMESH + 1] = {0};
 	int sub_smax[LFMGPU_MAX_SUBMESH] = {0}, sub_fmax[LFMGPU_MAX_SUBMESH] = {0};
 	size_t smem_bytes = 0;            // largest k_tile_stage request
