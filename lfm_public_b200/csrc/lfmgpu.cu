@@ -575,12 +575,22 @@ void tile_range(const lfmgpu_ctx* h, int sub, int& t0, int& t1, int& smax, int& 
 
 constexpr int kGradThreads = 128;
 
+// every submesh of the plan fits the compile-time shared-memory strides
+bool all_fixed(const lfmgpu_ctx* h) {
+	if (!h->fixed_strides) return false;
+	for (int s = 0; s < h->n_sub; s++)
+		if (h->tiles.sub_smax[s] > kFixedSmax || h->tiles.sub_fmax[s] > kFixedFmax) return false;
+	return true;
+}
+
 
 template <class R, int D> size_t stage_smem(int smax, int fmax) { return ((size_t)StagedLayout<D>::NS * smax + (size_t)(D + 2) * fmax) * sizeof(R); }
 template <class R, int D> size_t grad_smem(int smax, int fmax) { return ((size_t)(D + 2) * smax + (size_t)(D + 1) * fmax) * sizeof(R) + (size_t)fmax * sizeof(uint32_t); }
 
 template <class R, int D> int tile_grad(lfmgpu_ctx* h, int sub) {
-	if (sub < 0) {   // every submesh: one launch each, so that each gets its own shared-memory size
+	// every submesh at once (a rank without neighbours): one launch when all of them fit the compile-time strides (same
+	// shared-memory size anyway), else one launch each so that each gets its own shared-memory size
+	if (sub < 0 && !all_fixed(h)) {
 		for (int s = 0; s < h->n_sub; s++) TRY((tile_grad<R, D>(h, s)));
 		return 0;
 	}
@@ -602,7 +612,7 @@ template <class R, int D> int tile_grad(lfmgpu_ctx* h, int sub) {
 }
 
 template <class R, int D, int SCHEME> int tile_stage_s(lfmgpu_ctx* h, int sub, R dt, R Ak, R Bk, int first, int res) {
-	if (sub < 0) {
+	if (sub < 0 && !all_fixed(h)) {
 		for (int s = 0; s < h->n_sub; s++) TRY((tile_stage_s<R, D, SCHEME>(h, s, dt, Ak, Bk, first, res)));
 		return 0;
 	}
