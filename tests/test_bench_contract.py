@@ -1,0 +1,41 @@
+"""bench.py keeps the driver's contract: one JSON line with the agreed keys, for the reference arm (CPU) and the CUDA arm."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+import common
+
+BENCH = os.path.join(common.ROOT, "bench.py")
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+             "config", "e2e", "cpu_baseline", "gpu_launches"}
+
+
+def _run(args, timeout=900):
+    out = subprocess.run([sys.executable, BENCH] + args, capture_output=True, text=True, timeout=timeout, cwd=common.ROOT)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, out.stdout[-2000:]
+    return json.loads(lines[0])
+
+
+@pytest.mark.skipif(not common.have_ref(), reason="reference binary not built")
+def test_reference_arm_line():
+    d = _run(["--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-n", "16"])
+    assert d["impl"] == "reference" and BASE_KEYS <= set(d) and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["config"]["workload"]
+
+
+@pytest.mark.gpu
+def test_cuda_arm_line():
+    d = _run(["--n", "32", "--steps", "2", "--warmup", "3", "--ref-n", "16", "--ref-steps", "2"])
+    assert BASE_KEYS | {"roofline", "clocks"} <= set(d)
+    assert d["n_gpus"] == 1 and d["dtype"] == "f64" and d["value"] > 0 and d["finite"] and d["gpu_launches"] > 0
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["kernel"] == "tile_stage" and 0 < r["frac"] < 1.5 and r["unit"] == "GB/s"
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == e["d2h_bytes_per_step"] == 5 * 32 ** 3 * 8 and e["finite"]
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] > 0
