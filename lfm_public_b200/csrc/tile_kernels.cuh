@@ -352,6 +352,7 @@ __global__ void __launch_bounds__(NT, MINB)
     k_tile_stage(DevMesh<R> m, TileView<R> tv, const R* __restrict__ q, const R* __restrict__ drv, R* __restrict__ qn, R* __restrict__ drvn, int tile0, R dt, R Ak, R Bk, int first, int res) {
 	using L = StagedLayout<D>;
 	constexpr int NQ = D + 2;
+	static_assert(NT % 64 == 0, "phase C splits the CTA into two halves of whole warps (a barrier sits inside each half's code path)");
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int smax = SMAX ? SMAX : tv.smax, fmax = FMAX ? FMAX : tv.fmax;
 	R* st = reinterpret_cast<R*>(smem_raw);      // [NS (+D*D)][smax]
