@@ -20,12 +20,15 @@ typedef struct NAME(ctx) {
 	REAL *q, *dq, *RES;             /* stride 5 */
 	REAL *dudx, *tauMC;             /* stride 9 ([i*3+j]) */
 	REAL *dTdx, *sigmaU;            /* stride 3 */
+	REAL *rho_grad, *p_grad;        /* stride 3; solver 2 (M2-AUSM) only */
+	REAL *U_grad;                   /* stride 9 ([i*3+j] = dU_i/dx_j) */
 	unsigned char* is_ghost;
 	REAL *pAVG, *pRMS;
 	REAL gamma, gm1, Rgas_inv, mu, Cp, Pr_inv, rhoInf, UInf[3], EInf, pInf, TInf;
 	REAL Ak[LFMGPU_MAX_RK], Bk[LFMGPU_MAX_RK];
 	int comm_type;
 	int les;                        /* 0: calc_VIS, 1: calc_VIS_Smagorinsky */
+	int minmod;                     /* fvSchemes lfm/minmodExists: Mesh::solve calls calc_gradients[_M2AUSM] */
 } NAME(ctx);
 
 static void* NAME(xcalloc)(size_t n, size_t sz) {
@@ -88,6 +91,9 @@ static NAME(ctx)* NAME(create)(const lfmgpu_desc* ds) {
 	c->tauMC = (REAL*)NAME(xcalloc)((size_t)c->n_tot * 9, sizeof(REAL));
 	c->dTdx = (REAL*)NAME(xcalloc)((size_t)c->n_tot * 3, sizeof(REAL));
 	c->sigmaU = (REAL*)NAME(xcalloc)((size_t)c->n_tot * 3, sizeof(REAL));
+	c->rho_grad = (REAL*)NAME(xcalloc)((size_t)c->n_tot * 3, sizeof(REAL));
+	c->p_grad = (REAL*)NAME(xcalloc)((size_t)c->n_tot * 3, sizeof(REAL));
+	c->U_grad = (REAL*)NAME(xcalloc)((size_t)c->n_tot * 9, sizeof(REAL));
 	c->is_ghost = (unsigned char*)NAME(xcalloc)((size_t)c->n_tot, 1);
 	c->pAVG = (REAL*)NAME(xcalloc)((size_t)c->n_cells, sizeof(REAL));
 	c->pRMS = (REAL*)NAME(xcalloc)((size_t)c->n_cells, sizeof(REAL));
@@ -168,7 +174,8 @@ static void NAME(prepare_rkstep)(NAME(ctx)* c, int rk) {
 	for (int t = 0; t < c->n_cells; t++) {
 		for (int i = 0; i < c->NQ; i++) c->dq[t * 5 + i] *= c->Ak[rk];
 		for (int i = 0; i < 9; i++) c->dudx[t * 9 + i] = c->tauMC[t * 9 + i] = 0.;
-		for (int i = 0; i < 3; i++) c->dTdx[t * 3 + i] = 0.;
+		for (int i = 0; i < 3; i++) c->dTdx[t * 3 + i] = c->rho_grad[t * 3 + i] = c->p_grad[t * 3 + i] = 0.;
+		for (int i = 0; i < 9; i++) c->U_grad[t * 9 + i] = 0.;
 	}
 	for (int g = 0; g < c->n_bc; g++) c->is_ghost[c->n_cells + g] = 1;
 }
@@ -343,6 +350,93 @@ static void NAME(vis)(NAME(ctx)* c, int sub) {
 	}
 }
 
+/* src/cfd_v0.cpp:1384-1495 calc_gradients_M2AUSM over one submesh: Green-Gauss gradients of rho, p and U (the ones
+ * one_rk_step_M2AUSM reads; rhoU_grad, rhoE_grad, Rpsi_grad and c_grad are computed by the reference and never used).
+ * Ghost cells have vol_inv == 0 (never set by the reference), so nothing accumulates in them. */
+static void NAME(gradients_ausm)(NAME(ctx)* c, int sub) {
+	const int D = c->D;
+	const REAL HALF = 0.5;
+	REAL UU[3], cell_sov[3], adjc_sov[3];
+	for (int t = c->sub_cell_start[sub]; t < c->sub_cell_start[sub + 1]; t++) {
+		const REAL* vq = &c->q[t * 5];
+		for (int f = c->cell_face_start[t]; f < c->cell_face_start[t + 1]; f++) {
+			const int n = c->face_neigh[f];
+			const REAL* nq = &c->q[n * 5];
+			const REAL* S = &c->S[f * 3];
+			const REAL w = c->w[f];
+			for (int i = 0; i < D; i++) UU[i] = INTERP_LINEAR(w, vq[i + 1] / vq[0], nq[i + 1] / nq[0]);
+			const REAL rho = INTERP_LINEAR(w, vq[0], nq[0]);
+			for (int i = 0; i < D; i++) {
+				cell_sov[i] = S[i] * c->vol_inv[t];
+				adjc_sov[i] = -S[i] * c->vol_inv[n];
+			}
+			REAL r = vq[0];
+			REAL E = vq[D + 1] / r;
+			REAL vmag = 0.0;
+			for (int i = 0; i < D; i++) vmag += (vq[i + 1] / r) * (vq[i + 1] / r);
+			const REAL cell_p = r * c->gm1 * (E - HALF * vmag);
+			r = nq[0];
+			E = nq[D + 1] / r;
+			vmag = 0.0;
+			for (int i = 0; i < D; i++) vmag += (nq[i + 1] / r) * (nq[i + 1] / r);
+			const REAL neigh_p = r * c->gm1 * (E - HALF * vmag);
+			const REAL p = INTERP_LINEAR(w, cell_p, neigh_p);
+			for (int i = 0; i < D; i++) {
+				c->p_grad[t * 3 + i] += p * cell_sov[i];
+				c->p_grad[n * 3 + i] += p * adjc_sov[i];
+				for (int j = 0; j < D; j++) {
+					c->U_grad[t * 9 + j * 3 + i] += UU[j] * cell_sov[i];
+					c->U_grad[n * 9 + j * 3 + i] += UU[j] * adjc_sov[i];
+				}
+				c->rho_grad[t * 3 + i] += rho * cell_sov[i];
+				c->rho_grad[n * 3 + i] += rho * adjc_sov[i];
+			}
+		}
+	}
+}
+
+/* api/cfdv0_solver.h:311-370 calc_r / interp_minmod */
+static REAL NAME(sign)(REAL a) { return a < 0.0 ? -1.0 : 1.0; }
+static REAL NAME(calc_r)(int D, REAL phiP, REAL phiN, const REAL* phiGrad, const REAL* d) {
+	const REAL ONE = 1.0, ZERO = 0.0;
+	REAL gradf = phiN - phiP + 1.0e-30;
+	REAL gradcf = ZERO;
+	for (int i = 0; i < D; i++) gradcf += d[i] * phiGrad[i];
+	if (FABS(gradcf) >= 1000.0 * FABS(gradf)) return 2.0 * 1000.0 * NAME(sign)(gradcf) * NAME(sign)(gradf) - ONE;
+	return 2.0 * (gradcf / gradf) - ONE;
+}
+static REAL NAME(interp_minmod)(int D, REAL cell_phi, REAL adjc_phi, const REAL* grad_phi, const REAL* d, REAL weight_linear, REAL flux) {
+	const REAL ONE = 1.0, ZERO = 0.0, HALF = 0.5;
+	const REAL r = NAME(calc_r)(D, cell_phi, adjc_phi, grad_phi, d);
+	const REAL rm = r < ONE ? r : ONE;               /* min(r, ONE) */
+	const REAL limiter = rm < ZERO ? ZERO : rm;      /* max(.., ZERO) */
+	const REAL weight = limiter * weight_linear + (ONE - limiter) * (ONE + flux) * HALF;
+	return weight * cell_phi + (ONE - weight) * adjc_phi;
+}
+/* src/cfd_v0.cpp:1863-1894 */
+static REAL NAME(p5Pos)(REAL M, REAL alpha) {
+	REAL M2Pos = 0.25 * (M + 1.0) * (M + 1.0);
+	REAL M2Neg = -0.25 * (M - 1.0) * (M - 1.0);
+	REAL M1Pos = 0.5 * (M + FABS(M));
+	REAL p5;
+	if (FABS(M) < 1)
+		p5 = M2Pos * ((2.0 - M) - 16.0 * alpha * M * M2Neg);
+	else
+		p5 = M1Pos / M;
+	return p5;
+}
+static REAL NAME(p5Neg)(REAL M, REAL alpha) {
+	REAL M2Pos = 0.25 * (M + 1.0) * (M + 1.0);
+	REAL M2Neg = -0.25 * (M - 1.0) * (M - 1.0);
+	REAL M1Neg = 0.5 * (M - FABS(M));
+	REAL p5;
+	if (FABS(M) < 1)
+		p5 = M2Neg * ((-2.0 - M) + 16.0 * alpha * M * M2Pos);
+	else
+		p5 = M1Neg / M;
+	return p5;
+}
+
 /* src/cfd_v0.cpp:2530-2832 one_rk_step_M1 and :1897-2179 one_rk_step_M2 over one submesh.
  * RES_out (D+2 accumulators) may be NULL. */
 static void NAME(rk_stage)(NAME(ctx)* c, int sub, int scheme, int rk_step, REAL dt, REAL* RES_out) {
@@ -453,6 +547,60 @@ static void NAME(rk_stage)(NAME(ctx)* c, int sub, int scheme, int rk_step, REAL 
 				cell_H = cq[D + 1] / cq[0] + cell_Rpsi;
 				adjc_H = nq[D + 1] / nq[0] + adjc_Rpsi;
 				Havg = HALF * (cell_H + adjc_H);
+				if (scheme == 2) {
+					/* ---- AUSM+up pressure dissipation behind a shock sensor (cfd_v0.cpp:2270-2341) ---- */
+					const REAL M_ONE = -1.0;
+					REAL cell_divu = 0., neigh_divu = 0., cell_curlu = 0., neigh_curlu = 0., cell_vmag = 0., neigh_vmag = 0.;
+					REAL unPos = 0., unNeg = 0., norm = 0., cell_u[3], neigh_u[3];
+					const REAL* cd = &c->dudx[t * 9];
+					const REAL* nd = &c->dudx[n * 9];
+					cP = SQRT(c->gamma * cell_Rpsi);
+					cN = SQRT(c->gamma * adjc_Rpsi);
+					cavg = HALF * (cP + cN);
+					for (int nD = 0; nD < D; nD++) {
+						cell_divu += cd[nD * 3 + nD];
+						neigh_divu += nd[nD * 3 + nD];
+						for (int nD2 = nD + 1; nD2 < D; nD2++) {
+							cell_curlu += (cd[nD * 3 + nD2] - cd[nD2 * 3 + nD]) * (cd[nD * 3 + nD2] - cd[nD2 * 3 + nD]);
+							neigh_curlu += (nd[nD * 3 + nD2] - nd[nD2 * 3 + nD]) * (nd[nD * 3 + nD2] - nd[nD2 * 3 + nD]);
+						}
+						cell_u[nD] = cq[nD + 1] / cq[0];
+						cell_vmag += cell_u[nD] * cell_u[nD];
+						neigh_u[nD] = nq[nD + 1] / nq[0];
+						neigh_vmag += neigh_u[nD] * neigh_u[nD];
+						const REAL uP = NAME(interp_minmod)(D, cell_u[nD], neigh_u[nD], &c->U_grad[t * 9 + nD * 3], dv, weight, ONE);
+						const REAL uN = NAME(interp_minmod)(D, cell_u[nD], neigh_u[nD], &c->U_grad[n * 9 + nD * 3], dv, weight, M_ONE);
+						unPos += uP * S[nD];
+						unNeg += uN * S[nD];
+						norm += S[nD] * S[nD];
+					}
+					REAL th = -(cell_divu / sqrt(cell_divu * cell_divu + cell_curlu + 4e-2));
+					const REAL cell_theta = th > 0. ? th : 0.;
+					th = -(neigh_divu / sqrt(neigh_divu * neigh_divu + neigh_curlu + 4e-2));
+					const REAL neigh_theta = th > 0. ? th : 0.;
+					const REAL theta_avg = HALF * (cell_theta + neigh_theta);
+					REAL r = cq[0];
+					REAL E = cq[D + 1] / r;
+					const REAL cell_p = r * c->gm1 * (E - HALF * cell_vmag);
+					r = nq[0];
+					E = nq[D + 1] / r;
+					const REAL neigh_p = r * c->gm1 * (E - HALF * neigh_vmag);
+					const REAL rhoP = NAME(interp_minmod)(D, cq[0], nq[0], &c->rho_grad[t * 3], dv, weight, ONE);
+					const REAL rhoN = NAME(interp_minmod)(D, cq[0], nq[0], &c->rho_grad[n * 3], dv, weight, M_ONE);
+					const REAL pP = NAME(interp_minmod)(D, cell_p, neigh_p, &c->p_grad[t * 3], dv, weight, ONE);
+					const REAL pN = NAME(interp_minmod)(D, cell_p, neigh_p, &c->p_grad[n * 3], dv, weight, M_ONE);
+					const REAL Msq = (unPos * unPos + unNeg * unNeg) / (2. * cavg * cavg * norm);
+					const REAL MPos = unPos / (sqrt(norm) * cavg);
+					const REAL MNeg = unNeg / (sqrt(norm) * cavg);
+					const REAL Minf = 0.2;
+					REAL mx = Msq > Minf * Minf ? Msq : Minf * Minf;           /* max(Msq, Minf*Minf) */
+					const REAL M0 = sqrt((REAL)1.0 < mx ? (REAL)1.0 : mx);     /* sqrt(min(1.0, ..)) */
+					const REAL fa = M0 * (2.0 - M0);
+					const REAL alpha = 3.0 * (5.0 * fa * fa - 4.0) / 16.0;
+					const REAL phalf = pN * (NAME(p5Pos)(MNeg, alpha) - NAME(p5Neg)(MNeg, alpha)) - pP * (NAME(p5Pos)(MPos, alpha) - NAME(p5Neg)(MPos, alpha));
+					const REAL pu = -0.75 * NAME(p5Pos)(MPos, alpha) * NAME(p5Neg)(MNeg, alpha) * (rhoP + rhoN) * cavg * fa * (unNeg - unPos);
+					pavg += theta_avg * (pu - HALF * phalf);
+				}
 				phiavg = 0.0;
 				for (int i = 0; i < D; i++) {
 					uavg[i] = rhoUavg[i] * rhoavg_inv;

@@ -66,6 +66,12 @@ CASES = {
                             opts=dict(solver=1, dimension=3, deltaT=2e-3, Ls=0.4, commType=2, mu=7.17948717948718e-05, simulationType="LES")),
     "ogrid3d_m1_les": dict(mesh=lambda: meshgen.ogrid_cylinder(8, 16, 4, r_in=0.5, r_out=6.0, span=1.0, stretch=4.0), two_d=False,
                            blocks=None, opts=dict(solver=0, dimension=3, deltaT=1e-3, Ls=2.0, mu=7.17948717948718e-05, simulationType="LES")),
+    # solver 2: M2 + AUSM+up pressure dissipation with minmod-limited reconstruction (one_rk_step_M2AUSM)
+    "hex3d_ausm_p4": dict(mesh=_hex3d, two_d=False, blocks=(2, 2, 1),
+                          opts=dict(solver=2, dimension=3, deltaT=2e-3, Ls=0.4, commType=2, mu=7.17948717948718e-05, minmodExists=True)),
+    "ogrid2d_ausm": dict(mesh=lambda: meshgen.ogrid_cylinder(8, 16, 1, r_in=0.5, r_out=6.0, two_d=True, stretch=4.0), two_d=True,
+                         blocks=None, opts=dict(solver=2, dimension=2, deltaT=1e-3, Ls=2.0, minmodExists=True)),
+    "quad2d_ausm_nominmod": dict(mesh=_quad2d, two_d=True, blocks=None, opts=dict(solver=2, dimension=2, deltaT=2e-3, Ls=1.0)),
     "ogrid2d_m1": dict(mesh=lambda: meshgen.ogrid_cylinder(8, 16, 1, r_in=0.5, r_out=6.0, two_d=True, stretch=4.0), two_d=True,
                        blocks=None, opts=dict(solver=0, dimension=2, deltaT=1e-3, Ls=2.0, haveForces=True, haveAverage=True)),
 }

@@ -18,7 +18,7 @@ sys.path.insert(0, os.path.dirname(HERE))
 import common  # noqa: E402
 
 GOLDEN_CASES = ["quad2d_m1", "quad2d_m1_p4", "quad2d_m2_p2_packed", "tri2d_m2", "hex3d_m2", "hex3d_m2_p4", "hex3d_m1_p8",
-                "ogrid3d_m2", "ogrid2d_m1", "hex3d_m2_les_p4", "ogrid3d_m1_les"]
+                "ogrid3d_m2", "ogrid2d_m1", "hex3d_m2_les_p4", "ogrid3d_m1_les", "hex3d_ausm_p4", "ogrid2d_ausm"]
 GOLDEN_SP = ["quad2d_m1", "hex3d_m2_p4", "tri2d_m2"]
 
 

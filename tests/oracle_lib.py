@@ -25,6 +25,8 @@ def lib():
         L.lfmo_prepare_rkstep.argtypes = [C.c_void_p, C.c_int]
         L.lfmo_vis.argtypes = [C.c_void_p, C.c_int]
         L.lfmo_set_les.argtypes = [C.c_void_p, C.c_int]
+        L.lfmo_set_minmod.argtypes = [C.c_void_p, C.c_int]
+        L.lfmo_gradients_ausm.argtypes = [C.c_void_p, C.c_int]
         L.lfmo_rk_stage.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p]
         L.lfmo_halo_count.restype = C.c_size_t
         L.lfmo_halo_count.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -58,6 +60,8 @@ class Oracle:
         self.h = lib().lfmo_create(C.cast(case.desc_ptr, C.c_void_p))
         if not case.opts.laminar:          # turbulenceProperties simulationType != laminar: calc_VIS_Smagorinsky
             lib().lfmo_set_les(self.h, 1)
+        if case.opts.minmod:
+            lib().lfmo_set_minmod(self.h, 1)
 
     def download(self, field):
         kind = FIELD_SHAPES[field]
@@ -114,6 +118,7 @@ def lockstep_run(oracles, cases, scheme, dt, n_steps, record=None):
     D = oracles[0].D
     comm_type = cases[0].desc.c.comm_type
     recv = [{0: None, 1: None} for _ in range(n)]
+    grads = scheme == 2 and bool(cases[0].opts.minmod)     # calc_gradients_M2AUSM (only solver 2 reads the minmod gradients)
 
     def exchange(step):
         spc = scalars_per_cell(D, comm_type, step)
@@ -151,9 +156,14 @@ def lockstep_run(oracles, cases, scheme, dt, n_steps, record=None):
                 o.prepare_rkstep(rk)
                 unpack(r, 0)
                 o.set_bc()
+                if grads:
+                    o.gradients_ausm(0)
                 o.vis(0)
             exchange(1)
             for r, o in enumerate(oracles):
+                for s in range(1, cases[r].desc.n_sub):
+                    if grads:
+                        o.gradients_ausm(s)
                 for s in range(1, cases[r].desc.n_sub):
                     o.vis(s)
                 unpack(r, 1)
@@ -171,6 +181,7 @@ def drive_rank(orc, exchange, scheme, dt, n_steps):
     job's transport and unpacks them (ghost cells are only read by the boundary submesh's next call, so unpacking
     right after the exchange is equivalent to the reference's later mpi_wait)."""
     d = orc.case.desc
+    grads = scheme == 2 and bool(orc.case.opts.minmod)
     exchange(0)
     orc.set_bc()
     exchange(1)
@@ -180,8 +191,13 @@ def drive_rank(orc, exchange, scheme, dt, n_steps):
         for rk in range(d.c.rk_order):
             orc.prepare_rkstep(rk)
             orc.set_bc()
+            if grads:
+                orc.gradients_ausm(0)
             orc.vis(0)
             exchange(1)
+            for s in range(1, d.n_sub):
+                if grads:
+                    orc.gradients_ausm(s)
             for s in range(1, d.n_sub):
                 orc.vis(s)
             orc.rk_stage(0, scheme, rk, dt, None)
