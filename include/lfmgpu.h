@@ -27,7 +27,7 @@ extern "C" {
 #define LFMGPU_MAX_RK 8
 
 /* scheme selector == fastmesh_solver_t (reference: api/fastmesh.h:36-39) */
-enum { LFMGPU_SCHEME_M1 = 0, LFMGPU_SCHEME_M2 = 1 };
+enum { LFMGPU_SCHEME_M1 = 0, LFMGPU_SCHEME_M2 = 1, LFMGPU_SCHEME_M2AUSM = 2 };
 /* physical boundary roles (reference: src/cfd_v0.cpp:973-1005 init_boundary_conditions) */
 enum { LFMGPU_BC_NONE = 0, LFMGPU_BC_WALL = 1, LFMGPU_BC_INLET = 2, LFMGPU_BC_OUTLET = 3 };
 /* payload modes == t_mpi_comm_type (reference: api/mpi_env.h:34-39); FULL_BND is served as PACKED */
@@ -119,11 +119,12 @@ int lfmgpu_sync(lfmgpu_t h);                                 /* wait for all str
 int lfmgpu_prepare_timestep(lfmgpu_t h);                     /* cfd_v0.cpp:1326  dq = RES = 0           */
 int lfmgpu_prepare_rkstep(lfmgpu_t h, int rk_step);          /* cfd_v0.cpp:1339  dq *= A_k (folded)     */
 int lfmgpu_set_bc(lfmgpu_t h);                               /* cfd_v0.cpp:1010  set_boundary_conditions*/
-int lfmgpu_gradients(lfmgpu_t h, int submesh);               /* cfd_v0.cpp:1501  calc_gradients (minmod)*/
+int lfmgpu_gradients(lfmgpu_t h, int submesh);               /* cfd_v0.cpp:1501  calc_gradients (minmod; outputs unread by M1/M2: no work) */
+int lfmgpu_gradients_m2ausm(lfmgpu_t h, int submesh);        /* cfd_v0.cpp:1384  calc_gradients_M2AUSM (rho, p, U gradients of solver 2) */
 int lfmgpu_vis(lfmgpu_t h, int submesh);                     /* cfd_v0.cpp:1744  calc_VIS (laminar)     */
 int lfmgpu_vis_smagorinsky(lfmgpu_t h, int submesh);         /* cfd_v0.cpp:1574  calc_VIS_Smagorinsky   */
 int lfmgpu_rk_stage(lfmgpu_t h, int submesh, int scheme, int rk_step, double dt, int want_res);
-                                                             /* cfd_v0.cpp:2530 / 1897 one_rk_step_M1/M2 */
+                                                             /* cfd_v0.cpp:2530 / 1897 / 2186 one_rk_step_M1/_M2/_M2AUSM */
 int lfmgpu_halo_start(lfmgpu_t h, int comm_step);            /* cfd_v0.cpp:3547  mpi_communication      */
 int lfmgpu_halo_wait(lfmgpu_t h, int comm_step);             /* cfd_v0.cpp:3576  mpi_wait (+unpack)     */
 int lfmgpu_cfl(lfmgpu_t h, double dt, double* cfl_max);      /* cfd_v0.cpp:2887  compute_cfl (blocking) */
@@ -146,7 +147,9 @@ int lfmgpu_step_multi(const lfmgpu_t* hs, int n_ranks, int scheme, double dt, in
 int lfmgpu_allreduce(lfmgpu_t h, double* values, int n, int op);
 /* Options: "use_tiles" 1 (default) = fused shared-memory tile kernels, 0 = face kernel + gather kernels (tuning);
  * "laminar" 1 (default) / 0 = lfmgpu_step and lfmgpu_step_multi call calc_VIS / calc_VIS_Smagorinsky
- * (CInputReader::m_bLaminar, reference: src/inputReader.cpp:60, src/mesh_solver.cpp:556-560). */
+ * (CInputReader::m_bLaminar, reference: src/inputReader.cpp:60, src/mesh_solver.cpp:556-560);
+ * "minmod" 0 (default) / 1 = with LFMGPU_SCHEME_M2AUSM those loops call calc_gradients_M2AUSM before calc_VIS
+ * (fvSchemes lfm/minmodExists, mesh_solver.cpp:537-548, 582-594; lfmgpu_step's minmod argument sets it too). */
 int lfmgpu_set_option(lfmgpu_t h, const char* name, int value);
 
 /* ---- data movement --------------------------------------------------------------------------------- */

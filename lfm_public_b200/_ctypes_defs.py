@@ -4,7 +4,7 @@ import ctypes as C
 MAX_SUBMESH = 8
 MAX_RK = 8
 
-SCHEME_M1, SCHEME_M2 = 0, 1
+SCHEME_M1, SCHEME_M2, SCHEME_M2AUSM = 0, 1, 2
 BC_NONE, BC_WALL, BC_INLET, BC_OUTLET = 0, 1, 2, 3
 COMM_FULL_BND, COMM_PACKED, COMM_SPLIT = 0, 1, 2
 (FIELD_Q, FIELD_DQ, FIELD_DUDX, FIELD_DTDX, FIELD_RES, FIELD_PAVG, FIELD_PRMS, FIELD_QGHOST, FIELD_TAUMC,

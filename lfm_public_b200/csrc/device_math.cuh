@@ -214,8 +214,9 @@ template <class R, int D> __device__ __forceinline__ void ghost_face_viscous(con
 // vector) is only read in that case.
 // LES != 0: tauMC of both sides is read from the sides (c.tauMC(i, j), stored by the Smagorinsky gradient pass) instead of
 // being rebuilt from dudx.
+// SCHEME 2 (M2-AUSM): the M2 flux with `pavg_extra` (ausm_pressure_term) added to the face pressure (cfd_v0.cpp:2341).
 template <class R, int D, int SCHEME, class SideC, class SideN, int LES = 0>
-__device__ __forceinline__ void face_flux(const Consts<R>& k, const SideC& c, const SideN& n, const FaceGeo<R, D>& g, bool ghost, const R* dv, R* rhs) {
+__device__ __forceinline__ void face_flux(const Consts<R>& k, const SideC& c, const SideN& n, const FaceGeo<R, D>& g, bool ghost, const R* dv, R* rhs, R pavg_extra = R(0)) {
 	const R ONE = R(1.0), HALF = R(0.5), ZERO = R(0.0);
 	const R weight = g.w;
 	const R* S = g.S;
@@ -302,7 +303,8 @@ __device__ __forceinline__ void face_flux(const Consts<R>& k, const SideC& c, co
 		const R rhoavg = HALF * (c.q(0) + n.q(0));
 		const R rhoavg_inv = ONE / rhoavg;
 		const R Rpsiavg = HALF * (c.Rpsi() + n.Rpsi());
-		const R pavg = rhoavg * Rpsiavg;
+		R pavg = rhoavg * Rpsiavg;
+		if (SCHEME == 2) pavg += pavg_extra;
 		const R Havg = HALF * (c.aux() + n.aux());
 		R rhoUavg[D];
 		R phiavg = ZERO;
@@ -388,6 +390,98 @@ __device__ __forceinline__ void face_flux(const Consts<R>& k, const SideC& c, co
 	}
 	const R lapT = k.kappa * (g.delta_mag * (nT - cT) * dmag_inv + KdTdx);
 	rhs[D + 1] += divSigmaU + lapT;
+}
+
+// ---- solver 2: AUSM+up pressure dissipation behind a shock sensor (cfd_v0.cpp:2270-2341) -------------------------
+// calc_r / interp_minmod (api/cfdv0_solver.h:311-370), p5Pos / p5Neg (cfd_v0.cpp:1863-1894)
+template <class R> __device__ __forceinline__ R lfm_abs(R x) { return x < R(0) ? -x : x; }
+template <class R> __device__ __forceinline__ R sign_of(R a) { return a < R(0.0) ? R(-1.0) : R(1.0); }
+template <class R, int D> __device__ __forceinline__ R calc_r(R phiP, R phiN, const R* phiGrad, const R* d) {
+	const R gradf = phiN - phiP + R(1.0e-30);
+	R gradcf = R(0);
+#pragma unroll
+	for (int i = 0; i < D; i++) gradcf += d[i] * phiGrad[i];
+	if (lfm_abs(gradcf) >= R(1000.0) * lfm_abs(gradf)) return R(2.0) * R(1000.0) * sign_of(gradcf) * sign_of(gradf) - R(1.0);
+	return R(2.0) * (gradcf / gradf) - R(1.0);
+}
+template <class R, int D> __device__ __forceinline__ R interp_minmod(R cell_phi, R adjc_phi, const R* grad_phi, const R* d, R weight_linear, R flux) {
+	const R ONE = R(1.0), ZERO = R(0.0), HALF = R(0.5);
+	const R r = calc_r<R, D>(cell_phi, adjc_phi, grad_phi, d);
+	const R rm = r < ONE ? r : ONE;
+	const R limiter = rm < ZERO ? ZERO : rm;
+	const R weight = limiter * weight_linear + (ONE - limiter) * (ONE + flux) * HALF;
+	return weight * cell_phi + (ONE - weight) * adjc_phi;
+}
+template <class R> __device__ __forceinline__ R p5Pos(R M, R alpha) {
+	const R M2Pos = R(0.25) * (M + R(1.0)) * (M + R(1.0));
+	const R M2Neg = R(-0.25) * (M - R(1.0)) * (M - R(1.0));
+	const R M1Pos = R(0.5) * (M + lfm_abs(M));
+	if (lfm_abs(M) < R(1)) return M2Pos * ((R(2.0) - M) - R(16.0) * alpha * M * M2Neg);
+	return M1Pos / M;
+}
+template <class R> __device__ __forceinline__ R p5Neg(R M, R alpha) {
+	const R M2Pos = R(0.25) * (M + R(1.0)) * (M + R(1.0));
+	const R M2Neg = R(-0.25) * (M - R(1.0)) * (M - R(1.0));
+	const R M1Neg = R(0.5) * (M - lfm_abs(M));
+	if (lfm_abs(M) < R(1)) return M2Neg * ((R(-2.0) - M) + R(16.0) * alpha * M * M2Pos);
+	return M1Neg / M;
+}
+// theta_avg * (pu - HALF * phalf): what one_rk_step_M2AUSM adds to the mid-point pressure of a face.
+// cq/nq: conservatives, cd/nd: dudx, cUg/nUg: U_grad ([i][j] = dU_i/dx_j), crg/nrg: rho_grad, cpg/npg: p_grad of the two sides.
+template <class R, int D>
+__device__ __forceinline__ R ausm_pressure_term(const Consts<R>& k, const R* cq, const R* nq, R cell_Rpsi, R adjc_Rpsi, const R (*cd)[D], const R (*nd)[D], const R (*cUg)[D], const R (*nUg)[D],
+                                                const R* crg, const R* nrg, const R* cpg, const R* npg, const R* S, const R* dv, R weight) {
+	const R ONE = R(1.0), M_ONE = R(-1.0), HALF = R(0.5);
+	const R cP = LFM_SQRT(k.gamma * cell_Rpsi);
+	const R cN = LFM_SQRT(k.gamma * adjc_Rpsi);
+	const R cavg = HALF * (cP + cN);
+	R cell_divu = R(0), neigh_divu = R(0), cell_curlu = R(0), neigh_curlu = R(0), cell_vmag = R(0), neigh_vmag = R(0);
+	R unPos = R(0), unNeg = R(0), norm = R(0);
+#pragma unroll
+	for (int nD = 0; nD < D; nD++) {
+		cell_divu += cd[nD][nD];
+		neigh_divu += nd[nD][nD];
+#pragma unroll
+		for (int nD2 = nD + 1; nD2 < D; nD2++) {
+			cell_curlu += (cd[nD][nD2] - cd[nD2][nD]) * (cd[nD][nD2] - cd[nD2][nD]);
+			neigh_curlu += (nd[nD][nD2] - nd[nD2][nD]) * (nd[nD][nD2] - nd[nD2][nD]);
+		}
+		const R cu = cq[nD + 1] / cq[0];
+		cell_vmag += cu * cu;
+		const R nu = nq[nD + 1] / nq[0];
+		neigh_vmag += nu * nu;
+		const R uP = interp_minmod<R, D>(cu, nu, cUg[nD], dv, weight, ONE);
+		const R uN = interp_minmod<R, D>(cu, nu, nUg[nD], dv, weight, M_ONE);
+		unPos += uP * S[nD];
+		unNeg += uN * S[nD];
+		norm += S[nD] * S[nD];
+	}
+	R th = -(cell_divu / LFM_SQRT(cell_divu * cell_divu + cell_curlu + R(4e-2)));
+	const R cell_theta = th > R(0) ? th : R(0);
+	th = -(neigh_divu / LFM_SQRT(neigh_divu * neigh_divu + neigh_curlu + R(4e-2)));
+	const R neigh_theta = th > R(0) ? th : R(0);
+	const R theta_avg = HALF * (cell_theta + neigh_theta);
+	R r = cq[0];
+	R E = cq[D + 1] / r;
+	const R cell_p = r * k.gm1 * (E - HALF * cell_vmag);
+	r = nq[0];
+	E = nq[D + 1] / r;
+	const R neigh_p = r * k.gm1 * (E - HALF * neigh_vmag);
+	const R rhoP = interp_minmod<R, D>(cq[0], nq[0], crg, dv, weight, ONE);
+	const R rhoN = interp_minmod<R, D>(cq[0], nq[0], nrg, dv, weight, M_ONE);
+	const R pP = interp_minmod<R, D>(cell_p, neigh_p, cpg, dv, weight, ONE);
+	const R pN = interp_minmod<R, D>(cell_p, neigh_p, npg, dv, weight, M_ONE);
+	const R Msq = (unPos * unPos + unNeg * unNeg) / (R(2.) * cavg * cavg * norm);
+	const R MPos = unPos / (LFM_SQRT(norm) * cavg);
+	const R MNeg = unNeg / (LFM_SQRT(norm) * cavg);
+	const R Minf = R(0.2);
+	const R mx = Msq > Minf * Minf ? Msq : Minf * Minf;
+	const R M0 = LFM_SQRT(R(1.0) < mx ? R(1.0) : mx);
+	const R fa = M0 * (R(2.0) - M0);
+	const R alpha = R(3.0) * (R(5.0) * fa * fa - R(4.0)) / R(16.0);
+	const R phalf = pN * (p5Pos<R>(MNeg, alpha) - p5Neg<R>(MNeg, alpha)) - pP * (p5Pos<R>(MPos, alpha) - p5Neg<R>(MPos, alpha));
+	const R pu = R(-0.75) * p5Pos<R>(MPos, alpha) * p5Neg<R>(MNeg, alpha) * (rhoP + rhoN) * cavg * fa * (unNeg - unPos);
+	return theta_avg * (pu - HALF * phalf);
 }
 
 // Fills the derived members of a CellState whose q is already loaded (dudx, dTdx, sigmaU come from memory).

@@ -38,6 +38,7 @@ template <class R> struct DevMesh {
 	R* tauMC;                          // [D*D][ncs]  only with the Smagorinsky closure (laminar: rebuilt from dudx where needed)
 	const R* smag_c;                   // [n_cells]   -2 (Cs Delta)^2 of the cell whose face loop leaves the cell's final tauMC
 	int les;                           // calc_VIS_Smagorinsky instead of calc_VIS
+	R *g_rho, *g_p, *g_U;              // [D|D|D*D][ncs] minmod gradients of solver 2 (calc_gradients_M2AUSM); ghost slots stay 0
 	R* flux;                           // [NQ][nfs]   materialised face fluxes (unfused path)
 	R *pAVG, *pRMS;
 	const int *bc_cell, *bc_kind, *bc_face, *bc_patch;
@@ -186,6 +187,72 @@ template <class R, int D> __global__ void __launch_bounds__(kBlock) k_grad_cell(
 	}
 }
 
+// ---------------------------------------------------------------------------------------------------
+// calc_gradients_M2AUSM (cfd_v0.cpp:1384-1495) as a cell-centric gather: Green-Gauss gradients of rho, p and U of cells
+// [c0, c1) (the three one_rk_step_M2AUSM reads; the reference also fills rhoU/rhoE/Rpsi/c gradients that nothing reads).
+// ---------------------------------------------------------------------------------------------------
+template <class R, int D> __device__ __forceinline__ R pressure_of(const Consts<R>& k, const R* q) {
+	const R r = q[0];
+	const R E = q[D + 1] / r;
+	R vmag = R(0.0);
+#pragma unroll
+	for (int i = 0; i < D; i++) vmag += (q[i + 1] / r) * (q[i + 1] / r);
+	return r * k.gm1 * (E - R(0.5) * vmag);
+}
+template <class R, int D> __global__ void __launch_bounds__(kBlock) k_grad_ausm(DevMesh<R> m, const R* __restrict__ q, int c0, int c1) {
+	const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= c1) return;
+	R cq[D + 2];
+#pragma unroll
+	for (int i = 0; i < D + 2; i++) cq[i] = q[i * m.ncs + c];
+	const R cp = pressure_of<R, D>(m.k, cq);
+	const R vinv = m.vol_inv[c];
+	R g_rho[D], g_p[D], g_U[D][D];
+#pragma unroll
+	for (int i = 0; i < D; i++) {
+		g_rho[i] = g_p[i] = R(0);
+#pragma unroll
+		for (int j = 0; j < D; j++) g_U[i][j] = R(0);
+	}
+	for (int s = 0; s < m.F; s++) {
+		const int e = m.csr[(size_t)s * m.n_cells + c];
+		if (e == 0) break;
+		const bool own = e > 0;
+		const int f = (own ? e : -e) - 1;
+		const int o = own ? m.face_neigh[f] : m.face_owner[f];
+		R oq[D + 2];
+#pragma unroll
+		for (int i = 0; i < D + 2; i++) oq[i] = q[i * m.ncs + o];
+		const R op = pressure_of<R, D>(m.k, oq);
+		const R w = m.w[f];
+		// face values seen from the face's owner: INTERP_LINEAR(w, owner, neighbour)
+		const R* a = own ? cq : oq;
+		const R* b = own ? oq : cq;
+		R UU[D], sov[D];
+#pragma unroll
+		for (int i = 0; i < D; i++) {
+			UU[i] = interp<R>(w, a[i + 1] / a[0], b[i + 1] / b[0]);
+			sov[i] = own ? m.S[i * m.nfs + f] * vinv : -m.S[i * m.nfs + f] * vinv;
+		}
+		const R rho = interp<R>(w, a[0], b[0]);
+		const R p = own ? interp<R>(w, cp, op) : interp<R>(w, op, cp);
+#pragma unroll
+		for (int i = 0; i < D; i++) {
+			g_p[i] += p * sov[i];
+#pragma unroll
+			for (int j = 0; j < D; j++) g_U[j][i] += UU[j] * sov[i];
+			g_rho[i] += rho * sov[i];
+		}
+	}
+#pragma unroll
+	for (int i = 0; i < D; i++) {
+		m.g_rho[(size_t)i * m.ncs + c] = g_rho[i];
+		m.g_p[(size_t)i * m.ncs + c] = g_p[i];
+#pragma unroll
+		for (int j = 0; j < D; j++) m.g_U[(size_t)(i * D + j) * m.ncs + c] = g_U[i][j];
+	}
+}
+
 // Loads everything face_flux needs about cell x (real cell, physical ghost or MPI ghost).
 template <class R, int D, int SCHEME> __device__ __forceinline__ void load_state(const DevMesh<R>& m, const R* __restrict__ q, int x, CellState<R, D>& s) {
 #pragma unroll
@@ -229,7 +296,24 @@ template <class R, int D, int SCHEME> __global__ void __launch_bounds__(kBlock) 
 	FaceGeo<R, D> g;
 	make_geo<R, D>(S, dv, m.w[f], g);
 	const bool ghost = n >= m.n_cells && n < m.n_cells + m.n_bc;
-	face_flux<R, D, SCHEME>(m.k, RegSide<R, D>{c}, RegSide<R, D>{a}, g, ghost, dv, rhs);
+	R extra = R(0);
+	if (SCHEME == 2) {
+		R cUg[D][D], nUg[D][D], crg[D], nrg[D], cpg[D], npg[D];
+#pragma unroll
+		for (int i = 0; i < D; i++) {
+			crg[i] = m.g_rho[(size_t)i * m.ncs + o];
+			nrg[i] = m.g_rho[(size_t)i * m.ncs + n];
+			cpg[i] = m.g_p[(size_t)i * m.ncs + o];
+			npg[i] = m.g_p[(size_t)i * m.ncs + n];
+#pragma unroll
+			for (int j = 0; j < D; j++) {
+				cUg[i][j] = m.g_U[(size_t)(i * D + j) * m.ncs + o];
+				nUg[i][j] = m.g_U[(size_t)(i * D + j) * m.ncs + n];
+			}
+		}
+		extra = ausm_pressure_term<R, D>(m.k, c.q, a.q, c.Rpsi, a.Rpsi, c.dudx, a.dudx, cUg, nUg, crg, nrg, cpg, npg, S, dv, g.w);
+	}
+	face_flux<R, D, SCHEME>(m.k, RegSide<R, D>{c}, RegSide<R, D>{a}, g, ghost, dv, rhs, extra);
 #pragma unroll
 	for (int i = 0; i < D + 2; i++) m.flux[i * m.nfs + f] = rhs[i];
 }

@@ -152,6 +152,9 @@ struct lfmgpu_ctx {
 	int fixed_strides = 1;             // compile-time shared-memory strides when the plan fits them
 	int les_opt = 0;                   // option "laminar" == 0: lfmgpu_step / _step_multi use calc_VIS_Smagorinsky
 	int les = 0;                       // closure of the latest calc_VIS call (what the stage kernels and the halo pack see)
+	int minmod_opt = 0;                // option "minmod": lfmgpu_step / _step_multi call calc_gradients_M2AUSM before calc_VIS (solver 2)
+	bool ausm_set = false;             // calc_gradients_M2AUSM ran in the running stage
+	bool ausm_zero = false;            // g_rho / g_p / g_U hold what prepare_for_RKstep leaves (zeros)
 	std::vector<int> smag_owner;       // cell whose face loop leaves each cell's final tauMC (Smagorinsky constant)
 	int tile_smem_budget = 75 * 1024;  // bytes of shared memory one tile CTA may use
 	// introspection
@@ -287,6 +290,7 @@ template <class R> int build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
 	TRY(dev_alloc(h, (void**)&m.dTdx, (size_t)D * h->ncs * sizeof(R)));
 	TRY(dev_alloc(h, (void**)&m.sigmaU, (size_t)D * h->ncs * sizeof(R)));
 	m.tauMC = nullptr;   // allocated when the Smagorinsky closure is first used
+	m.g_rho = m.g_p = m.g_U = nullptr;   // allocated when solver 2 (M2-AUSM) is first used
 	m.les = 0;
 	{
 		// Smagorinsky constant -2 (Cs Delta)^2 per cell (cfd_v0.cpp:1601-1602), evaluated here with the C library's pow so that
@@ -432,17 +436,52 @@ template <class R, int D> int t_vis(lfmgpu_ctx* h, int sub, int les) {
 	return 0;
 }
 
+// solver 2: the three minmod-gradient arrays exist only once M2-AUSM is used
+template <class R, int D> int ausm_arrays(lfmgpu_ctx* h) {
+	DevMesh<R>& m = h->mesh<R>();
+	if (m.g_rho) return 0;
+	TRY(dev_alloc(h, (void**)&m.g_rho, (size_t)D * h->ncs * sizeof(R)));
+	TRY(dev_alloc(h, (void**)&m.g_p, (size_t)D * h->ncs * sizeof(R)));
+	TRY(dev_alloc(h, (void**)&m.g_U, (size_t)D * D * h->ncs * sizeof(R)));
+	h->ausm_zero = true;
+	return 0;
+}
+
+// calc_gradients_M2AUSM (cfd_v0.cpp:1384-1495) of one submesh (or all: sub < 0)
+template <class R, int D> int t_gradients_ausm(lfmgpu_ctx* h, int sub) {
+	int c0, c1, f0, f1;
+	sub_range(h, sub, c0, c1, f0, f1);
+	TRY((ausm_arrays<R, D>(h)));
+	h->ausm_set = true;
+	h->ausm_zero = false;
+	if (c1 <= c0) return 0;
+	LAUNCH(h, "k_grad_ausm", h->s_main, (k_grad_ausm<R, D><<<blocks_for(c1 - c0), kBlock, 0, h->s_main>>>(h->mesh<R>(), (const R*)h->q[h->cur], c0, c1)));
+	CHECK_LAUNCH();
+	return 0;
+}
+
 template <class R, int D> int t_rk_stage(lfmgpu_ctx* h, int sub, int scheme, int rk, double dt, int want_res) {
 	int c0, c1, f0, f1;
 	sub_range(h, sub, c0, c1, f0, f1);
 	DevMesh<R>& m = h->mesh<R>();
+	if (scheme == LFMGPU_SCHEME_M2AUSM) {
+		// without calc_gradients_M2AUSM in this stage the reference reads the zeros prepare_for_RKstep left (cfd_v0.cpp:1362-1371)
+		TRY((ausm_arrays<R, D>(h)));
+		if (!h->ausm_set && !h->ausm_zero) {
+			CU(cudaMemsetAsync(m.g_rho, 0, (size_t)D * h->ncs * sizeof(R), h->s_main));
+			CU(cudaMemsetAsync(m.g_p, 0, (size_t)D * h->ncs * sizeof(R), h->s_main));
+			CU(cudaMemsetAsync(m.g_U, 0, (size_t)D * D * h->ncs * sizeof(R), h->s_main));
+			h->ausm_zero = true;
+		}
+	}
 	const R* q = (const R*)h->q[h->cur];
 	R* qn = (R*)h->q[1 - h->cur];
 	const int res = (want_res && rk == 0) ? 1 : 0;
 	const int first = h->dq_zero ? 1 : 0;
 	const R Ak = (R)h->c.Ak[rk], Bk = (R)h->c.Bk[rk];
 	if (c1 > c0) {
-		if (h->use_tiles && h->tiles.ready) {
+		// solver 2 is served by the face kernel + gather kernels (the tile stage kernel has no M2-AUSM variant yet)
+		if (h->use_tiles && h->tiles.ready && scheme != LFMGPU_SCHEME_M2AUSM) {
 			TRY((ensure_drv<R, D>(h, scheme)));
 			TRY((tile_stage<R, D>(h, sub, scheme, (R)dt, Ak, Bk, first, res)));
 		} else {
@@ -452,6 +491,8 @@ template <class R, int D> int t_rk_stage(lfmgpu_ctx* h, int sub, int scheme, int
 			if (f1 > f0) {
 				if (scheme == LFMGPU_SCHEME_M1)
 					LAUNCH(h, "k_flux_face", h->s_main, (k_flux_face<R, D, 0><<<blocks_for(f1 - f0), kBlock, 0, h->s_main>>>(m, q, f0, f1)));
+				else if (scheme == LFMGPU_SCHEME_M2AUSM)
+					LAUNCH(h, "k_flux_face", h->s_main, (k_flux_face<R, D, 2><<<blocks_for(f1 - f0), kBlock, 0, h->s_main>>>(m, q, f0, f1)));
 				else
 					LAUNCH(h, "k_flux_face", h->s_main, (k_flux_face<R, D, 1><<<blocks_for(f1 - f0), kBlock, 0, h->s_main>>>(m, q, f0, f1)));
 				CHECK_LAUNCH();
@@ -477,6 +518,7 @@ template <class R, int D> int t_rk_stage(lfmgpu_ctx* h, int sub, int scheme, int
 		h->dq_zero = false;
 		h->stage_done = true;
 		h->vis_on_cur = false;
+		h->ausm_set = false;
 	}
 	return 0;
 }
@@ -1062,14 +1104,19 @@ int stage_all(lfmgpu_ctx** hs, int n, int scheme, int rk, double dt, int want_re
 		h->rk_pending = rk;
 		TRY(halo_wait_impl(h, 0));
 		TRY(DISPATCH(h, t_set_bc, h));
+		const bool grads = scheme == LFMGPU_SCHEME_M2AUSM && h->minmod_opt;   // mesh_solver.cpp:537-548
+		if (grads) TRY(DISPATCH(h, t_gradients_ausm, h, h->n_nbr ? 0 : -1));
 		TRY(DISPATCH(h, t_vis, h, h->n_nbr ? 0 : -1, h->les_opt));
 		TRY(halo_start_impl(h, 1));
 	}
 	for (int r = 0; r < n; r++) {
 		lfmgpu_ctx* h = hs[r];
 		TRY(use(h));
-		if (h->n_nbr)
+		if (h->n_nbr) {
+			if (scheme == LFMGPU_SCHEME_M2AUSM && h->minmod_opt)   // mesh_solver.cpp:582-594
+				for (int s = 1; s < h->n_sub; s++) TRY(DISPATCH(h, t_gradients_ausm, h, s));
 			for (int s = 1; s < h->n_sub; s++) TRY(DISPATCH(h, t_vis, h, s, h->les_opt));
+		}
 	}
 	for (int r = 0; r < n; r++) {
 		lfmgpu_ctx* h = hs[r];
@@ -1242,6 +1289,10 @@ int lfmgpu_set_option(lfmgpu_t h, const char* name, int value) {
 		h->les_opt = value ? 0 : 1;
 		return 0;
 	}
+	if (!strcmp(name, "minmod")) {   // fvSchemes lfm/minmodExists: the time loops call calc_gradients_M2AUSM (solver 2 only)
+		h->minmod_opt = value ? 1 : 0;
+		return 0;
+	}
 	if (!strcmp(name, "use_tiles")) {
 		h->use_tiles = value;
 		h->drv_valid[0] = h->drv_valid[1] = false;
@@ -1272,6 +1323,11 @@ int lfmgpu_gradients(lfmgpu_t h, int submesh) {
 	(void)submesh;
 	return 0;
 }
+int lfmgpu_gradients_m2ausm(lfmgpu_t h, int submesh) {
+	TRY(use(h));
+	if (submesh >= h->n_sub) return fail("submesh out of range");
+	return DISPATCH(h, t_gradients_ausm, h, submesh);
+}
 int lfmgpu_vis(lfmgpu_t h, int submesh) {
 	TRY(use(h));
 	if (submesh >= h->n_sub) return fail("submesh out of range");
@@ -1285,7 +1341,7 @@ int lfmgpu_vis_smagorinsky(lfmgpu_t h, int submesh) {
 int lfmgpu_rk_stage(lfmgpu_t h, int submesh, int scheme, int rk_step, double dt, int want_res) {
 	TRY(use(h));
 	if (submesh >= h->n_sub) return fail("submesh out of range");
-	if (scheme != LFMGPU_SCHEME_M1 && scheme != LFMGPU_SCHEME_M2) return fail("scheme %d is not served by the GPU path", scheme);
+	if (scheme != LFMGPU_SCHEME_M1 && scheme != LFMGPU_SCHEME_M2 && scheme != LFMGPU_SCHEME_M2AUSM) return fail("scheme %d is not served by the GPU path", scheme);
 	if (rk_step < 0 || rk_step >= LFMGPU_MAX_RK) return fail("rk_step out of range");
 	return DISPATCH(h, t_rk_stage, h, submesh, scheme, rk_step, dt, want_res);
 }
@@ -1331,9 +1387,9 @@ int lfmgpu_warmup(lfmgpu_t h) {
 }
 
 int lfmgpu_step(lfmgpu_t h, int scheme, double dt, int n_steps, int minmod, int want_res) {
-	(void)minmod;
 	TRY(use(h));
-	if (scheme != LFMGPU_SCHEME_M1 && scheme != LFMGPU_SCHEME_M2) return fail("scheme %d is not served by the GPU path", scheme);
+	h->minmod_opt = minmod ? 1 : 0;
+	if (scheme != LFMGPU_SCHEME_M1 && scheme != LFMGPU_SCHEME_M2 && scheme != LFMGPU_SCHEME_M2AUSM) return fail("scheme %d is not served by the GPU path", scheme);
 	if (h->transport == 1 && h->n_ranks > 1) return fail("lfmgpu_step: in-process ranks must be driven together (lfmgpu_step_multi)");
 	if (h->n_nbr && h->transport == 0) return fail("lfmgpu_step: rank has neighbours but no halo transport was initialised");
 	lfmgpu_ctx* hs[1] = {h};
@@ -1342,7 +1398,7 @@ int lfmgpu_step(lfmgpu_t h, int scheme, double dt, int n_steps, int minmod, int 
 
 int lfmgpu_step_multi(const lfmgpu_t* hs, int n_ranks, int scheme, double dt, int n_steps, int first, int want_res) {
 	if (!hs || n_ranks < 1) return fail("lfmgpu_step_multi: bad arguments");
-	if (scheme != LFMGPU_SCHEME_M1 && scheme != LFMGPU_SCHEME_M2) return fail("scheme %d is not served by the GPU path", scheme);
+	if (scheme != LFMGPU_SCHEME_M1 && scheme != LFMGPU_SCHEME_M2 && scheme != LFMGPU_SCHEME_M2AUSM) return fail("scheme %d is not served by the GPU path", scheme);
 	std::vector<lfmgpu_ctx*> v(hs, hs + n_ranks);
 	for (auto* h : v)
 		if (h->n_nbr && h->transport == 0) return fail("lfmgpu_step_multi: rank has neighbours but no halo transport");

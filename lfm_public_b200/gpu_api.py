@@ -21,7 +21,7 @@ LIB_PATH = os.environ.get("LFMGPU_LIB") or os.path.join(os.path.dirname(os.path.
 # every symbol include/lfmgpu.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "lfmgpu_last_error", "lfmgpu_device_count", "lfmgpu_create", "lfmgpu_destroy", "lfmgpu_sync",
-    "lfmgpu_prepare_timestep", "lfmgpu_prepare_rkstep", "lfmgpu_set_bc", "lfmgpu_gradients", "lfmgpu_vis", "lfmgpu_vis_smagorinsky",
+    "lfmgpu_prepare_timestep", "lfmgpu_prepare_rkstep", "lfmgpu_set_bc", "lfmgpu_gradients", "lfmgpu_gradients_m2ausm", "lfmgpu_vis", "lfmgpu_vis_smagorinsky",
     "lfmgpu_rk_stage", "lfmgpu_halo_start", "lfmgpu_halo_wait", "lfmgpu_cfl", "lfmgpu_dt", "lfmgpu_average",
     "lfmgpu_forces", "lfmgpu_residual", "lfmgpu_step", "lfmgpu_warmup", "lfmgpu_step_multi", "lfmgpu_allreduce",
     "lfmgpu_set_option", "lfmgpu_download", "lfmgpu_upload_q", "lfmgpu_upload_q_soa_async", "lfmgpu_download_q_soa_async",
@@ -43,7 +43,7 @@ def lib():
         sig = {
             "lfmgpu_device_count": [C.POINTER(i)], "lfmgpu_create": [vp, i, C.POINTER(vp)], "lfmgpu_destroy": [vp],
             "lfmgpu_sync": [vp], "lfmgpu_prepare_timestep": [vp], "lfmgpu_prepare_rkstep": [vp, i], "lfmgpu_set_bc": [vp],
-            "lfmgpu_gradients": [vp, i], "lfmgpu_vis": [vp, i], "lfmgpu_vis_smagorinsky": [vp, i], "lfmgpu_rk_stage": [vp, i, i, i, d, i],
+            "lfmgpu_gradients": [vp, i], "lfmgpu_gradients_m2ausm": [vp, i], "lfmgpu_vis": [vp, i], "lfmgpu_vis_smagorinsky": [vp, i], "lfmgpu_rk_stage": [vp, i, i, i, d, i],
             "lfmgpu_halo_start": [vp, i], "lfmgpu_halo_wait": [vp, i], "lfmgpu_cfl": [vp, d, C.POINTER(d)],
             "lfmgpu_dt": [vp, d, C.POINTER(d)], "lfmgpu_average": [vp, i], "lfmgpu_forces": [vp, i, vp, vp],
             "lfmgpu_residual": [vp, vp], "lfmgpu_step": [vp, i, d, i, i, i], "lfmgpu_warmup": [vp],
@@ -118,6 +118,12 @@ class GpuSolver:
             laminar = True
         if not laminar:                       # turbulenceProperties simulationType != laminar: calc_VIS_Smagorinsky in the time loop
             self.set_option("laminar", 0)
+        try:
+            self.minmod = int(case.opts.minmod)
+        except Exception:
+            self.minmod = 0
+        if self.minmod:                       # fvSchemes lfm/minmodExists: calc_gradients_M2AUSM in the time loop of solver 2
+            self.set_option("minmod", 1)
 
     # ---- ISolver virtuals -------------------------------------------------------------------------------
     def prepare_for_timestep(self):
@@ -131,6 +137,9 @@ class GpuSolver:
 
     def calc_gradients(self, submesh=-1):
         _check(lib().lfmgpu_gradients(self.h, submesh))
+
+    def calc_gradients_M2AUSM(self, submesh=-1):
+        _check(lib().lfmgpu_gradients_m2ausm(self.h, submesh))
 
     def calc_VIS(self, submesh=-1):
         _check(lib().lfmgpu_vis(self.h, submesh))
@@ -176,7 +185,7 @@ class GpuSolver:
         _check(lib().lfmgpu_warmup(self.h))
 
     def step(self, scheme, dt, n_steps=1, want_res=False):
-        _check(lib().lfmgpu_step(self.h, scheme, float(dt), n_steps, 0, int(want_res)))
+        _check(lib().lfmgpu_step(self.h, scheme, float(dt), n_steps, self.minmod, int(want_res)))
 
     def sync(self):
         _check(lib().lfmgpu_sync(self.h))
