@@ -130,12 +130,12 @@ public:
 	}
 	void set_boundary_conditions() override { LFMGPU_OK(lfmgpu_set_bc(handle())); }
 	void calc_gradients(MPI_env&) override { LFMGPU_OK(lfmgpu_gradients(handle(), this->m_nSubmeshIndex)); }
-	void calc_gradients_M2AUSM(MPI_env&) override { unsupported("calc_gradients_M2AUSM (solver 2)"); }
+	void calc_gradients_M2AUSM(MPI_env&) override { LFMGPU_OK(lfmgpu_gradients_m2ausm(handle(), this->m_nSubmeshIndex)); }
 	void calc_VIS(MPI_env&) override { LFMGPU_OK(lfmgpu_vis(handle(), this->m_nSubmeshIndex)); }
 	void calc_VIS_Smagorinsky(MPI_env&) override { LFMGPU_OK(lfmgpu_vis_smagorinsky(handle(), this->m_nSubmeshIndex)); }
 	void one_rk_step_M1(int rk_step, P dt, MPI_env&, P* RES) override { stage(LFMGPU_SCHEME_M1, rk_step, dt, RES); }
 	void one_rk_step_M2(int rk_step, P dt, MPI_env&, P* RES) override { stage(LFMGPU_SCHEME_M2, rk_step, dt, RES); }
-	void one_rk_step_M2AUSM(int, P, MPI_env&, P*) override { unsupported("one_rk_step_M2AUSM (solver 2)"); }
+	void one_rk_step_M2AUSM(int rk_step, P dt, MPI_env&, P* RES) override { stage(LFMGPU_SCHEME_M2AUSM, rk_step, dt, RES); }
 
 	void mpi_communication(MPI_env& mpi_env, int comm_step) override {
 		State& st = State::get();

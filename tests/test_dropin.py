@@ -51,7 +51,7 @@ def _pair(name, tmp_path, sp=False, **override):
 
 @needs_bins
 @pytest.mark.parametrize("name", ["quad2d_m1", "quad2d_m1_p4", "quad2d_m2_p2_packed", "tri2d_m2", "hex3d_m2_p4", "ogrid3d_m2", "hex3d_m2_les_p4",
-                                  "ogrid3d_m1_les"])
+                                  "ogrid3d_m1_les", "hex3d_ausm_p4", "ogrid2d_ausm", "quad2d_ausm_nominmod"])
 def test_dropin_fields_identical_fp64(name, tmp_path):
     o, ref_dir, gpu_dir, out_ref, out_gpu = _pair(name, tmp_path)
     D = o["dimension"]
@@ -69,7 +69,7 @@ def test_dropin_fields_identical_fp64(name, tmp_path):
 
 
 @needs_bins
-@pytest.mark.parametrize("name", ["quad2d_m1_p4", "quad2d_m2_p2_packed", "hex3d_m2_p4", "hex3d_m2_les_p4"])
+@pytest.mark.parametrize("name", ["quad2d_m1_p4", "quad2d_m2_p2_packed", "hex3d_m2_p4", "hex3d_m2_les_p4", "hex3d_ausm_p4"])
 def test_dropin_halo_messages_identical(name, tmp_path):
     """Host-staged halo: what the GPU path hands to the reference's MPI_env equals what the reference packs, message by message."""
     o, ref_dir, gpu_dir, _, _ = _pair(name, tmp_path)

@@ -151,7 +151,8 @@ def test_halo_packing_bit_exact(name, use_tiles, tmp_path):
 
 
 @pytest.mark.parametrize("use_tiles", MODES)
-@pytest.mark.parametrize("name", ["quad2d_m1", "hex3d_m2_p4", "tri2d_m2", "ogrid3d_m2", "hex3d_m1_p8", "hex3d_m2_les_p4", "ogrid3d_m1_les"])
+@pytest.mark.parametrize("name", ["quad2d_m1", "hex3d_m2_p4", "tri2d_m2", "ogrid3d_m2", "hex3d_m1_p8", "hex3d_m2_les_p4", "ogrid3d_m1_les",
+                                  "hex3d_ausm_p4", "ogrid2d_ausm"])
 def test_fields_fp32(name, use_tiles, tmp_path):
     """fp32: 1e-5 relative max-norm against the float oracle (and the float reference's golden fields)."""
     o, cases, oracles, gpus = _setup(name, tmp_path, use_tiles, sp=True)
