@@ -249,12 +249,6 @@ public:
 
 private:
 	bool isBnd() const { return this->m_nSubmeshIndex == 0; }
-	[[noreturn]] void unsupported(const char* what) {
-		fprintf(stderr, "lfmgpu: %s is not served by the GPU path (M1/M2 laminar only)\n", what);
-		MPI_Abort(MPI_COMM_WORLD, 701);
-		abort();
-	}
-
 	void stage(int scheme, int rk_step, P dt, P* RES) {
 		lfmgpu_t h = handle();
 		const int want_res = (RES != nullptr && rk_step == 0) ? 1 : 0;

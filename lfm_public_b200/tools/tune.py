@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--tile", default="8,4,4")
     ap.add_argument("--brick-order", default="morton")
+    ap.add_argument("--minmod", action="store_true", help="minmodExists: calc_gradients_M2AUSM in the time loop (with --scheme 2)")
     ap.add_argument("--les", action="store_true", help="Smagorinsky closure (calc_VIS_Smagorinsky) instead of laminar")
     ap.add_argument("--set", action="append", default=[], help="NAME=v1,v2,... (environment knob and its values)")
     args = ap.parse_args()
@@ -53,6 +54,9 @@ def main():
             continue
         if args.les:
             g.set_option("laminar", 0)
+        if args.minmod:
+            g.minmod = 1
+            g.set_option("minmod", 1)
         g.warmup()
         g.step(args.scheme, dt, 2)
         g.sync()
@@ -64,7 +68,7 @@ def main():
         g.step(args.scheme, dt, args.steps)
         g.sync()
         kt = {}
-        for name in ("tile_stage", "tile_grad", "k_flux_face", "k_update_cell", "k_grad_cell"):
+        for name in ("tile_stage", "tile_grad", "k_flux_face", "k_update_cell", "k_grad_cell", "k_grad_ausm"):
             t, nl = g.kernel_time(name)
             if nl:
                 kt[name] = round(t / args.steps, 3)

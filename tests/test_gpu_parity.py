@@ -214,13 +214,14 @@ def test_upload_download_roundtrip(tmp_path):
 
 
 def test_medium_mesh_all_paths(tmp_path):
-    """A mesh large enough for many tiles / blocks (64x48x40 hexes = 122 880 cells), 3 steps, both schemes,
-    both kernel paths, against the oracle bit for bit."""
+    """A mesh large enough for many tiles / blocks (64x48x40 hexes = 122 880 cells), 3 steps, the three schemes
+    (solver 2 with its minmod gradients), both kernel paths, against the oracle bit for bit."""
     from lfm_public_b200.tools import casegen, meshgen
     m = meshgen.hex_box(64, 48, 40, lengths=(4.0, 3.0, 2.5), z_cyclic=True)
-    for scheme in (0, 1):
+    for scheme in (0, 1, 2):
         case_dir = str(tmp_path / f"med{scheme}")
-        opts = casegen.write_case(case_dir, m, solver=scheme, dimension=3, deltaT=2e-3, endTime=1.0, Ls=0.8, mu=7.17948717948718e-05)
+        opts = casegen.write_case(case_dir, m, solver=scheme, dimension=3, deltaT=2e-3, endTime=1.0, Ls=0.8, mu=7.17948717948718e-05,
+                                  minmodExists=(scheme == 2))
         from lfm_public_b200 import host_api
         case = host_api.Case.open(case_dir).finish()
         orc = oracle_lib.Oracle(case)
