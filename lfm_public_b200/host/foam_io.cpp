@@ -259,17 +259,50 @@ Dict parseDictFile(const std::string& path) { return parseDictString(slurp(path)
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-// Positions `p` after the FoamFile{...} header (if any) and checks the format is ascii.
+// What the FoamFile{...} header says about the encoding of the lists that follow.  OpenFOAM's binary stream format
+// (IOstreamOption::BINARY; the 3D examples say `writeFormat binary`, and decomposePar writes what the case says) keeps
+// every token ASCII except the contents of contiguous lists: `N(` + N raw elements + `)`, little endian, element sizes
+// given by `arch "LSB;label=32;scalar=64"`.
+struct FoamHeader {
+	bool binary = false;
+	int labelBytes = 4, scalarBytes = 8;
+	size_t bodyStart = 0;      // offset behind the header's closing brace in the RAW (comments not stripped) text
+};
+
+FoamHeader parseHeader(const std::string& raw, const std::string& path) {
+	FoamHeader h;
+	size_t pos = raw.find("FoamFile");
+	if (pos == std::string::npos) return h;
+	size_t open = raw.find('{', pos);
+	size_t close = open == std::string::npos ? std::string::npos : raw.find('}', open);
+	if (open == std::string::npos || close == std::string::npos) fail("bad FoamFile header in " + path);
+	h.bodyStart = close + 1;
+	const std::string hdr = raw.substr(open + 1, close - open - 1);
+	size_t f = hdr.find("format");
+	if (f != std::string::npos) {
+		size_t semi = hdr.find(';', f), b = hdr.find("binary", f);
+		h.binary = b != std::string::npos && b < semi;
+	}
+	size_t a = hdr.find("arch");
+	if (a != std::string::npos) {
+		size_t semi = hdr.find("\";", a);
+		const std::string arch = hdr.substr(a, semi == std::string::npos ? std::string::npos : semi - a);
+		if (arch.find("MSB") != std::string::npos) fail("big-endian binary files are not supported: " + path);
+		size_t l = arch.find("label="), sc = arch.find("scalar=");
+		if (l != std::string::npos) h.labelBytes = atoi(arch.c_str() + l + 6) / 8;
+		if (sc != std::string::npos) h.scalarBytes = atoi(arch.c_str() + sc + 7) / 8;
+	}
+	if (h.binary && ((h.labelBytes != 4 && h.labelBytes != 8) || (h.scalarBytes != 4 && h.scalarBytes != 8))) fail("unsupported arch in " + path);
+	return h;
+}
+
+// Positions `p` after the FoamFile{...} header (if any) of comment-stripped text.
 const char* skipHeader(const std::string& s, const std::string& path) {
 	size_t pos = s.find("FoamFile");
 	if (pos == std::string::npos) return s.data();
 	size_t open = s.find('{', pos);
 	size_t close = s.find('}', open);
 	if (open == std::string::npos || close == std::string::npos) fail("bad FoamFile header in " + path);
-	std::string hdr = s.substr(open + 1, close - open - 1);
-	size_t f = hdr.find("format");
-	if (f != std::string::npos && hdr.find("binary", f) != std::string::npos && hdr.find("binary", f) < hdr.find(';', f))
-		fail("binary format is not supported: " + path);
 	return s.data() + close + 1;
 }
 
@@ -289,8 +322,82 @@ long readCount(const char*& p, const char* end, const std::string& path) {
 	return n;
 }
 
+// ---- binary lists: the text between lists is not comment-stripped (the raw bytes may hold any pattern) ----
+inline void skipWsComments(const char*& p, const char* end) {
+	for (;;) {
+		while (p < end && (unsigned char)*p <= ' ') p++;
+		if (p + 1 < end && p[0] == '/' && p[1] == '/') {
+			while (p < end && *p != '\n') p++;
+		} else if (p + 1 < end && p[0] == '/' && p[1] == '*') {
+			p += 2;
+			while (p + 1 < end && !(p[0] == '*' && p[1] == '/')) p++;
+			p = p + 2 <= end ? p + 2 : end;
+		} else {
+			return;
+		}
+	}
+}
+// `N(` : returns N with p on the first raw byte
+long readCountRaw(const char*& p, const char* end, const std::string& path) {
+	skipWsComments(p, end);
+	char* e = nullptr;
+	long n = strtol(p, &e, 10);
+	if (e == p || n < 0) fail("expected a list size in " + path);
+	p = e;
+	skipWsComments(p, end);
+	if (p >= end || *p != '(') fail("expected '(' after list size in " + path);
+	p++;
+	return n;
+}
+inline void closeRaw(const char*& p, const char* end, const std::string& path) {
+	if (p >= end || *p != ')') fail("expected ')' behind the binary block in " + path);
+	p++;
+}
+std::vector<int> readRawLabels(const char*& p, const char* end, int labelBytes, const std::string& path) {
+	const long n = readCountRaw(p, end, path);
+	if ((size_t)(end - p) < (size_t)n * labelBytes) fail("truncated binary label list in " + path);
+	std::vector<int> v((size_t)n);
+	if (labelBytes == 4) {
+		if (n) memcpy(v.data(), p, (size_t)n * 4);
+	} else {
+		for (long i = 0; i < n; i++) {
+			int64_t x;
+			memcpy(&x, p + (size_t)i * 8, 8);
+			v[(size_t)i] = (int)x;
+		}
+	}
+	p += (size_t)n * labelBytes;
+	closeRaw(p, end, path);
+	return v;
+}
+// n_expected < 0: any size; returns the scalars widened to double
+std::vector<double> readRawScalars(const char*& p, const char* end, int scalarBytes, int nComp, long n_expected, const std::string& path) {
+	const long n = readCountRaw(p, end, path);
+	if (n_expected >= 0 && n != n_expected) fail("list size mismatch in " + path);
+	const size_t cnt = (size_t)n * nComp;
+	if ((size_t)(end - p) < cnt * scalarBytes) fail("truncated binary scalar list in " + path);
+	std::vector<double> v(cnt);
+	if (scalarBytes == 8) {
+		if (cnt) memcpy(v.data(), p, cnt * 8);
+	} else {
+		for (size_t i = 0; i < cnt; i++) {
+			float x;
+			memcpy(&x, p + i * 4, 4);
+			v[i] = (double)x;
+		}
+	}
+	p += cnt * scalarBytes;
+	closeRaw(p, end, path);
+	return v;
+}
+
 std::vector<int> readLabelList(const std::string& path) {
 	std::string s = slurp(path);
+	const FoamHeader hd = parseHeader(s, path);
+	if (hd.binary) {
+		const char* p = s.data() + hd.bodyStart;
+		return readRawLabels(p, s.data() + s.size(), hd.labelBytes, path);
+	}
 	stripComments(s);
 	const char* end = s.data() + s.size();
 	const char* p = skipHeader(s, path);
@@ -475,11 +582,17 @@ PolyMesh readPolyMesh(const std::string& dir) {
 	{  // points
 		std::string path = dir + "/points";
 		std::string s = slurp(path);
-		stripComments(s);
+		const FoamHeader hd = parseHeader(s, path);
+		if (hd.binary) {
+			const char* pb = s.data() + hd.bodyStart;
+			m.points = readRawScalars(pb, s.data() + s.size(), hd.scalarBytes, 3, -1, path);
+			s.clear();
+		} else
+			stripComments(s);
 		const char* end = s.data() + s.size();
-		const char* p = skipHeader(s, path);
-		long n = readCount(p, end, path);
-		m.points.resize((size_t)n * 3);
+		const char* p = hd.binary ? end : skipHeader(s, path);
+		long n = hd.binary ? 0 : readCount(p, end, path);
+		if (!hd.binary) m.points.resize((size_t)n * 3);
 		for (long i = 0; i < n; i++) {
 			skipWs(p, end);
 			if (p >= end || *p != '(') fail("expected '(' in " + path);
@@ -498,14 +611,27 @@ PolyMesh readPolyMesh(const std::string& dir) {
 	{  // faces
 		std::string path = dir + "/faces";
 		std::string s = slurp(path);
-		stripComments(s);
-		if (s.find("faceCompactList") != std::string::npos) fail("faceCompactList is not supported: " + path);
+		const FoamHeader hd = parseHeader(s, path);
+		if (hd.binary) {
+			// class faceCompactList: the offsets (nFaces + 1 labels) followed by the concatenated point labels
+			if (s.substr(0, hd.bodyStart).find("faceCompactList") == std::string::npos) fail("binary faces file is not a faceCompactList: " + path);
+			const char* pb = s.data() + hd.bodyStart;
+			m.faceOffsets = readRawLabels(pb, s.data() + s.size(), hd.labelBytes, path);
+			m.facePoints = readRawLabels(pb, s.data() + s.size(), hd.labelBytes, path);
+			if (m.faceOffsets.empty() || m.faceOffsets.front() != 0 || (size_t)m.faceOffsets.back() != m.facePoints.size()) fail("inconsistent faceCompactList in " + path);
+			s.clear();
+		} else {
+			stripComments(s);
+			if (s.find("faceCompactList") != std::string::npos) fail("ascii faceCompactList is not supported: " + path);
+		}
 		const char* end = s.data() + s.size();
-		const char* p = skipHeader(s, path);
-		long n = readCount(p, end, path);
-		m.faceOffsets.resize((size_t)n + 1);
-		m.facePoints.reserve((size_t)n * 4);
-		m.faceOffsets[0] = 0;
+		const char* p = hd.binary ? end : skipHeader(s, path);
+		long n = hd.binary ? 0 : readCount(p, end, path);
+		if (!hd.binary) {
+			m.faceOffsets.resize((size_t)n + 1);
+			m.facePoints.reserve((size_t)n * 4);
+			m.faceOffsets[0] = 0;
+		}
 		for (long i = 0; i < n; i++) {
 			char* e = nullptr;
 			long np = strtol(p, &e, 10);
@@ -629,6 +755,25 @@ void writePolyMesh(const PolyMesh& m, const std::string& dir) {
 // ---------------------------------------------------------------------------------------------
 std::vector<double> readVolField(const std::string& path, int nCells, int nComp) {
 	std::string s = slurp(path);
+	const FoamHeader hd = parseHeader(s, path);
+	if (hd.binary) {
+		// only the contents of a nonuniform list are raw; `uniform` values and everything before the list are text
+		size_t pos = s.find("internalField", hd.bodyStart);
+		if (pos == std::string::npos) fail("no internalField in " + path);
+		const char* end = s.data() + s.size();
+		const char* p = s.data() + pos + strlen("internalField");
+		skipWsComments(p, end);
+		if (strncmp(p, "nonuniform", 10) == 0) {
+			p += 10;
+			skipWsComments(p, end);
+			while (p < end && (unsigned char)*p > ' ' && !(*p >= '0' && *p <= '9')) p++;  // List<scalar>
+			if (p < end && *p == '>') p++;
+			return readRawScalars(p, end, hd.scalarBytes, nComp, nCells, path);
+		}
+		size_t semi = s.find(';', pos);   // `uniform X;`: cut the text there and parse it as ascii below
+		if (semi == std::string::npos) fail("bad internalField in " + path);
+		s.resize(semi + 1);
+	}
 	stripComments(s);
 	skipHeader(s, path);
 	size_t pos = s.find("internalField");

@@ -97,3 +97,76 @@ def decompose_case(case_dir, n_ranks, time_name="0", fields=("p", "T", "U", "alp
         for name, v in vals.items():
             meshgen.write_field(os.path.join(pdir, time_name, name), name, pm, np.asarray(v)[pm["cellProcAddressing"]])
     return m, cell_rank, parts
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# OpenFOAM binary stream format (`writeFormat binary`, what decomposePar writes for the reference's 3D cases): tokens stay
+# text, the contents of contiguous lists are raw little-endian elements between `(` and `)`.
+# ---------------------------------------------------------------------------------------------------------------
+def _bin_header(cls, obj, label_bytes):
+    return ("FoamFile\n{\n    version     2.0;\n    format      binary;\n"
+            f"    arch        \"LSB;label={8 * label_bytes};scalar=64\";\n    class       {cls};\n    object      {obj};\n}}\n"
+            "// * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * //\n\n").encode()
+
+
+def _bin_list(arr):
+    return str(len(arr)).encode() + b"\n(" + np.ascontiguousarray(arr).tobytes() + b")\n"
+
+
+def to_binary(case_dir, label_bytes=4, time_name="0", fields=("p", "T", "U", "alpha")):
+    """Rewrites the polyMesh lists and the time-directory fields of an ASCII case (serial and processorN parts) in
+    OpenFOAM's binary format, in place (faces become a faceCompactList, as OpenFOAM writes them in binary)."""
+    lab = np.int32 if label_bytes == 4 else np.int64
+    roots = [case_dir] + sorted(os.path.join(case_dir, d) for d in os.listdir(case_dir) if d.startswith("processor"))
+    for root in roots:
+        md = os.path.join(root, "constant", "polyMesh")
+        if not os.path.isdir(md):
+            continue
+        n, t = _body(os.path.join(md, "points"))
+        pts = _numbers(t, np.float64).reshape(n, 3)
+        with open(os.path.join(md, "points"), "wb") as f:
+            f.write(_bin_header("vectorField", "points", label_bytes) + _bin_list(pts))
+        nf, t = _body(os.path.join(md, "faces"))
+        tok = _numbers(t, np.int64)
+        offs, labels, pos = [0], [], 0
+        for _ in range(nf):
+            k = int(tok[pos])
+            labels.extend(tok[pos + 1:pos + 1 + k].tolist())
+            offs.append(len(labels))
+            pos += 1 + k
+        with open(os.path.join(md, "faces"), "wb") as f:
+            f.write(_bin_header("faceCompactList", "faces", label_bytes) + _bin_list(np.array(offs, dtype=lab)) + b"\n" + _bin_list(np.array(labels, dtype=lab)))
+        n_cells = 0
+        for name in ("owner", "neighbour", "faceProcAddressing", "cellProcAddressing", "pointProcAddressing", "boundaryProcAddressing", "cellSubmesh"):
+            p = os.path.join(md, name)
+            if not os.path.exists(p):
+                continue
+            n, t = _body(p)
+            a = _numbers(t, np.int64)
+            assert len(a) == n
+            if name == "owner":
+                n_cells = int(a.max()) + 1
+            with open(p, "wb") as f:
+                f.write(_bin_header("labelList", name, label_bytes) + _bin_list(a.astype(lab)))
+        # polyBoundaryMesh stays a text dictionary list under a binary header, as OpenFOAM writes it
+        p = os.path.join(md, "boundary")
+        s = open(p).read().replace("format      ascii;", "format      binary;")
+        open(p, "w").write(s)
+        for name in fields:
+            p = os.path.join(root, time_name, name)
+            if not os.path.exists(p):
+                continue
+            s = open(p).read()
+            i = s.index("internalField")
+            if "nonuniform" not in s[i:i + 200]:
+                open(p, "w").write(s.replace("format      ascii;", "format      binary;"))
+                continue
+            v = read_internal_field(p, n_cells)
+            vec = v.ndim == 2
+            tail = s[s.index("boundaryField"):]
+            with open(p, "wb") as f:
+                f.write(_bin_header("volVectorField" if vec else "volScalarField", name, label_bytes))
+                f.write(b"dimensions      [0 0 0 0 0 0 0];\n\n")
+                f.write(f"internalField   nonuniform List<{'vector' if vec else 'scalar'}> \n".encode())
+                f.write(str(len(v)).encode() + b"\n(" + np.ascontiguousarray(v, dtype=np.float64).tobytes() + b");\n\n")
+                f.write(tail.encode())
