@@ -110,8 +110,17 @@ int FlatMesh::faceNeighbourCell(int f) const {
 	return (c == f) ? -1 : m_.owner[(size_t)c];
 }
 
+int FlatMesh::faceTag(int f) const {
+	// reference: polyMeshReaderOF.cpp:460-475 getBoundaryTag of the face's patch
+	const int b = m_.whichPatch(f);
+	return b < 0 ? 0 : m_.processorTag(b);
+}
+
 int FlatMesh::faceId(int f) const {
-	// reference: polyMeshReaderOF.cpp:251-261 getFaceId with tag == +-1 (plain processor patches)
+	// reference: polyMeshReaderOF.cpp:251-261 getFaceId: the global face (faceProcAddressing) behind plain processor
+	// patches (tag +-1), the index inside the patch behind processorCyclic patches (any other tag)
+	const int tag = faceTag(f);
+	if (tag < -1 || tag > 1) return f - m_.patches[(size_t)m_.whichPatch(f)].startFace;
 	if ((size_t)f < m_.faceProcAddressing.size()) return std::abs(m_.faceProcAddressing[(size_t)f]);
 	return f;
 }
@@ -232,6 +241,7 @@ std::vector<char> FlatMesh::exportFor(int i) const {
 	for (int f : faces) {
 		const int c = m_.owner[(size_t)f];
 		put<int32_t>(buf, (int32_t)faceId(f));
+		put<int32_t>(buf, (int32_t)faceTag(f));
 		put<int32_t>(buf, (int32_t)subIndex_[(size_t)c]);
 		for (int k = 0; k < 3; k++) put<double>(buf, m_.cellCentres[(size_t)c * 3 + k] - m_.faceCentres[(size_t)f * 3 + k]);
 	}
@@ -248,10 +258,11 @@ void FlatMesh::importFrom(int i, const char* data, size_t bytes) {
 	remoteByFaceId_[(size_t)i].clear();
 	for (int k = 0; k < nf; k++) {
 		const int id = get<int32_t>(p, end);
+		const int tag = get<int32_t>(p, end);
 		Remote r;
 		r.ownerBndIndex = get<int32_t>(p, end);
 		for (int d = 0; d < 3; d++) r.x[d] = get<double>(p, end);
-		remoteByFaceId_[(size_t)i][id] = r;
+		remoteByFaceId_[(size_t)i][std::make_pair(id, tag)] = r;
 	}
 	recvCells_[(size_t)i].resize((size_t)ns);
 	for (int k = 0; k < ns; k++) recvCells_[(size_t)i][(size_t)k] = get<int32_t>(p, end);
@@ -379,7 +390,7 @@ void FlatMesh::buildAll() {
 					s.keyId = bcGhostId[(size_t)g];
 				} else {
 					const int n = rank2local_.at(m_.patches[(size_t)b].neighbProcNo);
-					auto it = remoteByFaceId_[(size_t)n].find(faceId(f));
+					auto it = remoteByFaceId_[(size_t)n].find(std::make_pair(faceId(f), -faceTag(f)));   // the sender's tag is the reverse of ours (mesh_reader.cpp:460-473)
 					if (it == remoteByFaceId_[(size_t)n].end()) fail("processor face without a partner on the neighbour rank");
 					const Remote& r = it->second;
 					for (int k = 0; k < D; k++) vneigh[k] = r.x[k] + xf[k] - xc[k];

@@ -90,7 +90,7 @@ private:
 		int ownerBndIndex;
 		double x[3];
 	};
-	std::vector<std::map<int, Remote>> remoteByFaceId_;    // imported
+	std::vector<std::map<std::pair<int, int>, Remote>> remoteByFaceId_;    // imported, keyed (faceId, tag) like faceTagMapping (mesh_reader.cpp:404, 473)
 	std::vector<std::vector<int>> recvCells_;              // neigh_cells_to_recv (imported send lists)
 	std::vector<bool> imported_;
 
@@ -103,6 +103,7 @@ private:
 	lfmgpu_desc desc_;
 
 	int faceId(int f) const;
+	int faceTag(int f) const;
 	int cyclicTwin(int f) const;
 	int faceNeighbourCell(int f) const;
 };

@@ -451,10 +451,35 @@ int PolyMesh::whichPatch(int face) const {
 void PolyMesh::resolvePatches() {
 	for (Patch& p : patches) {
 		p.neighbPatchID = -1;
+		p.referPatchID = -1;
 		if (p.isCyclic())
 			for (size_t j = 0; j < patches.size(); j++)
 				if (patches[j].name == p.neighbourPatch) p.neighbPatchID = (int)j;
+		if (p.isProcessorCyclic()) {
+			for (size_t j = 0; j < patches.size(); j++)
+				if (patches[j].name == p.referPatch) p.referPatchID = (int)j;
+			if (p.referPatchID < 0) fail("processorCyclic patch " + p.name + " refers to the unknown patch " + p.referPatch);
+		}
 	}
+}
+
+// The signed tag the reference matches MPI faces with (polyMeshReaderOF.cpp:460-475 getBoundaryTag = tag() * (2 owner() - 1)).
+// Plain processor patches: tag() == UPstream::msgType() == 1.  processorCyclic patches: OpenFOAM hashes the name of the
+// referred cyclic patch on the owner side and of that patch's neighbour on the other side, so that both sides get the same
+// value; only that agreement (and a value outside [-1, 1], which switches getFaceId to the index inside the patch) matters
+// to the reference, so the hash here is FNV-1a folded into [2, 32767] rather than OpenFOAM's Jenkins hash.
+int PolyMesh::processorTag(int b) const {
+	const Patch& p = patches[(size_t)b];
+	if (!p.isProcessor()) return 0;
+	const int sign = p.myProcNo < p.neighbProcNo ? 1 : -1;   // processorPolyPatch::owner()
+	if (!p.isProcessorCyclic()) return sign;
+	if (p.tag > 1) return sign * p.tag;
+	const Patch& ref = patches[(size_t)p.referPatchID];
+	if (sign < 0 && ref.neighbPatchID < 0) fail("cyclic patch " + ref.name + " has no neighbourPatch");
+	const std::string& name = sign > 0 ? ref.name : patches[(size_t)ref.neighbPatchID].name;
+	uint32_t h = 2166136261u;
+	for (unsigned char ch : name) h = (h ^ ch) * 16777619u;
+	return sign * (int)(2u + h % 32766u);
 }
 
 void PolyMesh::buildCells() {
@@ -678,6 +703,8 @@ PolyMesh readPolyMesh(const std::string& dir) {
 			pt.neighbourPatch = e.sub->wordOr("neighbourPatch", "");
 			pt.myProcNo = (int)e.sub->scalarOr("myProcNo", -1);
 			pt.neighbProcNo = (int)e.sub->scalarOr("neighbProcNo", -1);
+			pt.referPatch = e.sub->wordOr("referPatch", "");
+			pt.tag = (int)e.sub->scalarOr("tag", -1);
 			m.patches.push_back(pt);
 		}
 	}
@@ -737,6 +764,7 @@ void writePolyMesh(const PolyMesh& m, const std::string& dir) {
 			if (p.isCyclic()) fprintf(f, "        neighbourPatch  %s;\n", p.neighbourPatch.c_str());
 			if (p.isProcessor())
 				fprintf(f, "        myProcNo        %d;\n        neighbProcNo    %d;\n", p.myProcNo, p.neighbProcNo);
+			if (p.isProcessorCyclic()) fprintf(f, "        referPatch      %s;\n", p.referPatch.c_str());
 			fprintf(f, "        nFaces          %d;\n        startFace       %d;\n    }\n", p.nFaces, p.startFace);
 		}
 		fprintf(f, ")\n");
@@ -844,6 +872,7 @@ void writeVolField(const std::string& path, const std::string& name, const PolyM
 		if (p.type == "empty") t = "empty";
 		if (p.type == "cyclic") t = "cyclic";
 		if (p.type == "processor") t = "processor";
+		if (p.type == "processorCyclic") t = "processorCyclic";
 		fprintf(f, "    %s\n    {\n        type            %s;\n    }\n", p.name.c_str(), t);
 	}
 	fprintf(f, "}\n");

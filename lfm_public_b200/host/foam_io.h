@@ -61,7 +61,11 @@ struct Patch {
 	int neighbPatchID = -1;      // resolved index of neighbourPatch
 	int myProcNo = -1;           // processor
 	int neighbProcNo = -1;       // processor
-	bool isProcessor() const { return type == "processor"; }
+	std::string referPatch;      // processorCyclic: the cyclic patch whose faces these were before the decomposition
+	int referPatchID = -1;       // resolved index of referPatch
+	int tag = -1;                // processorCyclic: message tag if the file gives one
+	bool isProcessorCyclic() const { return type == "processorCyclic"; }
+	bool isProcessor() const { return type == "processor" || isProcessorCyclic(); }   // processorCyclicPolyPatch derives from processorPolyPatch
 	bool isCyclic() const { return type == "cyclic"; }
 	bool coupled() const { return isProcessor() || isCyclic(); }
 };
@@ -92,6 +96,7 @@ struct PolyMesh {
 	int nInternalFaces() const { return (int)neighbour.size(); }
 	int nNonProcessor() const;          // index of the first processor patch
 	int whichPatch(int face) const;     // -1 for internal faces
+	int processorTag(int patch) const;   // processorPolyPatch::tag() * (2 owner() - 1); 0 for other patches (polyMeshReaderOF.cpp:460-475)
 	int facePointCount(int f) const { return faceOffsets[f + 1] - faceOffsets[f]; }
 
 	void buildCells();                  // cellFaceOffsets / cellFaces

@@ -441,7 +441,10 @@ def block_assignment(m, blocks):
 def decompose(m, cell_rank):
     """Returns a list of per-rank mesh dicts with processor patches (ascending neighbour rank, faces in
     ascending global face id on both sides), faceProcAddressing (1-based, negative when the local face
-    is flipped w.r.t. the global one), cellProcAddressing, pointProcAddressing, boundaryProcAddressing."""
+    is flipped w.r.t. the global one), cellProcAddressing, pointProcAddressing, boundaryProcAddressing.
+    A cyclic pair whose two cells live on different ranks becomes a pair of `processorCyclic` patches
+    (`procBoundaryAtoBthrough<cyclic patch>`, referPatch = the cyclic patch the faces came from, faces in the
+    order of the cyclic patch on both sides), as decomposePar does."""
     cell_rank = np.asarray(cell_rank, dtype=np.int64)
     n_ranks = int(cell_rank.max()) + 1
     nf = len(m["owner"])
@@ -452,13 +455,14 @@ def decompose(m, cell_rank):
     r_own = cell_rank[own]
     r_nei = np.where(nei >= 0, cell_rank[np.maximum(nei, 0)], -1)
     pid = np.full(nf, -1, dtype=np.int64)
+    twin_rank = np.full(nf, -1, dtype=np.int64)     # rank of the cyclic twin's cell where it differs from the face's own rank
     for i, p in enumerate(m["patches"]):
         if p["type"] == "cyclic":
-            # both halves of a cyclic pair must stay on one rank (no processorCyclic support)
             q = [x for x in m["patches"] if x["name"] == p["neighbourPatch"]][0]
-            ca = own[p["startFace"]:p["startFace"] + p["nFaces"]]
-            cb = own[q["startFace"]:q["startFace"] + q["nFaces"]]
-            assert (cell_rank[ca] == cell_rank[cb]).all(), "cyclic pair split across ranks"
+            assert q["nFaces"] == p["nFaces"]
+            ra = cell_rank[own[p["startFace"]:p["startFace"] + p["nFaces"]]]
+            rb = cell_rank[own[q["startFace"]:q["startFace"] + q["nFaces"]]]
+            twin_rank[p["startFace"]:p["startFace"] + p["nFaces"]] = np.where(ra != rb, rb, -1)
         pid[p["startFace"]:p["startFace"] + p["nFaces"]] = i
     out = []
     gfid = np.arange(nf, dtype=np.int64)
@@ -467,7 +471,8 @@ def decompose(m, cell_rank):
         local_of_global = np.full(m["nCells"], -1, dtype=np.int64)
         local_of_global[cells] = np.arange(len(cells))
         sel_int = (r_own == r) & (r_nei == r)
-        sel_bnd = (r_own == r) & (nei < 0)
+        sel_bnd = (r_own == r) & (nei < 0) & (twin_rank < 0)
+        sel_pc = (r_own == r) & (nei < 0) & (twin_rank >= 0)   # cyclic faces whose twin went to another rank
         sel_po = (r_own == r) & (nei >= 0) & (r_nei != r)      # we hold the global owner: keep orientation
         sel_pn = (r_nei == r) & (r_own != r)                   # we hold the global neighbour: flip
         f_int = gfid[sel_int]
@@ -477,8 +482,11 @@ def decompose(m, cell_rank):
         other = np.concatenate([r_nei[sel_po], r_own[sel_pn]])
         o = np.lexsort((f_proc, other))
         f_proc, flip_proc, other = f_proc[o], flip_proc[o], other[o]
-        f_all = np.concatenate([f_int, f_bnd, f_proc])
-        flip = np.concatenate([np.zeros(len(f_int) + len(f_bnd), bool), flip_proc])
+        f_pc = gfid[sel_pc]
+        o = np.lexsort((f_pc, pid[f_pc], twin_rank[f_pc]))     # by neighbour rank, then cyclic patch, then position in it
+        f_pc = f_pc[o]
+        f_all = np.concatenate([f_int, f_bnd, f_proc, f_pc])
+        flip = np.concatenate([np.zeros(len(f_int) + len(f_bnd), bool), flip_proc, np.zeros(len(f_pc), bool)])
         faces = _flip(m["faces"][f_all], flip)
         l_own = np.where(flip, local_of_global[np.maximum(nei[f_all], 0)], local_of_global[own[f_all]])
         l_nei = local_of_global[nei[f_int]]
@@ -502,6 +510,14 @@ def decompose(m, cell_rank):
                                 nFaces=n, startFace=start))
             start += n
             bpa.append(-1)
+        for nb in np.unique(twin_rank[f_pc]):
+            for i in np.unique(pid[f_pc][twin_rank[f_pc] == nb]):
+                n = int(np.count_nonzero((twin_rank[f_pc] == nb) & (pid[f_pc] == i)))
+                ref = m["patches"][int(i)]["name"]
+                patches.append(dict(name=f"procBoundary{r}to{int(nb)}through{ref}", type="processorCyclic", myProcNo=r,
+                                    neighbProcNo=int(nb), referPatch=ref, nFaces=n, startFace=start))
+                start += n
+                bpa.append(-1)
         # canonical order inside rank: internal faces are already (owner, neighbour)-sorted because the
         # local numbering preserves the global cell order
         assert (np.diff(l_own[:len(f_int)]) >= 0).all()
@@ -575,8 +591,10 @@ def write_polymesh(m, mesh_dir):
             f.write(f"    {p['name']}\n    {{\n        type            {p['type']};\n")
             if p["type"] == "cyclic":
                 f.write(f"        neighbourPatch  {p['neighbourPatch']};\n")
-            if p["type"] == "processor":
+            if p["type"] in ("processor", "processorCyclic"):
                 f.write(f"        myProcNo        {p['myProcNo']};\n        neighbProcNo    {p['neighbProcNo']};\n")
+            if p["type"] == "processorCyclic":
+                f.write(f"        referPatch      {p['referPatch']};\n")
             f.write(f"        nFaces          {p['nFaces']};\n        startFace       {p['startFace']};\n    }}\n")
         f.write(")\n")
     for key in ("faceProcAddressing", "cellProcAddressing", "pointProcAddressing", "boundaryProcAddressing", "cellSubmesh"):
@@ -597,6 +615,6 @@ def write_field(path, name, m, values):
             f.write("\n".join("%.17g" % v for v in values.tolist()))
         f.write("\n)\n;\n\nboundaryField\n{\n")
         for p in m["patches"]:
-            t = {"empty": "empty", "cyclic": "cyclic", "processor": "processor"}.get(p["type"], "zeroGradient")
+            t = {"empty": "empty", "cyclic": "cyclic", "processor": "processor", "processorCyclic": "processorCyclic"}.get(p["type"], "zeroGradient")
             f.write(f"    {p['name']}\n    {{\n        type            {t};\n    }}\n")
         f.write("}\n")

@@ -363,10 +363,7 @@ int CPolyMeshReaderOF::getBoundaryProcessorRank(const int b) const {
 	return MESH.patches[(size_t)b].neighbProcNo;
 }
 int CPolyMeshReaderOF::getBoundaryTag(const int b) const {
-	if (b < MESH.nNonProcessor()) return 0;
-	const lfm::Patch& p = MESH.patches[(size_t)b];
-	const int owner = p.myProcNo < p.neighbProcNo ? 1 : 0;   // processorPolyPatch::owner()
-	return 1 * (2 * owner - 1);                              // tag() == UPstream::msgType() == 1
+	return MESH.processorTag(b);   // tag() * (2 owner() - 1); plain processor patches: tag() == UPstream::msgType() == 1
 }
 int CPolyMeshReaderOF::getBoundaryCyclicPairIndex(const int b) const {
 	return MESH.patches[(size_t)b].coupled() ? -1 : MESH.patches[(size_t)b].neighbPatchID;

@@ -66,6 +66,12 @@ CASES = {
                             opts=dict(solver=1, dimension=3, deltaT=2e-3, Ls=0.4, commType=2, mu=7.17948717948718e-05, simulationType="LES")),
     "ogrid3d_m1_les": dict(mesh=lambda: meshgen.ogrid_cylinder(8, 16, 4, r_in=0.5, r_out=6.0, span=1.0, stretch=4.0), two_d=False,
                            blocks=None, opts=dict(solver=0, dimension=3, deltaT=1e-3, Ls=2.0, mu=7.17948717948718e-05, simulationType="LES")),
+    # z-periodic box split in z too: the cyclic pair is cut by the decomposition -> processorCyclic patches (faceId = index
+    # inside the patch, hashed tag; polyMeshReaderOF.cpp:251-261, 460-475), next to plain processor patches of the same rank pair
+    "hex3d_m2_pc8": dict(mesh=_hex3d, two_d=False, blocks=(2, 2, 2),
+                         opts=dict(solver=1, dimension=3, deltaT=2e-3, Ls=0.4, commType=2, mu=7.17948717948718e-05)),
+    "hex3d_m1_pc2": dict(mesh=_hex3d, two_d=False, blocks=(1, 1, 2),
+                         opts=dict(solver=0, dimension=3, deltaT=2e-3, Ls=0.4, commType=1, mu=7.17948717948718e-05)),
     # solver 2: M2 + AUSM+up pressure dissipation with minmod-limited reconstruction (one_rk_step_M2AUSM)
     "hex3d_ausm_p4": dict(mesh=_hex3d, two_d=False, blocks=(2, 2, 1),
                           opts=dict(solver=2, dimension=3, deltaT=2e-3, Ls=0.4, commType=2, mu=7.17948717948718e-05, minmodExists=True)),

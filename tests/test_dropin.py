@@ -51,7 +51,7 @@ def _pair(name, tmp_path, sp=False, **override):
 
 @needs_bins
 @pytest.mark.parametrize("name", ["quad2d_m1", "quad2d_m1_p4", "quad2d_m2_p2_packed", "tri2d_m2", "hex3d_m2_p4", "ogrid3d_m2", "hex3d_m2_les_p4",
-                                  "ogrid3d_m1_les", "hex3d_ausm_p4", "ogrid2d_ausm", "quad2d_ausm_nominmod"])
+                                  "ogrid3d_m1_les", "hex3d_ausm_p4", "ogrid2d_ausm", "quad2d_ausm_nominmod", "hex3d_m2_pc8"])
 def test_dropin_fields_identical_fp64(name, tmp_path):
     o, ref_dir, gpu_dir, out_ref, out_gpu = _pair(name, tmp_path)
     D = o["dimension"]

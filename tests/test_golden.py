@@ -1,5 +1,6 @@
 """The CPU restatement (oracle/lfm_oracle.c) against the committed golden vectors, which were produced by the
 reference's own CPU solver (tests/golden/make_golden.py).  Runs without /root/reference."""
+import hashlib
 import os
 
 import numpy as np
@@ -36,7 +37,12 @@ def test_oracle_matches_golden_fp64(name, tmp_path):
         for k in ("rho", "U", "E", "p"):
             assert np.array_equal(mine[k], g[f"r{r}_{k}"]), f"{name} rank {r} {k}"
     for (src, dst), msgs in record.items():
-        assert np.concatenate(msgs).tobytes() == g[f"halo_{src}_{dst}"].tobytes(), f"{name} halo {src}->{dst}"
+        stream = np.concatenate(msgs).tobytes()
+        if f"halo_{src}_{dst}" in g:
+            assert stream == g[f"halo_{src}_{dst}"].tobytes(), f"{name} halo {src}->{dst}"
+        else:                                      # large cases keep a digest of the stream (make_golden.py HALO_DIGEST)
+            assert hashlib.sha256(stream).digest() == g[f"halo_{src}_{dst}_sha256"].tobytes(), f"{name} halo {src}->{dst}"
+            assert int(g[f"halo_{src}_{dst}_n"].sum()) * 8 == len(stream)
 
 
 @pytest.mark.parametrize("name", GOLDEN_SP)
