@@ -145,7 +145,7 @@ int lfmgpu_step_multi(const lfmgpu_t* hs, int n_ranks, int scheme, double dt, in
 /* The scalar reductions Mesh::solve does with MPI_Allreduce / MPI_Reduce (mesh_solver.cpp:715, 763-779,
  * cfd_v0.cpp:3242-3243): op 0 = sum, 1 = min, 2 = max over the NCCL ranks, in place, n <= 8; blocking. */
 int lfmgpu_allreduce(lfmgpu_t h, double* values, int n, int op);
-/* Options: "use_tiles" 1 (default) = fused shared-memory tile kernels, 0 = face kernel + gather kernels (tuning);
+/* Options: "use_tiles" 1 (default) = fused shared-memory tile kernels (all three schemes), 0 = face kernel + gather kernels (tuning);
  * "laminar" 1 (default) / 0 = lfmgpu_step and lfmgpu_step_multi call calc_VIS / calc_VIS_Smagorinsky
  * (CInputReader::m_bLaminar, reference: src/inputReader.cpp:60, src/mesh_solver.cpp:556-560);
  * "minmod" 0 (default) / 1 = with LFMGPU_SCHEME_M2AUSM those loops call calc_gradients_M2AUSM before calc_VIS

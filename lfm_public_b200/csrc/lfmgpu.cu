@@ -20,6 +20,10 @@
 #include "lfmgpu.h"
 #include "tile_kernels.cuh"
 
+#ifndef LFM_AUSM_MINB64
+#define LFM_AUSM_MINB64 2
+#endif
+
 using namespace lfm;
 
 namespace {
@@ -480,8 +484,9 @@ template <class R, int D> int t_rk_stage(lfmgpu_ctx* h, int sub, int scheme, int
 	const int first = h->dq_zero ? 1 : 0;
 	const R Ak = (R)h->c.Ak[rk], Bk = (R)h->c.Bk[rk];
 	if (c1 > c0) {
-		// solver 2 is served by the face kernel + gather kernels (the tile stage kernel has no M2-AUSM variant yet)
-		if (h->use_tiles && h->tiles.ready && scheme != LFMGPU_SCHEME_M2AUSM) {
+		// solver 2 with the Smagorinsky closure would need both sets of extra rows staged: not served by either path
+		if (scheme == LFMGPU_SCHEME_M2AUSM && h->les) return fail("M2-AUSM is served with the laminar closure only");
+		if (h->use_tiles && h->tiles.ready) {
 			TRY((ensure_drv<R, D>(h, scheme)));
 			TRY((tile_stage<R, D>(h, sub, scheme, (R)dt, Ak, Bk, first, res)));
 		} else {
@@ -653,22 +658,44 @@ template <class R, int D> int tile_grad(lfmgpu_ctx* h, int sub) {
 	return 0;
 }
 
+// resident CTAs the M2-AUSM stage kernel is compiled for (register cap 65536 / (256 * n))
+template <class R> constexpr int kAusmMinBlocks = sizeof(R) == 8 ? LFM_AUSM_MINB64 : 2;
+
 template <class R, int D, int SCHEME> int tile_stage_s(lfmgpu_ctx* h, int sub, R dt, R Ak, R Bk, int first, int res) {
-	if (sub < 0 && !all_fixed(h)) {
+	if (sub < 0 && (!all_fixed(h) || SCHEME == 2)) {
 		for (int s = 0; s < h->n_sub; s++) TRY((tile_stage_s<R, D, SCHEME>(h, s, dt, Ak, Bk, first, res)));
 		return 0;
 	}
 	int t0, t1, smax, fmax;
 	tile_range(h, sub, t0, t1, smax, fmax);
 	if (t1 <= t0) return 0;
-	const bool fixed = h->fixed_strides && smax <= kFixedSmax && fmax <= kFixedFmax;
+	bool fixed = h->fixed_strides && smax <= kFixedSmax && fmax <= kFixedFmax;
 	if (fixed) {
 		smax = kFixedSmax;
 		fmax = kFixedFmax;
 	}
-	size_t smem = stage_smem<R, D>(smax, fmax) + (h->les ? (size_t)D * D * smax * sizeof(R) : 0);
+	if (SCHEME == 2) {
+		// solver 2: the 2D + D^2 gradient rows are staged too; with the launch's own strides (not the compile-time ones) two
+		// CTAs still fit an SM
+		fixed = false;
+		tile_range(h, sub, t0, t1, smax, fmax);
+	}
+	size_t smem = stage_smem<R, D>(smax, fmax) + (h->les ? (size_t)D * D * smax * sizeof(R) : 0) + (SCHEME == 2 ? (size_t)(2 * D + D * D) * smax * sizeof(R) : 0);
 	if (const char* e = getenv("LFMGPU_SMEM_PAD")) smem += (size_t)atoi(e) * 1024;   // experiment knob: fewer resident CTAs
 	TileView<R> tview = tile_view<R>(h, smax, fmax);
+	if constexpr (SCHEME == 2) {   // M2-AUSM: one configuration (256 threads), laminar closure
+		const int nt_ = 256;
+		int dev_smem = 0;
+		CU(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+		if (smem > (size_t)dev_smem) return fail("M2-AUSM: a tile needs %zu bytes of shared memory (limit %d): lower LFMGPU_TILE_CELLS or set use_tiles=0", smem, dev_smem);
+		auto kern = k_tile_stage<R, D, SCHEME, 256, kAusmMinBlocks<R>, 0, 0, 2>;
+		if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		LAUNCH(h, "tile_stage", h->s_main,
+		       (kern<<<t1 - t0, nt_, smem, h->s_main>>>(h->mesh<R>(), tview, (const R*)h->q[h->cur], (const R*)h->drv[h->cur], (R*)h->q[1 - h->cur], (R*)h->drv[1 - h->cur], t0, dt, Ak, Bk,
+		                                              first, res)));
+		CHECK_LAUNCH();
+		return 0;
+	} else {
 	if (h->les) {   // Smagorinsky closure: tauMC is staged too (one configuration: 256 threads, 2 CTAs/SM)
 		const int nt_ = 256;
 		int dev_smem = 0;
@@ -740,8 +767,10 @@ template <class R, int D, int SCHEME> int tile_stage_s(lfmgpu_ctx* h, int sub, R
 #undef LFM_STAGE_LAUNCH
 	CHECK_LAUNCH();
 	return 0;
+	}   // SCHEME != 2
 }
 template <class R, int D> int tile_stage(lfmgpu_ctx* h, int sub, int scheme, R dt, R Ak, R Bk, int first, int res) {
+	if (scheme == LFMGPU_SCHEME_M2AUSM) return tile_stage_s<R, D, 2>(h, sub, dt, Ak, Bk, first, res);
 	return scheme == LFMGPU_SCHEME_M1 ? tile_stage_s<R, D, 0>(h, sub, dt, Ak, Bk, first, res) : tile_stage_s<R, D, 1>(h, sub, dt, Ak, Bk, first, res);
 }
 

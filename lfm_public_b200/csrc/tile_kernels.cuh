@@ -98,6 +98,10 @@ template <int D> struct StagedLayout {
 	static constexpr int NS = SIGMAU + D;
 	static constexpr int TAUMC = NS;             // staged only with the Smagorinsky closure
 	static constexpr int NS_LES = NS + D * D;
+	// solver 2 (M2-AUSM): the minmod gradients of calc_gradients_M2AUSM ride along (instead of tauMC: laminar closure only)
+	static constexpr int GRHO = NS, GP = NS + D, GU = NS + 2 * D;
+	static constexpr int NS_AUSM = NS + 2 * D + D * D;
+	__host__ __device__ static constexpr int rows(int mode) { return mode == 1 ? NS_LES : (mode == 2 ? NS_AUSM : NS); }
 };
 
 // a side of a face staged in shared memory (SoA rows of stride smax); values are loaded where they are used
@@ -113,7 +117,36 @@ template <class R, int D> struct SmemSide {
 	__device__ __forceinline__ R dTdx(int a) const { return st[(L::DTDX + a) * smax + i]; }
 	__device__ __forceinline__ R sigmaU(int a) const { return st[(L::SIGMAU + a) * smax + i]; }
 	__device__ __forceinline__ R tauMC(int a, int b) const { return st[(L::TAUMC + a * D + b) * smax + i]; }
+	__device__ __forceinline__ R g_rho(int a) const { return st[(L::GRHO + a) * smax + i]; }
+	__device__ __forceinline__ R g_p(int a) const { return st[(L::GP + a) * smax + i]; }
+	__device__ __forceinline__ R g_U(int a, int b) const { return st[(L::GU + a * D + b) * smax + i]; }
 };
+
+// The AUSM+up pressure term of one face of solver 2 with both sides staged in shared memory (ausm_pressure_term of
+// device_math.cuh fed from the staged rows; dv = owner -> neighbour vector of the face).
+template <class R, int D> __device__ __forceinline__ R ausm_extra_staged(const Consts<R>& k, const SmemSide<R, D>& c, const SmemSide<R, D>& n, const R* S, const R* dv, R weight) {
+	R cq[D + 2], nq[D + 2], cd[D][D], nd[D][D], cUg[D][D], nUg[D][D], crg[D], nrg[D], cpg[D], npg[D];
+#pragma unroll
+	for (int i = 0; i < D + 2; i++) {
+		cq[i] = c.q(i);
+		nq[i] = n.q(i);
+	}
+#pragma unroll
+	for (int i = 0; i < D; i++) {
+		crg[i] = c.g_rho(i);
+		nrg[i] = n.g_rho(i);
+		cpg[i] = c.g_p(i);
+		npg[i] = n.g_p(i);
+#pragma unroll
+		for (int j = 0; j < D; j++) {
+			cd[i][j] = c.dudx(i, j);
+			nd[i][j] = n.dudx(i, j);
+			cUg[i][j] = c.g_U(i, j);
+			nUg[i][j] = n.g_U(i, j);
+		}
+	}
+	return ausm_pressure_term<R, D>(k, cq, nq, c.Rpsi(), n.Rpsi(), cd, nd, cUg, nUg, crg, nrg, cpg, npg, S, dv, weight);
+}
 
 constexpr int kMaxSlots = 6;   // FACE_CNT of the reference is at most 6 (hexahedra)
 
@@ -356,7 +389,7 @@ __global__ void __launch_bounds__(NT, MINB)
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int smax = SMAX ? SMAX : tv.smax, fmax = FMAX ? FMAX : tv.fmax;
 	R* st = reinterpret_cast<R*>(smem_raw);      // [NS (+D*D)][smax]
-	R* fl = st + (size_t)(LES ? L::NS_LES : L::NS) * smax;   // [NQ][fmax]
+	R* fl = st + (size_t)L::rows(LES) * smax;   // [NQ][fmax]
 	const TileDesc td = tv.tiles[tile0 + blockIdx.x];
 	const int ns = td.nt + td.nh;
 	const int nf = td.nfo + td.ninc;
@@ -375,9 +408,18 @@ __global__ void __launch_bounds__(NT, MINB)
 			cp_async_elem(st + (L::DTDX + k) * smax + i, m.dTdx + (size_t)k * m.ncs + x);
 			cp_async_elem(st + (L::SIGMAU + k) * smax + i, m.sigmaU + (size_t)k * m.ncs + x);
 		}
-		if (LES) {
+		if (LES == 1) {
 #pragma unroll
 			for (int k = 0; k < D * D; k++) cp_async_elem(st + (L::TAUMC + k) * smax + i, m.tauMC + (size_t)k * m.ncs + x);
+		}
+		if (LES == 2) {   // solver 2: minmod gradients (ghost slots hold zeros, as in the reference)
+#pragma unroll
+			for (int k = 0; k < D; k++) {
+				cp_async_elem(st + (L::GRHO + k) * smax + i, m.g_rho + (size_t)k * m.ncs + x);
+				cp_async_elem(st + (L::GP + k) * smax + i, m.g_p + (size_t)k * m.ncs + x);
+			}
+#pragma unroll
+			for (int k = 0; k < D * D; k++) cp_async_elem(st + (L::GU + k) * smax + i, m.g_U + (size_t)k * m.ncs + x);
 		}
 	}
 	// the first face's constants travel while the copies land
@@ -395,13 +437,15 @@ __global__ void __launch_bounds__(NT, MINB)
 		R dv[D];
 #pragma unroll
 		for (int i = 0; i < D; i++) dv[i] = R(0);
-		if (ghost) {
+		if (ghost || LES == 2) {   // solver 2 reconstructs along d on every face
 			const int f = tv.f_gface[(size_t)td.f_off + lf];
 #pragma unroll
 			for (int i = 0; i < D; i++) dv[i] = m.d[i * m.nfs + f];
 		}
 		R rhs[NQ];
-		face_flux<R, D, SCHEME, SmemSide<R, D>, SmemSide<R, D>, LES>(m.k, SmemSide<R, D>{st, smax, lo}, SmemSide<R, D>{st, smax, ln}, cur.g, ghost, dv, rhs);
+		R extra = R(0);
+		if (LES == 2) extra = ausm_extra_staged<R, D>(m.k, SmemSide<R, D>{st, smax, lo}, SmemSide<R, D>{st, smax, ln}, cur.g.S, dv, cur.g.w);
+		face_flux<R, D, SCHEME, SmemSide<R, D>, SmemSide<R, D>, (LES == 1 ? 1 : 0)>(m.k, SmemSide<R, D>{st, smax, lo}, SmemSide<R, D>{st, smax, ln}, cur.g, ghost, dv, rhs, extra);
 #pragma unroll
 		for (int i = 0; i < NQ; i++) fl[i * fmax + lf] = rhs[i];
 		if (lf + NT < nf) cur = nxt;
