@@ -161,6 +161,7 @@ struct lfmgpu_ctx {
 	bool ausm_zero = false;            // g_rho / g_p / g_U hold what prepare_for_RKstep leaves (zeros)
 	std::vector<int> smag_owner;       // cell whose face loop leaves each cell's final tauMC (Smagorinsky constant)
 	int tile_smem_budget = 75 * 1024;  // bytes of shared memory one tile CTA may use
+	int smem_pad_kb = 0;               // extra shared memory requested per stage CTA (occupancy experiments)
 	// introspection
 	uint64_t launches = 0;
 	bool timing = false;
@@ -681,7 +682,7 @@ template <class R, int D, int SCHEME> int tile_stage_s(lfmgpu_ctx* h, int sub, R
 		tile_range(h, sub, t0, t1, smax, fmax);
 	}
 	size_t smem = stage_smem<R, D>(smax, fmax) + (h->les ? (size_t)D * D * smax * sizeof(R) : 0) + (SCHEME == 2 ? (size_t)(2 * D + D * D) * smax * sizeof(R) : 0);
-	if (const char* e = getenv("LFMGPU_SMEM_PAD")) smem += (size_t)atoi(e) * 1024;   // experiment knob: fewer resident CTAs
+	smem += (size_t)h->smem_pad_kb * 1024;   // experiment knob LFMGPU_SMEM_PAD: fewer resident CTAs
 	TileView<R> tview = tile_view<R>(h, smax, fmax);
 	if constexpr (SCHEME == 2) {   // M2-AUSM: one configuration (256 threads), laminar closure
 		const int nt_ = 256;
@@ -1266,6 +1267,7 @@ int lfmgpu_create(const lfmgpu_desc* ds, int device, lfmgpu_t* out) {
 	if (const char* e = getenv("LFMGPU_USE_TILES")) h->use_tiles = atoi(e);
 	if (const char* e = getenv("LFMGPU_FIXED_STRIDES")) h->fixed_strides = atoi(e);
 	if (const char* e = getenv("LFMGPU_TILE_SMEM")) h->tile_smem_budget = std::max(16, atoi(e)) * 1024;
+	if (const char* e = getenv("LFMGPU_SMEM_PAD")) h->smem_pad_kb = std::max(0, atoi(e));
 	if (!rc) rc = tile_plan_build(h, ds);
 	if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = fail("upload failed: %s", cudaGetErrorString(cudaGetLastError()));
 	if (rc) {
