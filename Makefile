@@ -16,7 +16,7 @@ NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xco
            -I$(INC) -I$(NCCL_INC) $(EXTRA_NVFLAGS)
 REF    ?= /root/reference
 
-HOST_SRC := $(HOST)/foam_io.cpp $(HOST)/flatten.cpp $(HOST)/hostapi.cpp
+HOST_SRC := $(HOST)/foam_io.cpp $(HOST)/flatten.cpp $(HOST)/hostapi.cpp $(HOST)/hpath.cpp
 GPU_SRC  := $(CSRC)/lfmgpu.cu
 GPU_HDR  := $(wildcard $(CSRC)/*.cuh) $(INC)/lfmgpu.h
 

@@ -73,6 +73,10 @@ int lfmhost_finish(lfmhost_case* c);
 const lfmgpu_desc* lfmhost_desc(const lfmhost_case* c);
 /* polyMesh geometry as computed for this case: any pointer may be NULL */
 int lfmhost_geometry(const lfmhost_case* c, double* face_areas, double* face_centres, double* cell_centres, double* cell_volumes);
+/* Hamiltonian-path cell numbering of the case's mesh (reference: hpathRenumber/hpathRenumber.C, the `hpath` method of
+ * renumberMesh): order[new] = old, boundary submesh first.  stats[4]: boundary cells, boundary walk ok, interior walk ok,
+ * fraction of the interior cells on the path itself. */
+int lfmhost_hpath_order(const lfmhost_case* c, int32_t* order, double* stats);
 int lfmhost_mesh_sizes(const lfmhost_case* c, int32_t* n_points, int32_t* n_faces, int32_t* n_internal, int32_t* n_cells);
 /* Writes `values` ([n_cells] traversal order, nComp components interleaved) as an OpenFOAM vol field in polyMesh cell order */
 int lfmhost_write_field(const lfmhost_case* c, const char* path, const char* name, const double* values, int n_comp, int precision);

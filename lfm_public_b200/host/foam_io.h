@@ -121,4 +121,7 @@ void writeVolField(const std::string& path, const std::string& name, const PolyM
 
 std::string timeName(double t, int precision = 12);   // OpenFOAM "general" time formatting
 
+// hpath.cpp: restatement of the reference's hpathRenumber plugin; order[new] = old, stats as in lfmhost_hpath_order
+std::vector<int> hpathOrder(const PolyMesh& mesh, double stats[4]);
+
 }  // namespace lfm

@@ -215,6 +215,19 @@ int lfmhost_geometry(const lfmhost_case* c, double* fa, double* fc, double* cc, 
 	if (cv) memcpy(cv, m.cellVolumes.data(), m.cellVolumes.size() * sizeof(double));
 	return 0;
 }
+int lfmhost_hpath_order(const lfmhost_case* c, int32_t* order, double* stats) {
+	try {
+		double st[4] = {0, 0, 0, 0};
+		const std::vector<int> o = lfm::hpathOrder(c->mesh, st);
+		if ((int)o.size() != c->mesh.nCells) throw std::runtime_error("hpath: the order does not cover the mesh");
+		for (size_t i = 0; i < o.size(); i++) order[i] = o[i];
+		if (stats)
+			for (int k = 0; k < 4; k++) stats[k] = st[k];
+		return 0;
+	} catch (const std::exception& e) {
+		return setErr(e);
+	}
+}
 int lfmhost_mesh_sizes(const lfmhost_case* c, int32_t* np, int32_t* nf, int32_t* ni, int32_t* nc) {
 	if (np) *np = c->mesh.nPoints();
 	if (nf) *nf = c->mesh.nFaces();

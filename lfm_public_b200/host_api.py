@@ -38,6 +38,7 @@ def lib():
         L.lfmhost_desc.restype = C.POINTER(Desc)
         L.lfmhost_geometry.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.lfmhost_mesh_sizes.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 4
+        L.lfmhost_hpath_order.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.lfmhost_write_field.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int]
         L.lfmhost_close.argtypes = [C.c_void_p]
         _LIB = L
@@ -178,6 +179,15 @@ class Case:
         fa = np.zeros((nf.value, 3)); fc = np.zeros((nf.value, 3)); cc = np.zeros((nc.value, 3)); cv = np.zeros(nc.value)
         lib().lfmhost_geometry(self._h, fa.ctypes.data, fc.ctypes.data, cc.ctypes.data, cv.ctypes.data)
         return dict(face_areas=fa, face_centres=fc, cell_centres=cc, cell_volumes=cv)
+
+    def hpath_order(self):
+        """Hamiltonian-path numbering of the case's mesh (hpathRenumber plugin restated): (order[new] = old, stats dict)."""
+        nc = C.c_int32()
+        lib().lfmhost_mesh_sizes(self._h, None, None, None, C.byref(nc))
+        order = np.zeros(nc.value, dtype=np.int32)
+        st = np.zeros(4)
+        _check(lib().lfmhost_hpath_order(self._h, order.ctypes.data, st.ctypes.data))
+        return order, dict(boundary_cells=int(st[0]), boundary_walk_ok=bool(st[1]), interior_walk_ok=bool(st[2]), interior_path_fraction=float(st[3]))
 
     def to_mesh_order(self, values):
         """[n_cells, ...] in traversal order -> polyMesh cell order."""

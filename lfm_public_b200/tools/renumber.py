@@ -2,7 +2,7 @@
 """Standalone cell renumbering of an OpenFOAM/LFM case: the pre-processing step the reference does with OpenFOAM's
 `renumberMesh` (examples/*/constant/renumberMeshDict: CuthillMcKee, or the hpathRenumber plugin in 2D), without OpenFOAM.
 
-    python -m lfm_public_b200.tools.renumber <case_in> <case_out> [--method morton|hilbert|rcm]
+    python -m lfm_public_b200.tools.renumber <case_in> <case_out> [--method morton|hilbert|rcm|hpath]
 
 Writes <case_out> with the permuted polyMesh (faces re-sorted into OpenFOAM's upper-triangular order) and the permuted
 fields of the start time directory; dictionaries are copied.  Methods:
@@ -10,7 +10,9 @@ fields of the start time directory; dictionaries are copied.  Methods:
            wavefront numbering keeps a cell's neighbours ~one front width away -- poor for shared-memory tiles;
   morton   cells along a Z-order curve through their centres: consecutive ids form compact patches, which is what the
            tile kernels (and hpath's "boundary cells first, then a path through the interior") want;
-  hilbert  2D Hilbert curve (x, y), slightly more compact than Z-order for extruded 2D meshes.
+  hilbert  2D Hilbert curve (x, y), slightly more compact than Z-order for extruded 2D meshes;
+  hpath    the reference's own hpathRenumber plugin restated (lfm_public_b200/host/hpath.cpp): boundary submesh first,
+           then a Hamiltonian-like path through the interior (2D meshes).
 """
 from __future__ import annotations
 
@@ -69,9 +71,20 @@ def locality(m, new_of_old=None):
     return dict(mean=float(d.mean()), median=float(np.median(d)), p90=float(np.percentile(d, 90)), max=int(d.max()))
 
 
+def hpath_order(case_in):
+    """new_of_old of the reference's hpath numbering, computed by liblfmhost.so on the case's polyMesh (+ the walk statistics)."""
+    from .. import host_api
+    case = host_api.Case.open(case_in)
+    order, stats = case.hpath_order()          # order[new] = old
+    case.close()
+    new_of_old = np.empty(len(order), dtype=np.int64)
+    new_of_old[order] = np.arange(len(order))
+    return new_of_old, stats
+
+
 def renumber_case(case_in, case_out, method="morton", time_name="0", fields=("p", "T", "U", "alpha")):
     m = foamcase.read_polymesh(os.path.join(case_in, "constant", "polyMesh"))
-    new_of_old = order_cells(m, method)
+    new_of_old = hpath_order(case_in)[0] if method == "hpath" else order_cells(m, method)
     out = meshgen.renumber_cells(m, new_of_old)
     if os.path.exists(case_out):
         shutil.rmtree(case_out)
@@ -95,7 +108,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("case_in")
     ap.add_argument("case_out")
-    ap.add_argument("--method", default="morton", choices=["morton", "hilbert", "rcm"])
+    ap.add_argument("--method", default="morton", choices=["morton", "hilbert", "rcm", "hpath"])
     args = ap.parse_args()
     m, out, p = renumber_case(args.case_in, args.case_out, args.method)
     print("before:", locality(m))
