@@ -380,7 +380,8 @@ __device__ __forceinline__ void gather_update(const DevMesh<R>& m, const TileVie
 	}
 }
 
-template <class R, int D, int SCHEME, int NT, int MINB, int SMAX = 0, int FMAX = 0, int LES = 0>
+// EXTRA: rows staged on top of StagedLayout::NS -- 0 none, 1 tauMC (Smagorinsky closure), 2 the minmod gradients of solver 2 (M2-AUSM)
+template <class R, int D, int SCHEME, int NT, int MINB, int SMAX = 0, int FMAX = 0, int EXTRA = 0>
 __global__ void __launch_bounds__(NT, MINB)
     k_tile_stage(DevMesh<R> m, TileView<R> tv, const R* __restrict__ q, const R* __restrict__ drv, R* __restrict__ qn, R* __restrict__ drvn, int tile0, R dt, R Ak, R Bk, int first, int res) {
 	using L = StagedLayout<D>;
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(NT, MINB)
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int smax = SMAX ? SMAX : tv.smax, fmax = FMAX ? FMAX : tv.fmax;
 	R* st = reinterpret_cast<R*>(smem_raw);      // [NS (+D*D)][smax]
-	R* fl = st + (size_t)L::rows(LES) * smax;   // [NQ][fmax]
+	R* fl = st + (size_t)L::rows(EXTRA) * smax;   // [NQ][fmax]
 	const TileDesc td = tv.tiles[tile0 + blockIdx.x];
 	const int ns = td.nt + td.nh;
 	const int nf = td.nfo + td.ninc;
@@ -408,11 +409,11 @@ __global__ void __launch_bounds__(NT, MINB)
 			cp_async_elem(st + (L::DTDX + k) * smax + i, m.dTdx + (size_t)k * m.ncs + x);
 			cp_async_elem(st + (L::SIGMAU + k) * smax + i, m.sigmaU + (size_t)k * m.ncs + x);
 		}
-		if (LES == 1) {
+		if (EXTRA == 1) {
 #pragma unroll
 			for (int k = 0; k < D * D; k++) cp_async_elem(st + (L::TAUMC + k) * smax + i, m.tauMC + (size_t)k * m.ncs + x);
 		}
-		if (LES == 2) {   // solver 2: minmod gradients (ghost slots hold zeros, as in the reference)
+		if (EXTRA == 2) {   // solver 2: minmod gradients (ghost slots hold zeros, as in the reference)
 #pragma unroll
 			for (int k = 0; k < D; k++) {
 				cp_async_elem(st + (L::GRHO + k) * smax + i, m.g_rho + (size_t)k * m.ncs + x);
@@ -437,15 +438,15 @@ __global__ void __launch_bounds__(NT, MINB)
 		R dv[D];
 #pragma unroll
 		for (int i = 0; i < D; i++) dv[i] = R(0);
-		if (ghost || LES == 2) {   // solver 2 reconstructs along d on every face
+		if (ghost || EXTRA == 2) {   // solver 2 reconstructs along d on every face
 			const int f = tv.f_gface[(size_t)td.f_off + lf];
 #pragma unroll
 			for (int i = 0; i < D; i++) dv[i] = m.d[i * m.nfs + f];
 		}
 		R rhs[NQ];
 		R extra = R(0);
-		if (LES == 2) extra = ausm_extra_staged<R, D>(m.k, SmemSide<R, D>{st, smax, lo}, SmemSide<R, D>{st, smax, ln}, cur.g.S, dv, cur.g.w);
-		face_flux<R, D, SCHEME, SmemSide<R, D>, SmemSide<R, D>, (LES == 1 ? 1 : 0)>(m.k, SmemSide<R, D>{st, smax, lo}, SmemSide<R, D>{st, smax, ln}, cur.g, ghost, dv, rhs, extra);
+		if (EXTRA == 2) extra = ausm_extra_staged<R, D>(m.k, SmemSide<R, D>{st, smax, lo}, SmemSide<R, D>{st, smax, ln}, cur.g.S, dv, cur.g.w);
+		face_flux<R, D, SCHEME, SmemSide<R, D>, SmemSide<R, D>, (EXTRA == 1 ? 1 : 0)>(m.k, SmemSide<R, D>{st, smax, lo}, SmemSide<R, D>{st, smax, ln}, cur.g, ghost, dv, rhs, extra);
 #pragma unroll
 		for (int i = 0; i < NQ; i++) fl[i * fmax + lf] = rhs[i];
 		if (lf + NT < nf) cur = nxt;
