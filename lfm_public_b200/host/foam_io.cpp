@@ -853,20 +853,34 @@ std::vector<double> readVolField(const std::string& path, int nCells, int nComp)
 }
 
 void writeVolField(const std::string& path, const std::string& name, const PolyMesh& m, const std::vector<double>& values,
-                   int nComp, int precision) {
-	FILE* f = fopen(path.c_str(), "w");
+                   int nComp, int precision, bool binary) {
+	// binary: OpenFOAM's binary stream format (controlDict writeFormat binary): the list contents are raw doubles
+	FILE* f = fopen(path.c_str(), binary ? "wb" : "w");
 	if (!f) fail("cannot write " + path);
-	writeHeader(f, nComp == 1 ? "volScalarField" : "volVectorField", name.c_str(), nullptr);
+	const char* cls = nComp == 1 ? "volScalarField" : "volVectorField";
+	if (binary)
+		fprintf(f, "FoamFile\n{\n    version     2.0;\n    format      binary;\n    arch        \"LSB;label=32;scalar=64\";\n    class       %s;\n    object      %s;\n}\n\n", cls, name.c_str());
+	else
+		writeHeader(f, cls, name.c_str(), nullptr);
 	fprintf(f, "dimensions      [0 0 0 0 0 0 0];\n\n");
 	const size_t n = values.size() / (size_t)nComp;
-	fprintf(f, "internalField   nonuniform List<%s> \n%zu\n(\n", nComp == 1 ? "scalar" : "vector", n);
-	for (size_t c = 0; c < n; c++) {
-		if (nComp == 1)
-			fprintf(f, "%.*g\n", precision, values[c]);
-		else
-			fprintf(f, "(%.*g %.*g %.*g)\n", precision, values[c * 3], precision, values[c * 3 + 1], precision, values[c * 3 + 2]);
+	if (binary) {
+		fprintf(f, "internalField   nonuniform List<%s> \n%zu\n(", nComp == 1 ? "scalar" : "vector", n);
+		if (!values.empty() && fwrite(values.data(), sizeof(double), values.size(), f) != values.size()) {
+			fclose(f);
+			fail("short write on " + path);
+		}
+		fprintf(f, ")\n;\n\nboundaryField\n{\n");
+	} else {
+		fprintf(f, "internalField   nonuniform List<%s> \n%zu\n(\n", nComp == 1 ? "scalar" : "vector", n);
+		for (size_t c = 0; c < n; c++) {
+			if (nComp == 1)
+				fprintf(f, "%.*g\n", precision, values[c]);
+			else
+				fprintf(f, "(%.*g %.*g %.*g)\n", precision, values[c * 3], precision, values[c * 3 + 1], precision, values[c * 3 + 2]);
+		}
+		fprintf(f, ")\n;\n\nboundaryField\n{\n");
 	}
-	fprintf(f, ")\n;\n\nboundaryField\n{\n");
 	for (const Patch& p : m.patches) {
 		const char* t = "zeroGradient";
 		if (p.type == "empty") t = "empty";

@@ -117,7 +117,7 @@ void writePolyMesh(const PolyMesh& m, const std::string& meshDir);
 std::vector<double> readVolField(const std::string& path, int nCells, int nComp);
 // Writes a field with zeroGradient patches (empty patches get "empty", processor/cyclic their own type).
 void writeVolField(const std::string& path, const std::string& name, const PolyMesh& m,
-                   const std::vector<double>& values, int nComp, int precision = 17);
+                   const std::vector<double>& values, int nComp, int precision = 17, bool binary = false);
 
 std::string timeName(double t, int precision = 12);   // OpenFOAM "general" time formatting
 

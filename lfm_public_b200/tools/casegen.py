@@ -17,7 +17,7 @@ DEFAULTS = dict(
     haveAverage=False, haveForces=False, haveResiduals=True, saveForcesStep=1, printInfoFreq=1,
     tStartAverage=0.0,
     startTime=0.0, endTime=1.0, deltaT=1e-3, writeInterval=1000000, adjustTimeStep=False, maxCo=1.0,
-    solver=0, dimension=2, rkOrder=5, minmodExists=False,
+    solver=0, dimension=2, rkOrder=5, minmodExists=False, writeFormat="ascii",
     pinf=1.0, Tinf=1.0, Uinf=(0.2, 0.0, 0.0), Ls=0.0, M=0.2,
     Cp=2.5, molWeight=11640.3, mu=0.0018667, Pr=0.75, simulationType="laminar",
 )
@@ -44,7 +44,7 @@ def write_dicts(case_dir, **kw):
         f.write("        saveResiduals   false;\n        saveBlendFactor false;\n        saveRank        false;\n    }\n}\n\n")
         f.write(f"startFrom       startTime;\nstartTime       {o['startTime']!r};\nstopAt          endTime;\n")
         f.write(f"endTime         {o['endTime']!r};\ndeltaT          {o['deltaT']!r};\nwriteControl    timeStep;\n")
-        f.write(f"writeInterval   {o['writeInterval']};\npurgeWrite      0;\nwriteFormat     ascii;\nwritePrecision  17;\n")
+        f.write(f"writeInterval   {o['writeInterval']};\npurgeWrite      0;\nwriteFormat     {o['writeFormat']};\nwritePrecision  17;\n")
         f.write("timeFormat      general;\ntimePrecision   12;\n")
         f.write(f"adjustTimeStep  {'yes' if o['adjustTimeStep'] else 'no'};\nmaxCo           {o['maxCo']!r};\n")
     with open(os.path.join(case_dir, "system", "fvSchemes"), "w") as f:

@@ -40,6 +40,7 @@ struct ShimTime {
 	int writeInterval = 1;
 	bool adjust = false;
 	int timePrecision = 12, writePrecision = 17;
+	bool writeBinary = false;      // controlDict writeFormat binary (the reference's 3D cases)
 	ShimMesh* mesh = nullptr;
 	std::string timeName() const { return lfm::timeName(value, timePrecision); }
 };
@@ -167,6 +168,7 @@ CRunTimeManagerOF::CRunTimeManagerOF(const int nRank) {
 		t->timePrecision = (int)cd.scalarOr("timePrecision", 6);
 		const char* wp = getenv("LFM_WRITE_PRECISION");
 		t->writePrecision = wp ? atoi(wp) : (int)cd.scalarOr("writePrecision", 6);
+		t->writeBinary = cd.wordOr("writeFormat", "ascii") == "binary";
 	} catch (const std::exception& e) {
 		fatal(e.what());
 	}
@@ -208,7 +210,7 @@ void CRunTimeManagerOF::writeResults() {
 	std::string dir = t->caseDir + "/" + t->timeName();
 	mkdir(dir.c_str(), 0777);
 	for (ShimField* f : t->mesh->fields)
-		lfm::writeVolField(dir + "/" + f->name, f->name, t->mesh->mesh, f->v, f->nComp, t->writePrecision);
+		lfm::writeVolField(dir + "/" + f->name, f->name, t->mesh->mesh, f->v, f->nComp, t->writePrecision, t->writeBinary);
 }
 
 // =================================================================================================

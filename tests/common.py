@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import os
+import re
 import shutil
 import struct
 import subprocess
@@ -132,7 +133,17 @@ def run_reference(case_dir, o, sp=False, dump=True, timeout=600):
 
 
 def read_field(path, ncomp=1):
-    s = open(path).read()
+    raw = open(path, "rb").read()
+    head = raw[:raw.index(b"}") + 1]
+    if b"binary" in head:                               # OpenFOAM binary stream format: N( raw doubles )
+        i = raw.index(b"internalField")
+        m = re.search(rb"(\d+)\s*\(", raw[i:])
+        n = int(m.group(1))
+        a0 = i + m.end()
+        a = np.frombuffer(raw[a0:a0 + 8 * n * ncomp], dtype="<f8").copy()
+        assert raw[a0 + 8 * n * ncomp:a0 + 8 * n * ncomp + 1] == b")"
+        return a.reshape(-1, ncomp) if ncomp > 1 else a
+    s = raw.decode()
     i = s.index("internalField")
     j = s.index("boundaryField")
     body = s[s.index("(", i) + 1:s.rindex(")", i, j)]

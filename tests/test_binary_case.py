@@ -59,3 +59,20 @@ def test_reference_binary_reads_binary_case(name, tmp_path):
         assert ra["rho"].std() > 0
         for k in ("rho", "U", "E", "p"):
             assert np.array_equal(ra[k], rb[k]), k
+
+
+@pytest.mark.skipif(not common.have_ref(), reason="reference binary not built")
+def test_write_format_binary(tmp_path):
+    """controlDict `writeFormat binary` (the setting of the reference's 3D cases): the time directory is written in the binary
+    stream format and holds exactly the doubles of the 17-digit ASCII run."""
+    a_dir, b_dir = str(tmp_path / "ascii"), str(tmp_path / "binary")
+    m, o = common.build_case("hex3d_m2_p4", a_dir)
+    common.build_case("hex3d_m2_p4", b_dir, writeFormat="binary")
+    common.run_reference(a_dir, o, dump=False)
+    common.run_reference(b_dir, o, dump=False)
+    t = o["deltaT"] * common.N_STEPS
+    assert b"format      binary" in open(f"{b_dir}/processor0/{common.time_name(t)}/rho", "rb").read(200)
+    qa, qb = common.read_reference_q(a_dir, o, t, 3), common.read_reference_q(b_dir, o, t, 3)
+    for ra, rb in zip(qa, qb):
+        for k in ("rho", "U", "E", "p"):
+            assert np.array_equal(ra[k], rb[k]), k
