@@ -152,6 +152,12 @@ int lfmgpu_allreduce(lfmgpu_t h, double* values, int n, int op);
  * (fvSchemes lfm/minmodExists, mesh_solver.cpp:537-548, 582-594; lfmgpu_step's minmod argument sets it too). */
 int lfmgpu_set_option(lfmgpu_t h, const char* name, int value);
 
+/* Host-only check of the tile plan lfmgpu_create would build for this rank (no device needed): partition, halo lists, face
+ * tables, local gather lists and shared-memory strides are verified against the descriptor; tile_cells / smem_limit_bytes
+ * <= 0 take the defaults (128 cells, 227 KB).  stats[8]: tileable, tiles, max staged cells, max faces per tile,
+ * incoming/own faces, halo cells per cell, stage-kernel shared memory (bytes), cells per tile after halving. */
+int lfmgpu_plan_check(const lfmgpu_desc* desc, int tile_cells, int smem_limit_bytes, double* stats);
+
 /* ---- data movement --------------------------------------------------------------------------------- */
 int lfmgpu_download(lfmgpu_t h, int field, void* dst, size_t dst_bytes);   /* blocking                 */
 int lfmgpu_upload_q(lfmgpu_t h, const void* q, size_t bytes);              /* [n_cells][D+2], blocking */

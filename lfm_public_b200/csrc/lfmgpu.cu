@@ -810,13 +810,22 @@ template <class R, int D> int tile_geo(lfmgpu_ctx* h) {
 // tile-ordered face list (own faces grouped by rank among the owner's faces, then the incoming faces) and the
 // tile-local indices the kernels use.  Returns 0 with plan.ready == false when the mesh does not fit the
 // shared-memory budget even with the smallest tile (the unfused kernels serve it then).
-int tile_plan_build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
+// The host half of the plan: everything the tile kernels index with, built from the flattened rank alone (no device), so
+// that it can be checked on a machine without a GPU (lfmgpu_plan_check, tests/test_tile_plan.py).
+struct HostPlan {
+	bool ok = false;                   // false: not tileable within the budget (the unfused kernels serve the rank)
+	std::vector<TileDesc> tiles;
+	std::vector<int> halo_cell, f_gface;
+	std::vector<uint32_t> f_idx;
+	std::vector<int16_t> csr_local;
+	int TCs[LFMGPU_MAX_SUBMESH] = {0};
+};
+
+int tile_plan_host(lfmgpu_ctx* h, const lfmgpu_desc* ds, int dev_smem, HostPlan& hp) {
 	TilePlan& p = h->tiles;
-	p.ready = false;
+	hp.ok = false;
 	const int nc = h->n_cells, nf = h->n_faces, F = h->F, D = h->D;
 	if (nc == 0) return 0;
-	int dev_smem = 0;
-	CU(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
 	const size_t budget = std::min<size_t>((size_t)dev_smem, (size_t)h->tile_smem_budget);
 	const size_t es = (size_t)h->prec;
 	const int NS = (D == 3 ? StagedLayout<3>::NS : StagedLayout<2>::NS), NQ = h->NQ;
@@ -836,10 +845,10 @@ int tile_plan_build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
 	for (int f = 0; f < nf; f++) cfs[(size_t)ds->face_owner[f] + 1]++;
 	for (int c = 0; c < nc; c++) cfs[(size_t)c + 1] += cfs[(size_t)c];
 
-	std::vector<TileDesc> tiles;
-	std::vector<int> halo_cell, f_gface;
-	std::vector<uint32_t> f_idx;
-	std::vector<int16_t> csr_local;
+	std::vector<TileDesc>& tiles = hp.tiles;
+	std::vector<int>&halo_cell = hp.halo_cell, &f_gface = hp.f_gface;
+	std::vector<uint32_t>& f_idx = hp.f_idx;
+	std::vector<int16_t>& csr_local = hp.csr_local;
 	std::vector<int> stamp((size_t)h->n_tot, -1), local_of((size_t)h->n_tot, 0);
 	std::vector<int> own_pos, inc_rank((size_t)nc, 0);
 	std::vector<std::pair<int, int>> inc_sorted;   // (mesh face, tile-local index) of the tile's incoming faces
@@ -847,7 +856,7 @@ int tile_plan_build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
 		int rank, ln, f;
 	};
 	std::vector<Inc> inc;
-	int TCs[LFMGPU_MAX_SUBMESH];
+	int* TCs = hp.TCs;
 	for (int s = 0; s < LFMGPU_MAX_SUBMESH; s++) TCs[s] = h->tile_cells;
 	int probe_id = -1;
 	for (;;) {
@@ -1015,6 +1024,27 @@ int tile_plan_build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
 		if (failed_sub < 0 || TCs[failed_sub] <= 16) return 0;   // not tileable within the budget: unfused kernels
 		TCs[failed_sub] /= 2;
 	}
+	hp.ok = true;
+	return 0;
+}
+
+int tile_plan_build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
+	TilePlan& p = h->tiles;
+	p.ready = false;
+	const int D = h->D;
+	if (h->n_cells == 0) return 0;
+	int dev_smem = 0;
+	CU(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+	HostPlan hp;
+	TRY(tile_plan_host(h, ds, dev_smem, hp));
+	if (!hp.ok) return 0;
+	std::vector<TileDesc>& tiles = hp.tiles;
+	std::vector<int>&halo_cell = hp.halo_cell, &f_gface = hp.f_gface;
+	std::vector<uint32_t>& f_idx = hp.f_idx;
+	std::vector<int16_t>& csr_local = hp.csr_local;
+	const int* TCs = hp.TCs;
+	const size_t es = (size_t)h->prec;
+	const int NS = (D == 3 ? StagedLayout<3>::NS : StagedLayout<2>::NS), NQ = h->NQ;
 	if (getenv("LFMGPU_PLAN_STATS")) {
 		for (int sb = 0; sb < h->n_sub; sb++) {
 			std::vector<int> a, b, c;
@@ -1197,28 +1227,8 @@ int steps_all(lfmgpu_ctx** hs, int n, int scheme, double dt, int n_steps, int fi
 	return 0;
 }
 
-}  // namespace
-
-// ======================================================================================================
-// C ABI
-// ======================================================================================================
-extern "C" {
-
-const char* lfmgpu_last_error(void) { return g_err.c_str(); }
-
-int lfmgpu_device_count(int* n) {
-	CU(cudaGetDeviceCount(n));
-	return 0;
-}
-
-int lfmgpu_create(const lfmgpu_desc* ds, int device, lfmgpu_t* out) {
-	if (!ds || !out) return fail("lfmgpu_create: null argument");
-	if (ds->precision != 4 && ds->precision != 8) return fail("lfmgpu_create: precision must be 4 or 8");
-	if (ds->dim != 2 && ds->dim != 3) return fail("lfmgpu_create: dim must be 2 or 3");
-	if (ds->n_sub < 1 || ds->n_sub > LFMGPU_MAX_SUBMESH) return fail("lfmgpu_create: bad submesh count");
-	CU(cudaSetDevice(device));
-	lfmgpu_ctx* h = new lfmgpu_ctx();
-	h->device = device;
+// sizes and index ranges of the rank, as the descriptor gives them (no device work)
+int ctx_from_desc(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
 	h->prec = ds->precision;
 	h->D = ds->dim;
 	h->NQ = ds->dim + 2;
@@ -1242,10 +1252,36 @@ int lfmgpu_create(const lfmgpu_desc* ds, int device, lfmgpu_t* out) {
 	if (ds->n_nbr) {
 		h->send_start.assign(ds->send_start, ds->send_start + ds->n_nbr + 1);
 		h->recv_start.assign(ds->recv_start, ds->recv_start + ds->n_nbr + 1);
-		if (h->recv_start[(size_t)ds->n_nbr] != ds->n_mpi_ghosts) {
-			delete h;
-			return fail("lfmgpu_create: recv_start does not cover n_mpi_ghosts");
-		}
+		if (h->recv_start[(size_t)ds->n_nbr] != ds->n_mpi_ghosts) return fail("lfmgpu_create: recv_start does not cover n_mpi_ghosts");
+	}
+	return 0;
+}
+
+}  // namespace
+
+// ======================================================================================================
+// C ABI
+// ======================================================================================================
+extern "C" {
+
+const char* lfmgpu_last_error(void) { return g_err.c_str(); }
+
+int lfmgpu_device_count(int* n) {
+	CU(cudaGetDeviceCount(n));
+	return 0;
+}
+
+int lfmgpu_create(const lfmgpu_desc* ds, int device, lfmgpu_t* out) {
+	if (!ds || !out) return fail("lfmgpu_create: null argument");
+	if (ds->precision != 4 && ds->precision != 8) return fail("lfmgpu_create: precision must be 4 or 8");
+	if (ds->dim != 2 && ds->dim != 3) return fail("lfmgpu_create: dim must be 2 or 3");
+	if (ds->n_sub < 1 || ds->n_sub > LFMGPU_MAX_SUBMESH) return fail("lfmgpu_create: bad submesh count");
+	CU(cudaSetDevice(device));
+	lfmgpu_ctx* h = new lfmgpu_ctx();
+	h->device = device;
+	if (ctx_from_desc(h, ds)) {
+		delete h;
+		return 1;
 	}
 	int lo, hi;
 	cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -1275,6 +1311,129 @@ int lfmgpu_create(const lfmgpu_desc* ds, int device, lfmgpu_t* out) {
 		return rc;
 	}
 	*out = h;
+	return 0;
+}
+
+// ---- host-only check of the tile plan (no device) ----------------------------------------------------
+// Builds the host half of the plan exactly as lfmgpu_create does and verifies what the tile kernels rely on: the tiles
+// partition the cells without straddling a submesh; a tile's halo is sorted, disjoint from the tile and entirely used; its
+// face table holds every face owned by a tile cell (owner / neighbour staged indices and the physical-ghost flag right)
+// followed by every incoming face; the local gather lists name, slot by slot in ascending mesh-face order, the table
+// entry of the same mesh face with the same sign; the shared-memory strides cover every tile and fit the budget.
+// stats[8]: tileable, tiles, max staged cells, max faces, incoming/own faces, halo cells per cell, stage-kernel shared
+// memory in bytes, cells per tile requested after halving.
+int lfmgpu_plan_check(const lfmgpu_desc* ds, int tile_cells, int smem_limit_bytes, double* stats) {
+	if (!ds || !stats) return fail("lfmgpu_plan_check: null argument");
+	if (ds->precision != 4 && ds->precision != 8) return fail("lfmgpu_plan_check: precision must be 4 or 8");
+	if (ds->dim != 2 && ds->dim != 3) return fail("lfmgpu_plan_check: dim must be 2 or 3");
+	if (ds->n_sub < 1 || ds->n_sub > LFMGPU_MAX_SUBMESH) return fail("lfmgpu_plan_check: bad submesh count");
+	for (int i = 0; i < 8; i++) stats[i] = 0.0;
+	lfmgpu_ctx ctx;
+	lfmgpu_ctx* h = &ctx;
+	TRY(ctx_from_desc(h, ds));
+	if (tile_cells > 0) h->tile_cells = std::max(16, tile_cells);
+	HostPlan hp;
+	TRY(tile_plan_host(h, ds, smem_limit_bytes > 0 ? smem_limit_bytes : 227 * 1024, hp));
+	if (!hp.ok) return 0;
+	const TilePlan& p = h->tiles;
+	const int nc = h->n_cells, F = h->F, D = h->D;
+	const int NS = (D == 3 ? StagedLayout<3>::NS : StagedLayout<2>::NS);
+	auto bad = [](const char* what, int tile) { return fail("tile plan check: %s (tile %d)", what, tile); };
+	int next = 0, smax_all = 0, fmax_all = 0;
+	long long own = 0, incoming = 0, halo = 0;
+	std::vector<int> row((size_t)F), used;
+	for (int s = 0; s < h->n_sub; s++) {
+		if (p.sub_tile_start[s] > p.sub_tile_start[s + 1]) return bad("submesh tile ranges out of order", p.sub_tile_start[s]);
+		if (p.sub_smax[s] % 4 || p.sub_fmax[s] % 4) return bad("strides not multiples of 4", p.sub_tile_start[s]);
+		if (((size_t)NS * p.sub_smax[s] + (size_t)h->NQ * p.sub_fmax[s]) * (size_t)h->prec > (size_t)h->tile_smem_budget) return bad("shared memory over the budget", p.sub_tile_start[s]);
+		for (int t = p.sub_tile_start[s]; t < p.sub_tile_start[s + 1]; t++) {
+			const TileDesc& td = hp.tiles[(size_t)t];
+			const int c0 = td.c0, c1 = td.c0 + td.nt;
+			if (c0 != next || td.nt < 1) return bad("tiles do not tile the cells", t);
+			next = c1;
+			if (c0 < h->sub_cell_start[s] || c1 > h->sub_cell_start[s + 1]) return bad("tile straddles a submesh", t);
+			if (td.nt + td.nh > p.sub_smax[s] || td.nfo + td.ninc > p.sub_fmax[s]) return bad("tile larger than the strides of its launch", t);
+			const int* hc = hp.halo_cell.data() + td.halo_off;
+			for (int i = 0; i < td.nh; i++) {
+				if (i && hc[i] <= hc[i - 1]) return bad("halo not strictly ascending", t);
+				if (hc[i] >= c0 && hc[i] < c1) return bad("halo cell inside the tile", t);
+				if (hc[i] < 0 || hc[i] >= h->n_tot) return bad("halo cell out of range", t);
+			}
+			used.assign((size_t)td.nh, 0);
+			auto cell_of = [&](int staged) { return staged < td.nt ? c0 + staged : hc[staged - td.nt]; };
+			int n_own = 0;
+			for (int c = c0; c < c1; c++)
+				for (int k = 0; k < F; k++) n_own += ds->cell_slot_face[(size_t)c * F + k] > 0 ? 1 : 0;
+			if (n_own != td.nfo) return bad("own-face count differs from the faces the tile's cells own", t);
+			for (int j = 0; j < td.nfo + td.ninc; j++) {
+				const int f = hp.f_gface[(size_t)td.f_off + j];
+				const uint32_t idx = hp.f_idx[(size_t)td.f_off + j];
+				const int lo = (int)(idx & 0xffffu), ln = (int)((idx >> 16) & 0x7fffu);
+				const bool ghost = (idx >> 31) != 0;
+				if (f < 0 || f >= h->n_faces || lo >= td.nt + td.nh || ln >= td.nt + td.nh) return bad("face table entry out of range", t);
+				if (cell_of(lo) != ds->face_owner[f] || cell_of(ln) != ds->face_neigh[f]) return bad("staged owner/neighbour of a table face is not the mesh's", t);
+				const int n = ds->face_neigh[f];
+				if (ghost != (n >= nc && n < nc + h->n_bc)) return bad("physical-ghost flag wrong", t);
+				if (j < td.nfo) {
+					if (lo >= td.nt) return bad("own face whose owner is outside the tile", t);
+				} else {
+					if (lo < td.nt || ln >= td.nt || ghost) return bad("incoming face not from a halo cell into the tile", t);
+				}
+				if (lo >= td.nt) used[(size_t)(lo - td.nt)] = 1;
+				if (ln >= td.nt) used[(size_t)(ln - td.nt)] = 1;
+			}
+			for (int i = 0; i < td.nh; i++)
+				if (!used[(size_t)i]) return bad("halo cell no face refers to", t);
+			int n_inc = 0;
+			for (int c = c0; c < c1; c++) {
+				int n = 0;
+				for (int k = 0; k < F; k++) {
+					const int e = ds->cell_slot_face[(size_t)c * F + k];
+					if (e) row[(size_t)n++] = e;
+				}
+				std::sort(row.begin(), row.begin() + n, [](int a, int b) { return std::abs(a) < std::abs(b); });
+				for (int k = 0; k < F; k++) {
+					const int l = hp.csr_local[(size_t)k * nc + c];
+					if (k >= n) {
+						if (l) return bad("gather list longer than the cell's face list", t);
+						continue;
+					}
+					const int e = row[(size_t)k], lf = std::abs(l) - 1;
+					if (!l || (l > 0) != (e > 0) || lf >= td.nfo + td.ninc) return bad("gather entry missing, of the wrong sign or out of range", t);
+					if (hp.f_gface[(size_t)td.f_off + lf] != std::abs(e) - 1) return bad("gather entry names another mesh face", t);
+					if (e < 0) {
+						const int o = ds->face_owner[std::abs(e) - 1];
+						if (o < c0 || o >= c1) {
+							n_inc++;
+							if (lf < td.nfo) return bad("incoming face filed among the own faces", t);
+						} else if (lf >= td.nfo) {
+							return bad("own face filed among the incoming faces", t);
+						}
+					}
+				}
+			}
+			if (n_inc != td.ninc) return bad("incoming-face count differs from the gather lists", t);
+			smax_all = std::max(smax_all, td.nt + td.nh);
+			fmax_all = std::max(fmax_all, td.nfo + td.ninc);
+			own += td.nfo;
+			incoming += td.ninc;
+			halo += td.nh;
+		}
+	}
+	if (next != nc || p.sub_tile_start[h->n_sub] != (int)hp.tiles.size()) return bad("tiles do not cover the cells", (int)hp.tiles.size());
+	int smax = 0, fmax = 0;
+	for (int s = 0; s < h->n_sub; s++) {
+		smax = std::max(smax, p.sub_smax[s]);
+		fmax = std::max(fmax, p.sub_fmax[s]);
+	}
+	stats[0] = 1.0;
+	stats[1] = (double)hp.tiles.size();
+	stats[2] = smax_all;
+	stats[3] = fmax_all;
+	stats[4] = own ? (double)incoming / (double)own : 0.0;
+	stats[5] = (double)halo / (double)nc;
+	stats[6] = (double)(((size_t)NS * smax + (size_t)h->NQ * fmax) * (size_t)h->prec);
+	stats[7] = hp.TCs[h->n_sub - 1];
 	return 0;
 }
 

@@ -24,7 +24,7 @@ SYMBOLS = [
     "lfmgpu_prepare_timestep", "lfmgpu_prepare_rkstep", "lfmgpu_set_bc", "lfmgpu_gradients", "lfmgpu_gradients_m2ausm", "lfmgpu_vis", "lfmgpu_vis_smagorinsky",
     "lfmgpu_rk_stage", "lfmgpu_halo_start", "lfmgpu_halo_wait", "lfmgpu_cfl", "lfmgpu_dt", "lfmgpu_average",
     "lfmgpu_forces", "lfmgpu_residual", "lfmgpu_step", "lfmgpu_warmup", "lfmgpu_step_multi", "lfmgpu_allreduce",
-    "lfmgpu_set_option", "lfmgpu_download", "lfmgpu_upload_q", "lfmgpu_upload_q_soa_async", "lfmgpu_download_q_soa_async",
+    "lfmgpu_set_option", "lfmgpu_plan_check", "lfmgpu_download", "lfmgpu_upload_q", "lfmgpu_upload_q_soa_async", "lfmgpu_download_q_soa_async",
     "lfmgpu_pipe_in_start", "lfmgpu_pipe_in_commit", "lfmgpu_pipe_out_start", "lfmgpu_pipe_out_fetch",
     "lfmgpu_host_alloc", "lfmgpu_host_free", "lfmgpu_nccl_unique_id", "lfmgpu_comm_init_nccl", "lfmgpu_comm_init_local",
     "lfmgpu_halo_send_count", "lfmgpu_download_send_buffer", "lfmgpu_halo_pack_to_host", "lfmgpu_halo_unpack_from_host", "lfmgpu_launch_count", "lfmgpu_enable_kernel_timing",
@@ -48,7 +48,7 @@ def lib():
             "lfmgpu_dt": [vp, d, C.POINTER(d)], "lfmgpu_average": [vp, i], "lfmgpu_forces": [vp, i, vp, vp],
             "lfmgpu_residual": [vp, vp], "lfmgpu_step": [vp, i, d, i, i, i], "lfmgpu_warmup": [vp],
             "lfmgpu_step_multi": [vp, i, i, d, i, i, i], "lfmgpu_allreduce": [vp, vp, i, i],
-            "lfmgpu_set_option": [vp, C.c_char_p, i], "lfmgpu_download": [vp, i, vp, sz], "lfmgpu_upload_q": [vp, vp, sz],
+            "lfmgpu_set_option": [vp, C.c_char_p, i], "lfmgpu_plan_check": [vp, i, i, vp], "lfmgpu_download": [vp, i, vp, sz], "lfmgpu_upload_q": [vp, vp, sz],
             "lfmgpu_upload_q_soa_async": [vp, vp, sz], "lfmgpu_download_q_soa_async": [vp, vp, sz],
             "lfmgpu_pipe_in_start": [vp, vp, sz], "lfmgpu_pipe_in_commit": [vp], "lfmgpu_pipe_out_start": [vp],
             "lfmgpu_pipe_out_fetch": [vp, vp, sz],
@@ -96,6 +96,14 @@ class PinnedArray:
             self.array = None
             lib().lfmgpu_host_free(C.c_void_p(self.ptr))
             self.ptr = None
+
+
+def plan_check(case, tile_cells=0, smem_limit_bytes=0):
+    """Host-only verification of the tile plan of a finished host_api.Case (no GPU needed); returns the plan statistics."""
+    st = np.zeros(8)
+    _check(lib().lfmgpu_plan_check(C.cast(case.desc_ptr, C.c_void_p), int(tile_cells), int(smem_limit_bytes), st.ctypes.data))
+    return dict(tileable=bool(st[0]), n_tiles=int(st[1]), max_staged=int(st[2]), max_faces=int(st[3]), halo_face_ratio=float(st[4]),
+                halo_cell_ratio=float(st[5]), smem_bytes=int(st[6]), tile_cells=int(st[7]))
 
 
 class GpuSolver:
