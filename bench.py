@@ -78,8 +78,10 @@ def block_fields(m, n, blocks, rank):
     return dict(p=p, T=T, U=U, alpha=alpha), h
 
 
-def build_rank_case(n, blocks, rank, n_ranks, precision, scheme, tile=None, brick_order="morton"):
-    m = meshgen.hex_block((n, n, n), blocks, rank, tile=tile, brick_order=brick_order)
+def build_rank_case(n, blocks, rank, n_ranks, precision, scheme, tile=None, brick_order="morton", z_cyclic=None):
+    # z_cyclic=None: z periodic while there is one block in z, walls otherwise; True: periodic for every block layout (the
+    # cut periodic plane becomes processorCyclic patches)
+    m = meshgen.hex_block((n, n, n), blocks, rank, tile=tile, brick_order=brick_order, z_cyclic=z_cyclic)
     fields, h = block_fields(m, (n, n, n), blocks, rank)
     if "new_of_old" in m:                                  # fields were built in lexicographic order: renumber them too
         perm = m["new_of_old"]
@@ -224,7 +226,8 @@ def workload_config(args, n_gpus):
     n = args.n
     bl = BLOCKS[n_gpus]
     return {"workload": f"synthetic 3D hex polyMesh weak scaling, {n}^3 = {n ** 3} cells per GPU, blocks {bl[0]}x{bl[1]}x{bl[2]} "
-                        f"({n ** 3 * n_gpus} cells), {'M2' if args.scheme == 1 else 'M1'} + laminar viscous + sponge, RK5, commType 2",
+                        f"({n ** 3 * n_gpus} cells), {'M2' if args.scheme == 1 else 'M1'} + laminar viscous + sponge, RK5, commType 2"
+                        + (", z periodic (processorCyclic)" if getattr(args, "z_cyclic", False) and bl[2] > 1 else ""),
             "cell_numbering": f"bricks {args.tile}, {args.brick_order} brick order", "cells_per_gpu": n ** 3, "total_cells": n ** 3 * n_gpus, "rk_stages_per_step": 5,
             "l2_policy": "inputs larger than L2 (about 7 GB of state per GPU at 256^3), no flush"}
 
@@ -252,7 +255,8 @@ def run_gpu_arm(args):
     blocks = BLOCKS[world]
     t0 = time.time()
     tile = tuple(int(x) for x in args.tile.split(",")) if args.tile and args.tile != "none" else None
-    case, dt = build_rank_case(args.n, blocks, rank, world, args.precision, args.scheme, tile, args.brick_order)
+    case, dt = build_rank_case(args.n, blocks, rank, world, args.precision, args.scheme, tile, args.brick_order,
+                               z_cyclic=True if args.z_cyclic else None)
     if world > 1:
         host_api.exchange_distributed(case, rank)
     else:
@@ -420,6 +424,7 @@ def main():
     ap.add_argument("--ref-n", type=int, default=64, help="cells per side of the CPU sample")
     ap.add_argument("--ref-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--z-cyclic", action="store_true", help="keep z periodic when the block layout cuts it (8 GPUs: processorCyclic patches); default: walls there")
     args = ap.parse_args()
     if args.gpus not in BLOCKS:
         raise SystemExit("--gpus must be 1, 2, 4 or 8")

@@ -53,6 +53,7 @@ typedef struct lfmhost_mesh_in {
 	const int32_t* patch_nbr_proc;
 	const int32_t* face_proc_addressing;/* [n_faces] or NULL                                */
 	const int32_t* cell_submesh;        /* [n_cells] or NULL                                */
+	const char* const* patch_refer_name;/* processorCyclic referPatch ("" otherwise), or NULL */
 } lfmhost_mesh_in;
 
 const char* lfmhost_last_error(void);

@@ -69,4 +69,5 @@ class MeshIn(C.Structure):
         ("patch_nbr_name", C.POINTER(C.c_char_p)),
         ("patch_my_proc", C.POINTER(C.c_int32)), ("patch_nbr_proc", C.POINTER(C.c_int32)),
         ("face_proc_addressing", C.POINTER(C.c_int32)), ("cell_submesh", C.POINTER(C.c_int32)),
+        ("patch_refer_name", C.POINTER(C.c_char_p)),
     ]

@@ -153,6 +153,7 @@ int lfmhost_case_from_arrays(const lfmhost_mesh_in* in, const lfmhost_opts* opts
 			pt.neighbourPatch = in->patch_nbr_name ? in->patch_nbr_name[b] : "";
 			pt.myProcNo = in->patch_my_proc ? in->patch_my_proc[b] : -1;
 			pt.neighbProcNo = in->patch_nbr_proc ? in->patch_nbr_proc[b] : -1;
+			pt.referPatch = in->patch_refer_name ? in->patch_refer_name[b] : "";
 			m.patches.push_back(pt);
 		}
 		if (in->face_proc_addressing) m.faceProcAddressing.assign(in->face_proc_addressing, in->face_proc_addressing + in->n_faces);

@@ -96,6 +96,7 @@ class Case:
         names = (C.c_char_p * n)(*[p["name"].encode() for p in P])
         types = (C.c_char_p * n)(*[p["type"].encode() for p in P])
         nbrn = (C.c_char_p * n)(*[p.get("neighbourPatch", "").encode() for p in P])
+        refn = (C.c_char_p * n)(*[p.get("referPatch", "").encode() for p in P])
         nf = np.asarray([p["nFaces"] for p in P], dtype=np.int32)
         st = np.asarray([p["startFace"] for p in P], dtype=np.int32)
         myp = np.asarray([p.get("myProcNo", -1) for p in P], dtype=np.int32)
@@ -106,7 +107,7 @@ class Case:
         mi = MeshIn(len(pts), pts.ctypes.data_as(C.POINTER(C.c_double)), len(faces), faces.ctypes.data_as(i32p),
                     owner.ctypes.data_as(i32p), len(nei), nei.ctypes.data_as(i32p), int(m["nCells"]), n, names, types,
                     nf.ctypes.data_as(i32p), st.ctypes.data_as(i32p), nbrn, myp.ctypes.data_as(i32p), nbp.ctypes.data_as(i32p),
-                    fpa.ctypes.data_as(i32p) if fpa is not None else None, csm.ctypes.data_as(i32p) if csm is not None else None)
+                    fpa.ctypes.data_as(i32p) if fpa is not None else None, csm.ctypes.data_as(i32p) if csm is not None else None, refn)
         p = np.ascontiguousarray(fields["p"], dtype=np.float64)
         T = np.ascontiguousarray(fields["T"], dtype=np.float64)
         U = np.ascontiguousarray(fields["U"], dtype=np.float64)

@@ -315,7 +315,8 @@ def hex_block(n, blocks=(1, 1, 1), rank=0, cell_size=None, z_cyclic=None, tile=N
     rank = bi + bx*(bj + by*bk) as in block_assignment().  Physically identical to
     decompose(hex_box(n*blocks), block_assignment)[rank] (same points, same cell order, same patches; the
     processor-face ids are a different but consistent global numbering -- they only serve to match the two sides).
-    z is a cyclic pair when bz == 1 (default), walls otherwise.
+    z is a cyclic pair when bz == 1 (default), walls otherwise; z_cyclic=True with bz > 1 keeps the span periodic: the bottom
+    plane of the lowest blocks and the top plane of the highest become `processorCyclic` patches (as in decompose()).
     tile=(ti,tj,tk): number the cells brick by brick (blocked_order, aligned with the interior submesh); the
     permutation is returned as m["new_of_old"] (fields given in lexicographic order must be permuted with it)."""
     nx, ny, nz = n
@@ -326,7 +327,6 @@ def hex_block(n, blocks=(1, 1, 1), rank=0, cell_size=None, z_cyclic=None, tile=N
         cell_size = (1.0 / GX, 1.0 / GX, 1.0 / GX)
     if z_cyclic is None:
         z_cyclic = bz == 1
-    assert not (z_cyclic and bz > 1)
     L = (cell_size[0] * GX, cell_size[1] * GY, cell_size[2] * GZ)
     faces, a, b, side, _ = _structured(nx, ny, nz)
     xs = (L[0] * np.linspace(0.0, 1.0, GX + 1))[bi * nx:(bi + 1) * nx + 1]
@@ -351,6 +351,17 @@ def hex_block(n, blocks=(1, 1, 1), rank=0, cell_size=None, z_cyclic=None, tile=N
     for r in proc_ranks:
         patch_defs.append(dict(name=f"procBoundary{rank}to{r}", type="processor", myProcNo=rank, neighbProcNo=r))
     side_patch = [phys[s] if nbr[s] < 0 else n_phys + proc_ranks.index(nbr[s]) for s in range(6)]
+    if z_cyclic and bz > 1:
+        # the periodic pair is cut by the decomposition: the cyclic patches stay (empty) and their faces move to
+        # processorCyclic patches towards the rank that holds the twin plane
+        through = []
+        if bk == 0:
+            through.append((rk(bi, bj, bz - 1), "periodic_m", 4))
+        if bk == bz - 1:
+            through.append((rk(bi, bj, 0), "periodic_p", 5))
+        for r, ref, s_ in sorted(through):
+            side_patch[s_] = len(patch_defs)
+            patch_defs.append(dict(name=f"procBoundary{rank}to{r}through{ref}", type="processorCyclic", myProcNo=rank, neighbProcNo=r, referPatch=ref))
     # a global id for every boundary face of the block (unique per geometric face, the same on both ranks)
     nf = len(side)
     n_i, n_j = (nx + 1) * ny * nz, nx * (ny + 1) * nz

@@ -36,3 +36,40 @@ def test_decomposed_periodic_run_equals_serial(name, tmp_path):
             if "through" in line:
                 assert line.strip().startswith(f"procBoundary{r}to") and line.strip().split("through")[1] in ("periodic_m", "periodic_p")
     assert n_pc == len(ranks)        # one processorCyclic patch per rank: its half of the cut periodic plane
+
+
+def test_per_rank_generator_keeps_the_span_periodic(tmp_path):
+    """meshgen.hex_block (the weak-scaling bench's per-rank generator) with z_cyclic=True and two blocks in z writes the same
+    processorCyclic patches as decompose() of the global periodic box: rank by rank the flattened descriptors are identical,
+    and so are the fields after the run."""
+    from lfm_public_b200 import defs
+    from lfm_public_b200.tools import casegen, meshgen
+    n, blocks = (4, 4, 3), (2, 2, 2)
+    G = tuple(a * b for a, b in zip(n, blocks))
+    size = 1.0 / G[0]
+    glob = meshgen.hex_box(*G, lengths=(G[0] * size, G[1] * size, G[2] * size), z_cyclic=True)
+    parts = meshgen.decompose(glob, meshgen.block_assignment(glob, blocks))
+    opts = host_api.default_opts(solver=1, dimension=3, delta_t=1e-3, Ls=0.1, mu0=7.17948717948718e-05, mach=0.2, comm_type=2)
+    fields_g = casegen.synthetic_fields(glob, meshgen.cell_centres_estimate(glob))
+    a_cases, b_cases = [], []
+    for r in range(8):
+        mb = meshgen.hex_block(n, blocks, r, z_cyclic=True)
+        ma = parts[r]
+        assert [(p["name"], p["type"], p["nFaces"]) for p in ma["patches"]] == [(p["name"], p["type"], p["nFaces"]) for p in mb["patches"]]
+        assert sum(p["type"] == "processorCyclic" for p in mb["patches"]) == 1
+        f = {k: np.asarray(v)[ma["cellProcAddressing"]] for k, v in fields_g.items()}
+        f["alpha"] = np.ones(ma["nCells"])
+        a_cases.append(host_api.Case.from_mesh(ma, opts, f, r, 8))
+        b_cases.append(host_api.Case.from_mesh(mb, opts, f, r, 8))
+    host_api.exchange_in_process(a_cases)
+    host_api.exchange_in_process(b_cases)
+    for ca, cb in zip(a_cases, b_cases):
+        xa, xb = ca.arrays(), cb.arrays()
+        for k in xa:
+            assert np.array_equal(np.asarray(xa[k]), np.asarray(xb[k])), k
+    oa, ob = [oracle_lib.Oracle(c) for c in a_cases], [oracle_lib.Oracle(c) for c in b_cases]
+    oracle_lib.run(oa, 1, 1e-3, 3)
+    oracle_lib.run(ob, 1, 1e-3, 3)
+    for x, y in zip(oa, ob):
+        q = x.download(defs.FIELD_Q)
+        assert np.isfinite(q).all() and np.array_equal(q, y.download(defs.FIELD_Q))
