@@ -67,7 +67,7 @@ def test_halo_messages_bit_exact(name, tmp_path):
 
 @needs_ref
 @pytest.mark.skipif(not common.have_ref(sp=True), reason="single-precision reference not built")
-@pytest.mark.parametrize("name", ["quad2d_m1", "hex3d_m2_p4", "tri2d_m2"])
+@pytest.mark.parametrize("name", ["quad2d_m1", "hex3d_m2_p4", "tri2d_m2", "hex3d_ausm_p4", "ogrid2d_ausm", "hex3d_m2_les_p4", "hex3d_m2_pc8"])
 def test_fields_match_reference_fp32(name, tmp_path):
     case_dir, o, cases, oracles = _run_pair(name, tmp_path, sp=True)
     oracle_lib.run(oracles, o["solver"], o["deltaT"], N_STEPS)
