@@ -154,8 +154,9 @@ int lfmgpu_set_option(lfmgpu_t h, const char* name, int value);
 
 /* Host-only check of the tile plan lfmgpu_create would build for this rank (no device needed): partition, halo lists, face
  * tables, local gather lists and shared-memory strides are verified against the descriptor; tile_cells / smem_limit_bytes
- * <= 0 take the defaults (128 cells, 227 KB).  stats[8]: tileable, tiles, max staged cells, max faces per tile,
- * incoming/own faces, halo cells per cell, stage-kernel shared memory (bytes), cells per tile after halving. */
+ * <= 0 take the defaults (128 cells, 227 KB).  stats[10]: tileable, tiles, max staged cells, max faces per tile,
+ * incoming/own faces, halo cells per cell, stage-kernel shared memory (bytes), cells per tile after halving, mean halo
+ * cells per tile, mean runs of consecutive ids per halo list. */
 int lfmgpu_plan_check(const lfmgpu_desc* desc, int tile_cells, int smem_limit_bytes, double* stats);
 
 /* ---- data movement --------------------------------------------------------------------------------- */

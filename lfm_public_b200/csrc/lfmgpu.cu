@@ -1320,14 +1320,15 @@ int lfmgpu_create(const lfmgpu_desc* ds, int device, lfmgpu_t* out) {
 // face table holds every face owned by a tile cell (owner / neighbour staged indices and the physical-ghost flag right)
 // followed by every incoming face; the local gather lists name, slot by slot in ascending mesh-face order, the table
 // entry of the same mesh face with the same sign; the shared-memory strides cover every tile and fit the budget.
-// stats[8]: tileable, tiles, max staged cells, max faces, incoming/own faces, halo cells per cell, stage-kernel shared
-// memory in bytes, cells per tile requested after halving.
+// stats[10]: tileable, tiles, max staged cells, max faces, incoming/own faces, halo cells per cell, stage-kernel shared
+// memory in bytes, cells per tile requested after halving, mean halo cells per tile, mean runs of consecutive cell ids per
+// tile's halo list (what a run-wise copy would issue per staged row instead of one copy per halo cell).
 int lfmgpu_plan_check(const lfmgpu_desc* ds, int tile_cells, int smem_limit_bytes, double* stats) {
 	if (!ds || !stats) return fail("lfmgpu_plan_check: null argument");
 	if (ds->precision != 4 && ds->precision != 8) return fail("lfmgpu_plan_check: precision must be 4 or 8");
 	if (ds->dim != 2 && ds->dim != 3) return fail("lfmgpu_plan_check: dim must be 2 or 3");
 	if (ds->n_sub < 1 || ds->n_sub > LFMGPU_MAX_SUBMESH) return fail("lfmgpu_plan_check: bad submesh count");
-	for (int i = 0; i < 8; i++) stats[i] = 0.0;
+	for (int i = 0; i < 10; i++) stats[i] = 0.0;
 	lfmgpu_ctx ctx;
 	lfmgpu_ctx* h = &ctx;
 	TRY(ctx_from_desc(h, ds));
@@ -1340,7 +1341,7 @@ int lfmgpu_plan_check(const lfmgpu_desc* ds, int tile_cells, int smem_limit_byte
 	const int NS = (D == 3 ? StagedLayout<3>::NS : StagedLayout<2>::NS);
 	auto bad = [](const char* what, int tile) { return fail("tile plan check: %s (tile %d)", what, tile); };
 	int next = 0, smax_all = 0, fmax_all = 0;
-	long long own = 0, incoming = 0, halo = 0;
+	long long own = 0, incoming = 0, halo = 0, halo_runs = 0;
 	std::vector<int> row((size_t)F), used;
 	for (int s = 0; s < h->n_sub; s++) {
 		if (p.sub_tile_start[s] > p.sub_tile_start[s + 1]) return bad("submesh tile ranges out of order", p.sub_tile_start[s]);
@@ -1358,6 +1359,7 @@ int lfmgpu_plan_check(const lfmgpu_desc* ds, int tile_cells, int smem_limit_byte
 				if (i && hc[i] <= hc[i - 1]) return bad("halo not strictly ascending", t);
 				if (hc[i] >= c0 && hc[i] < c1) return bad("halo cell inside the tile", t);
 				if (hc[i] < 0 || hc[i] >= h->n_tot) return bad("halo cell out of range", t);
+				if (!i || hc[i] != hc[i - 1] + 1) halo_runs++;
 			}
 			used.assign((size_t)td.nh, 0);
 			auto cell_of = [&](int staged) { return staged < td.nt ? c0 + staged : hc[staged - td.nt]; };
@@ -1434,6 +1436,8 @@ int lfmgpu_plan_check(const lfmgpu_desc* ds, int tile_cells, int smem_limit_byte
 	stats[5] = (double)halo / (double)nc;
 	stats[6] = (double)(((size_t)NS * smax + (size_t)h->NQ * fmax) * (size_t)h->prec);
 	stats[7] = hp.TCs[h->n_sub - 1];
+	stats[8] = (double)halo / (double)hp.tiles.size();
+	stats[9] = (double)halo_runs / (double)hp.tiles.size();
 	return 0;
 }
 

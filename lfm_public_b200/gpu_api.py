@@ -100,10 +100,10 @@ class PinnedArray:
 
 def plan_check(case, tile_cells=0, smem_limit_bytes=0):
     """Host-only verification of the tile plan of a finished host_api.Case (no GPU needed); returns the plan statistics."""
-    st = np.zeros(8)
+    st = np.zeros(10)
     _check(lib().lfmgpu_plan_check(C.cast(case.desc_ptr, C.c_void_p), int(tile_cells), int(smem_limit_bytes), st.ctypes.data))
     return dict(tileable=bool(st[0]), n_tiles=int(st[1]), max_staged=int(st[2]), max_faces=int(st[3]), halo_face_ratio=float(st[4]),
-                halo_cell_ratio=float(st[5]), smem_bytes=int(st[6]), tile_cells=int(st[7]))
+                halo_cell_ratio=float(st[5]), smem_bytes=int(st[6]), tile_cells=int(st[7]), halo_per_tile=float(st[8]), halo_runs_per_tile=float(st[9]))
 
 
 class GpuSolver:
