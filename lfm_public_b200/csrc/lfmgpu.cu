@@ -598,6 +598,7 @@ template <class R> TileView<R> tile_view(lfmgpu_ctx* h, int smax, int fmax) {
 	v.fSmag = (const R*)p.d_fSmag;
 	v.T = p.T;
 	v.csr_local = p.d_csr_local;
+	v.staged_cell = p.d_staged_cell;
 	v.smax = smax;
 	v.fmax = fmax;
 	return v;
@@ -761,6 +762,13 @@ template <class R, int D, int SCHEME> int tile_stage_s(lfmgpu_ctx* h, int sub, R
 	switch (h->stage_cfg) {
 		case 1: LFM_STAGE_CFG(128, 4) break;
 		case 6: LFM_STAGE_CFG(256, 2) break;
+		case 7:   // 256 x 2 with the EARLY copy-in (needs the staged-cell table: compile-time strides only)
+			if (fixed && h->tiles.d_staged_cell) {
+				const int nt_ = 256;
+				LFM_STAGE_LAUNCH(256, 2, kFixedSmax, kFixedFmax, 0, 1)
+			} else
+				LFM_STAGE_CFG(256, 2)
+			break;
 		case 12: LFM_STAGE_CFG(512, 1) break;
 		default: LFM_STAGE_CFG(256, 3) break;
 	}
@@ -1079,6 +1087,17 @@ int tile_plan_build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
 	TRY(upload<int>(h, &p.d_f_gface, f_gface.data(), f_gface.size()));
 	TRY(upload<uint32_t>(h, &p.d_f_idx, f_idx.data(), f_idx.size()));
 	TRY(upload<int16_t>(h, &p.d_csr_local, csr_local.data(), csr_local.size()));
+	p.d_staged_cell = nullptr;
+	if (h->stage_cfg == 7 && all_fixed(h)) {   // experiment (DESIGN.md 9 a'): fixed-pitch staged-cell table for the EARLY stage kernel
+		std::vector<int> staged((size_t)tiles.size() * kFixedSmax, -1);
+		for (size_t t = 0; t < tiles.size(); t++) {
+			const TileDesc& td = tiles[t];
+			int* row = &staged[t * kFixedSmax];
+			for (int i = 0; i < td.nt; i++) row[i] = td.c0 + i;
+			for (int i = 0; i < td.nh; i++) row[td.nt + i] = halo_cell[(size_t)td.halo_off + i];
+		}
+		TRY(upload<int>(h, &p.d_staged_cell, staged.data(), staged.size()));
+	}
 	TRY(h->prec == 8 ? (D == 3 ? tile_geo<double, 3>(h) : tile_geo<double, 2>(h)) : (D == 3 ? tile_geo<float, 3>(h) : tile_geo<float, 2>(h)));
 	p.ready = true;
 	return 0;

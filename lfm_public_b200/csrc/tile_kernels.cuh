@@ -53,6 +53,8 @@ template <class R> struct TileView {
 	size_t T;                        // stride of the face tables
 	const int16_t* csr_local;        // [F][n_cells] +-(tile-local face index + 1), ascending mesh face id, 0-padded
 	int smax, fmax;                  // shared-memory strides of this launch (staged cells, faces)
+	const int* staged_cell;          // [n_tiles][kFixedSmax] global cell id of every staged slot (own cells, then halo; -1 padding):
+	                                 // lets a CTA issue its copies without waiting for its descriptor (EARLY kernels); may be null
 };
 
 // per-face constants (make_geo) computed once on the device with the same expressions the flux loops use
@@ -381,7 +383,9 @@ __device__ __forceinline__ void gather_update(const DevMesh<R>& m, const TileVie
 }
 
 // EXTRA: rows staged on top of StagedLayout::NS -- 0 none, 1 tauMC (Smagorinsky closure), 2 the minmod gradients of solver 2 (M2-AUSM)
-template <class R, int D, int SCHEME, int NT, int MINB, int SMAX = 0, int FMAX = 0, int EXTRA = 0>
+// EARLY (compile-time strides only): the staged cell ids come from the fixed-pitch table tv.staged_cell, so the copies are
+// two dependent round trips away from the kernel's start (ids, data) instead of three (descriptor, halo ids, data).
+template <class R, int D, int SCHEME, int NT, int MINB, int SMAX = 0, int FMAX = 0, int EXTRA = 0, int EARLY = 0>
 __global__ void __launch_bounds__(NT, MINB)
     k_tile_stage(DevMesh<R> m, TileView<R> tv, const R* __restrict__ q, const R* __restrict__ drv, R* __restrict__ qn, R* __restrict__ drvn, int tile0, R dt, R Ak, R Bk, int first, int res) {
 	using L = StagedLayout<D>;
@@ -391,13 +395,20 @@ __global__ void __launch_bounds__(NT, MINB)
 	const int smax = SMAX ? SMAX : tv.smax, fmax = FMAX ? FMAX : tv.fmax;
 	R* st = reinterpret_cast<R*>(smem_raw);      // [NS (+D*D)][smax]
 	R* fl = st + (size_t)L::rows(EXTRA) * smax;   // [NQ][fmax]
+	static_assert(!EARLY || SMAX > 0, "the staged-cell table has the pitch of the compile-time strides");
 	const TileDesc td = tv.tiles[tile0 + blockIdx.x];
-	const int ns = td.nt + td.nh;
+	const int ns = EARLY ? SMAX : td.nt + td.nh;
 	const int nf = td.nfo + td.ninc;
 
 	// ---- A: request the cell states (asynchronous copies, no registers) ----------------------------------
 	for (int i = threadIdx.x; i < ns; i += NT) {
-		const int x = i < td.nt ? td.c0 + i : tv.halo_cell[td.halo_off + i - td.nt];
+		int x;
+		if (EARLY) {
+			x = tv.staged_cell[(size_t)(tile0 + blockIdx.x) * SMAX + i];
+			if (x < 0) continue;
+		} else {
+			x = i < td.nt ? td.c0 + i : tv.halo_cell[td.halo_off + i - td.nt];
+		}
 #pragma unroll
 		for (int k = 0; k < NQ; k++) cp_async_elem(st + k * smax + i, q + (size_t)k * m.ncs + x);
 #pragma unroll
@@ -712,6 +723,7 @@ struct TilePlan {
 	uint32_t* d_f_idx = nullptr;
 	int* d_f_gface = nullptr;
 	int16_t* d_csr_local = nullptr;
+	int* d_staged_cell = nullptr;     // [n_tiles][kFixedSmax], only when every tile fits the compile-time strides
 	void *d_fS = nullptr, *d_fK = nullptr, *d_fw = nullptr, *d_fdm = nullptr, *d_fdi = nullptr, *d_fSmag = nullptr;
 };
 

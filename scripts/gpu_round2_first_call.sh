@@ -9,7 +9,10 @@ mkdir -p gpurun_out
 LFM_FULL_SIZE_TESTS=1 timeout 900 python -m pytest tests/test_zz_large.py -m gpu -q > gpurun_out/${TAG}_full_size_parity.log 2>&1; tail -3 gpurun_out/${TAG}_full_size_parity.log
 # 2. solver 2 in fp32 (is the AUSM stage still arithmetic-bound there?) next to fp64
 for P in 8 4; do timeout 120 python -m lfm_public_b200.tools.tune --n 128 --scheme 2 --minmod --precision $P --steps 3; done > gpurun_out/${TAG}_ausm_fp64_fp32.log 2>&1; tail -2 gpurun_out/${TAG}_ausm_fp64_fp32.log
-# 3. where the stage kernel waits: full ncu capture with source-level stall sampling of 4 launches at 128^3
+# 3. the EARLY copy-in variant (DESIGN.md 9 a'): parity first, then its time next to the default
+LFMGPU_STAGE_CFG=7 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "bit_exact_fp64 or medium" > gpurun_out/${TAG}_early_parity.log 2>&1; tail -2 gpurun_out/${TAG}_early_parity.log
+timeout 200 python -m lfm_public_b200.tools.tune --n 128 --steps 5 --set LFMGPU_STAGE_CFG=6,7 > gpurun_out/${TAG}_early_tune.log 2>&1; tail -2 gpurun_out/${TAG}_early_tune.log
+# 4. where the stage kernel waits: full ncu capture with source-level stall sampling of 4 launches at 128^3
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_tile_stage -s 10 -c 4 -o gpurun_out/${TAG}_stage128 \
 	python -m lfm_public_b200.tools.tune --n 128 --steps 1 > gpurun_out/${TAG}_ncu.log 2>&1; tail -2 gpurun_out/${TAG}_ncu.log
 # read here with:
