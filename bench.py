@@ -154,38 +154,55 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------
 # reference CPU arm: the reference's own solver binary on a bounded sample of the workload
 # ----------------------------------------------------------------------------------------------------------
-def reference_run(n_sample, n_ranks, steps, scheme, precision, keep_dir=None):
-    """Runs oracle/_ref/lfm_solve_ref[_sp] (the reference's unmodified src/*.cpp) on an n_sample^3 hex box split into
-    n_ranks blocks (mini-MPI shim: one forked process per rank) and returns cell-stages/s from the reference's own
-    `Rk Loop` timer (src/mesh_solver.cpp:906-919)."""
+REF_BLOCKS = {1: None, 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2), 16: (4, 2, 2), 32: (4, 4, 2), 64: (4, 4, 4)}
+
+
+def reference_case(tmp, n_sample, n_ranks, scheme, precision):
+    """Writes the reference's input (an OpenFOAM case: n_sample^3 hex box in the mesh generator's lexicographic numbering,
+    decomposed into n_ranks blocks, the bench workload's dictionaries and fields) into `tmp`; returns (dt, block layout)."""
+    blocks = REF_BLOCKS[n_ranks]
+    m = meshgen.hex_box(n_sample, n_sample, n_sample, lengths=(1.0, 1.0, 1.0), z_cyclic=(blocks is None or blocks[2] == 1))
+    h = 1.0 / n_sample
+    dt = 0.5 * h / 1.2
+    cr = meshgen.block_assignment(m, blocks) if blocks else None
+    fields, _ = block_fields(m, (n_sample, n_sample, n_sample), (1, 1, 1), 0)
+    casegen.write_case(tmp, m, fields=fields, cell_rank=cr, solver=scheme, dimension=3, deltaT=dt, endTime=dt,
+                       writeInterval=10 ** 7, Ls=0.15, mu=MU, haveResiduals=False, printInfoFreq=10 ** 6,
+                       doublePrecision=(precision == 8), commType=2)
+    return dt, blocks
+
+
+def reference_exec(tmp, dt, n_sample, n_ranks, steps, precision):
+    """Runs oracle/_ref/lfm_solve_ref[_sp] (the reference's unmodified src/*.cpp over the mini-MPI shim: one forked process per
+    rank) for `steps` time steps on the case in `tmp`; cell-stages/s from the reference's own `Rk Loop` timer
+    (src/mesh_solver.cpp:906-919)."""
     exe = REF_BIN if precision == 8 else REF_BIN_SP
     if not os.path.exists(exe):
         raise RuntimeError(f"{exe} missing (built by `make -C oracle ref` where /root/reference exists)")
-    blocks = {1: None, 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2), 16: (4, 2, 2), 32: (4, 4, 2), 64: (4, 4, 4)}[n_ranks]
-    tmp = keep_dir or tempfile.mkdtemp(prefix="lfm_ref_")
+    casegen.set_end_time(tmp, dt * steps)
+    env = dict(os.environ)
+    args = [exe]
+    if REF_BLOCKS[n_ranks] is not None:
+        env["LFM_MPI_NP"] = str(n_ranks)
+        args.append("-p")
+    out = subprocess.run(args, cwd=tmp, env=env, capture_output=True, text=True, timeout=1800)
+    if "Simulation finished successfully" not in out.stdout:
+        raise RuntimeError("reference run failed: " + out.stdout[-1500:] + out.stderr[-1500:])
+    rk = float(re.search(r"\[\s*([0-9.eE+-]+)\]: Rk Loop", out.stdout).group(1))
+    return dict(cells=n_sample ** 3, steps=steps, rk_loop_s=rk, value=n_sample ** 3 * 5 * steps / rk)
+
+
+def reference_run(n_sample, n_ranks, steps, scheme, precision, warm_steps=0):
+    """One bounded sample of the workload through the reference binary: case written once, optional untimed warm-up run
+    (page cache, binary), then the timed run."""
+    tmp = tempfile.mkdtemp(prefix="lfm_ref_")
     try:
-        m = meshgen.hex_box(n_sample, n_sample, n_sample, lengths=(1.0, 1.0, 1.0), z_cyclic=(blocks is None or blocks[2] == 1))
-        h = 1.0 / n_sample
-        dt = 0.5 * h / 1.2
-        cr = meshgen.block_assignment(m, blocks) if blocks else None
-        nx = n_sample
-        fields, _ = block_fields(m, (nx, nx, nx), (1, 1, 1), 0)
-        casegen.write_case(tmp, m, fields=fields, cell_rank=cr, solver=scheme, dimension=3, deltaT=dt, endTime=dt * steps,
-                           writeInterval=10 ** 7, Ls=0.15, mu=MU, haveResiduals=False, printInfoFreq=10 ** 6,
-                           doublePrecision=(precision == 8), commType=2)
-        env = dict(os.environ)
-        args = [exe]
-        if cr is not None:
-            env["LFM_MPI_NP"] = str(n_ranks)
-            args.append("-p")
-        out = subprocess.run(args, cwd=tmp, env=env, capture_output=True, text=True, timeout=1800)
-        if "Simulation finished successfully" not in out.stdout:
-            raise RuntimeError("reference run failed: " + out.stdout[-1500:] + out.stderr[-1500:])
-        rk = float(re.search(r"\[\s*([0-9.eE+-]+)\]: Rk Loop", out.stdout).group(1))
-        return dict(cells=n_sample ** 3, steps=steps, rk_loop_s=rk, value=n_sample ** 3 * 5 * steps / rk)
+        dt, _ = reference_case(tmp, n_sample, n_ranks, scheme, precision)
+        if warm_steps > 0:
+            reference_exec(tmp, dt, n_sample, n_ranks, warm_steps, precision)
+        return reference_exec(tmp, dt, n_sample, n_ranks, steps, precision)
     finally:
-        if not keep_dir:
-            shutil.rmtree(tmp, ignore_errors=True)
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 def pick_cpu_ranks():
@@ -201,25 +218,54 @@ def run_reference_arm(args):
     if rank != 0:
         return
     ranks, cores = pick_cpu_ranks()
-    n_sample = args.ref_n
+    n_sample = args.ref_arm_n
     steps = max(1, args.steps)
-    if args.warmup > 0:
-        reference_run(n_sample, ranks, max(1, min(args.warmup, 2)), args.scheme, args.precision)   # page-cache / binary warm-up
-    r = reference_run(n_sample, ranks, steps, args.scheme, args.precision)
+    r = reference_run(n_sample, ranks, steps, args.scheme, args.precision, warm_steps=max(0, min(args.warmup, 2)))
     ms = 1e3 * r["rk_loop_s"] / steps
+    bl = REF_BLOCKS[ranks] or (1, 1, 1)
     sample = (f"{n_sample}^3 hex box ({r['cells']} cells) in {ranks} blocks, {steps} time steps x 5 RK stages, reference binary "
               f"oracle/_ref/lfm_solve_ref over the mini-MPI shim (one process per rank), reference's own 'Rk Loop' timer")
+    # a second, smaller sample shows how the CPU figure depends on the mesh size (cache residency vs halo share)
+    small = None
+    if args.ref_n != n_sample:
+        try:
+            rs = reference_run(args.ref_n, ranks, max(steps, args.ref_steps), args.scheme, args.precision)
+            small = {"value": rs["value"], "sample": f"{args.ref_n}^3 hex box ({rs['cells']} cells) in {ranks} blocks, {rs['steps']} steps"}
+        except Exception as e:
+            small = {"value": None, "sample": f"failed: {e}"[:200]}
+    cfg = workload_config(args, args.gpus)
+    # this line's workload is the mesh the CPU arm actually advanced: a bounded sample of the GPU arm's workload (same
+    # scheme, dictionaries, fields and RK5; smaller box, lexicographic numbering, one block per host core)
+    cfg["workload"] = (f"bounded CPU sample of the GPU arm's workload: synthetic 3D hex polyMesh {n_sample}^3 = {n_sample ** 3} cells in "
+                       f"{bl[0]}x{bl[1]}x{bl[2]} blocks (one per host core used), {'M2' if args.scheme == 1 else 'M1'} + laminar viscous + "
+                       f"sponge, RK5, commType 2; GPU arm: {args.n}^3 cells per GPU")
+    cfg["cell_numbering"] = "lexicographic (mesh generator order), decomposed into blocks"
+    cfg["cells_per_gpu"] = None
+    cfg["total_cells"] = n_sample ** 3
+    cfg["l2_policy"] = "n/a (CPU)"
     line = {
         "impl": "reference", "metric": "cell-updates/s per RK stage", "value": r["value"], "unit": "cell-updates/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.precision == 8 else "f32", "data": "synthetic",
-        "config": workload_config(args, args.gpus),
+        "config": cfg,
         "cpu_baseline": {"value": r["value"], "unit": "cell-updates/s", "cores": ranks, "kind": "reference", "sample": sample,
-                         "host_cores": cores},
+                         "host_cores": cores, "smaller_sample": small,
+                         "caveat": "the ranks talk through the in-tree mini-MPI shim (forked processes, AF_UNIX sockets), not a tuned MPI; "
+                                   "the sample is smaller than one GPU's block"},
         "e2e": {"value": r["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def numbering_of(args):
+    """(tile argument of meshgen.hex_block, description) of the cell numbering the bench mesh is generated in."""
+    if args.numbering == "lex":
+        return None, "lexicographic (the mesh generator's order, no renumbering)"
+    if args.numbering == "morton":
+        return "morton", "Z-order curve through the cell centres == `python -m lfm_public_b200.tools.renumber --method morton` on this block"
+    tile = tuple(int(x) for x in args.tile.split(","))
+    return tile, f"bricks {args.tile} aligned with the interior submesh, {args.brick_order} brick order (hand-fitted to the 128-cell tiles)"
 
 
 def workload_config(args, n_gpus):
@@ -227,14 +273,92 @@ def workload_config(args, n_gpus):
     bl = BLOCKS[n_gpus]
     return {"workload": f"synthetic 3D hex polyMesh weak scaling, {n}^3 = {n ** 3} cells per GPU, blocks {bl[0]}x{bl[1]}x{bl[2]} "
                         f"({n ** 3 * n_gpus} cells), {'M2' if args.scheme == 1 else 'M1'} + laminar viscous + sponge, RK5, commType 2"
-                        + (", z periodic (processorCyclic)" if getattr(args, "z_cyclic", False) and bl[2] > 1 else ""),
-            "cell_numbering": f"bricks {args.tile}, {args.brick_order} brick order", "cells_per_gpu": n ** 3, "total_cells": n ** 3 * n_gpus, "rk_stages_per_step": 5,
+                        + (", z periodic (processorCyclic)" if not getattr(args, "z_walls", False) and bl[2] > 1 else ""),
+            "cell_numbering": numbering_of(args)[1], "cells_per_gpu": n ** 3, "total_cells": n ** 3 * n_gpus, "rk_stages_per_step": 5,
             "l2_policy": "inputs larger than L2 (about 7 GB of state per GPU at 256^3), no flush"}
 
 
 # ----------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------
+def quick_measure(n, precision, scheme, tile, brick_order, steps, device=0):
+    """Device-resident throughput of one single-rank block (sub-records of the N = 1 line): ms per step, cell-updates/s,
+    per-kernel times and the two roofline fractions, on a freshly built case."""
+    from lfm_public_b200 import gpu_api
+    case, dt = build_rank_case(n, (1, 1, 1), 0, 1, precision, scheme, tile, brick_order)
+    case.finish()
+    g = gpu_api.GpuSolver(case, device)
+    try:
+        g.warmup()
+        g.step(scheme, dt, 3)
+        g.sync()
+        g.event_record(0)
+        g.step(scheme, dt, steps)
+        g.event_record(1)
+        g.sync()
+        ms = g.event_elapsed_ms(0, 1) / steps
+        g.enable_kernel_timing(True)
+        g.step(scheme, dt, 2)
+        g.sync()
+        kt = {}
+        for name in ("tile_stage", "tile_grad"):
+            t, nl = g.kernel_time(name)
+            if nl:
+                kt[name] = t / 2
+        g.enable_kernel_timing(False)
+        peak, _ = measured_peak()
+        Gb, Fb = b_alg(g.D, precision, 3.0)
+        nc = g.n_cells
+        out = {"cells": nc, "ms_per_step": ms, "value": nc * 5 / (ms * 1e-3), "kernel_ms_per_step": kt,
+               "stage_frac": (Gb + Fb) * nc * 5 / (ms * 1e-3) / 1e9 / peak, "tiles": g.tile_info()}
+        if "tile_stage" in kt:
+            out["frac"] = Fb * nc * 5 / (kt["tile_stage"] * 1e-3) / 1e9 / peak
+        return out
+    finally:
+        g.close()
+        case.close()
+
+
+def nccl_parity_check(args, dist, rank, world, local_rank, n=24, steps=3):
+    """Outside the timed region, N > 1 only: a small block case (n^3 cells per rank, the bench workload's layout and
+    dictionaries) advanced `steps` time steps (a) on this rank's GPU with the halo exchange over NCCL and (b) by the CPU
+    restatement of the reference (oracle/, the checker) for ALL ranks in lockstep inside this process.  Conservatives and
+    ghost states of this rank must be bit-identical (fp64; fp32: relative 1e-5).  Returns (ok, sha256 of q on the GPU)."""
+    import hashlib
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    from lfm_public_b200 import gpu_api
+    blocks = BLOCKS[world]
+    z_cyc = None if args.z_walls else True
+    cases = []
+    for r in range(world):
+        c, dt = build_rank_case(n, blocks, r, world, args.precision, args.scheme, "morton", args.brick_order, z_cyclic=z_cyc)
+        cases.append(c)
+    host_api.exchange_in_process(cases)
+    oracles = [oracle_lib.Oracle(c) for c in cases]
+    oracle_lib.run(oracles, args.scheme, dt, steps, first=True)
+    want_q, want_g = oracles[rank].download(0), oracles[rank].download(7)
+    g = gpu_api.GpuSolver(cases[rank], local_rank)
+    ids = [gpu_api.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    g.comm_init_nccl(ids[0], rank, world)
+    g.warmup()
+    g.step(args.scheme, dt, steps)
+    g.sync()
+    got_q, got_g = g.download(0), g.download(7)
+    if args.precision == 8:
+        ok = bool(np.array_equal(got_q, want_q) and np.array_equal(got_g, want_g))
+    else:
+        ok = bool(np.abs(got_q - want_q).max() <= 1e-5 * np.abs(want_q).max())
+    digest = hashlib.sha256(np.ascontiguousarray(got_q).tobytes()).hexdigest()
+    g.close()
+    for o in oracles:
+        o.close()
+    for c in cases:
+        c.close()
+    return ok, digest
+
+
 def run_gpu_arm(args):
     from lfm_public_b200 import gpu_api
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -253,10 +377,19 @@ def run_gpu_arm(args):
     if gpu_api.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
     blocks = BLOCKS[world]
+    parity_nccl = None
+    if world > 1 and not args.no_parity:
+        ok, digest = nccl_parity_check(args, dist, rank, world, local_rank)
+        import torch
+        t = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        parity_nccl = bool(t.item() == 1.0)
+        if not ok:
+            print(f"bench.py: rank {rank}: NCCL-exchanged run differs from the oracle (sha256 of q {digest})", file=sys.stderr, flush=True)
     t0 = time.time()
-    tile = tuple(int(x) for x in args.tile.split(",")) if args.tile and args.tile != "none" else None
-    case, dt = build_rank_case(args.n, blocks, rank, world, args.precision, args.scheme, tile, args.brick_order,
-                               z_cyclic=True if args.z_cyclic else None)
+    tile = numbering_of(args)[0]
+    z_cyc = None if args.z_walls else True          # z stays periodic in every block layout (processorCyclic at 2x2x2)
+    case, dt = build_rank_case(args.n, blocks, rank, world, args.precision, args.scheme, tile, args.brick_order, z_cyclic=z_cyc)
     if world > 1:
         host_api.exchange_distributed(case, rank)
     else:
@@ -344,6 +477,7 @@ def run_gpu_arm(args):
     for p_ in pin_in + pin_out:
         p_.free()
 
+    tile_info = g.tile_info()
     total_cells = n_cells * world if dist is None else int(max_over_ranks(float(n_cells))) * world
     ms_step = ms_total / K
     value = total_cells * 5 / (ms_step * 1e-3)
@@ -354,6 +488,8 @@ def run_gpu_arm(args):
         if dist is not None:
             dist.barrier()
             dist.destroy_process_group()
+        if parity_nccl is False:
+            raise SystemExit(3)
         return
 
     # ---- roofline of the dominant kernel ------------------------------------------------------------------------------
@@ -391,6 +527,27 @@ def run_gpu_arm(args):
         except Exception as e:      # the baseline is reported, never required for the GPU number
             cpu = {"value": None, "unit": "cell-updates/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"[:300]}
 
+    # ---- sub-records of the N = 1 line: the fp32 arm of the sweep and the same block in the other cell numberings ----------
+    extras = None
+    if world == 1 and not args.no_extras:
+        g.close()
+        case.close()
+        g = None
+        extras = {}
+        try:
+            if args.precision == 8:
+                r = quick_measure(args.n, 4, args.scheme, tile, args.brick_order, max(3, min(K, 5)), local_rank)
+                extras["f32"] = dict(r, workload=f"the headline workload in fp32 ({args.n}^3 cells, {numbering_of(args)[0]!r} numbering)")
+            variants = {"morton": "morton", "bricks": tuple(int(x) for x in args.tile.split(",")), "lex": None}
+            ne = args.extras_n
+            extras["numbering"] = {"n": ne, "precision": args.precision,
+                                   "note": f"{ne}^3 cells, same scheme; morton = tools/renumber.py --method morton, bricks = {args.tile} bricks "
+                                           "aligned with the interior submesh (hand-fitted), lex = the generator's order"}
+            for name, tl in variants.items():
+                extras["numbering"][name] = quick_measure(ne, args.precision, args.scheme, tl, args.brick_order, 5, local_rank)
+        except Exception as e:      # sub-records never take the headline down
+            extras["error"] = str(e)[:300]
+
     line = {
         "metric": "cell-updates/s per RK stage", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -400,13 +557,19 @@ def run_gpu_arm(args):
                 "d2h_bytes_per_step": int(NQ * n_cells * s) * world, "ms_per_step": ms_e2e, "finite": e2e_ok,
                 "mode": "pipelined batches: H2D of batch k+1 and D2H of batch k-1 overlap the step of batch k (pinned host buffers)"},
         "gpu_launches": int(launches), "clocks": clk, "finite": finite, "setup_s": t_setup,
-        "tiles": g.tile_info(), "use_tiles": args.use_tiles,
+        "tiles": tile_info, "use_tiles": args.use_tiles, "extra": extras,
     }
+    if parity_nccl is not None:
+        line["parity_nccl"] = parity_nccl
+        line["parity_nccl_case"] = "24^3 cells per rank, the bench layout, 3 time steps over NCCL vs the lockstep CPU oracle, q + ghost states bit-exact"
     print(json.dumps(line), flush=True)
-    g.close()
+    if g is not None:
+        g.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    if parity_nccl is False:
+        raise SystemExit(3)
 
 
 def main():
@@ -421,10 +584,17 @@ def main():
     ap.add_argument("--use-tiles", type=int, default=1)
     ap.add_argument("--tile", default="8,4,4", help="brick numbering of the synthetic mesh (renumberMesh analogue), or 'none'")
     ap.add_argument("--brick-order", default="morton", choices=["lex", "morton"], help="order of the bricks in the numbering")
-    ap.add_argument("--ref-n", type=int, default=64, help="cells per side of the CPU sample")
+    ap.add_argument("--ref-n", type=int, default=64, help="cells per side of the CPU sample timed next to the GPU arm (cpu_baseline)")
+    ap.add_argument("--ref-arm-n", type=int, default=int(os.environ.get("LFM_REF_ARM_N", "128")), help="cells per side of the --impl reference workload")
     ap.add_argument("--ref-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--z-cyclic", action="store_true", help="keep z periodic when the block layout cuts it (8 GPUs: processorCyclic patches); default: walls there")
+    ap.add_argument("--z-walls", action="store_true", help="close z with walls when the block layout cuts it (8 GPUs); default: z stays periodic through processorCyclic patches")
+    ap.add_argument("--numbering", default=os.environ.get("LFM_BENCH_NUMBERING", "morton"), choices=["morton", "bricks", "lex"],
+                    help="cell numbering of the synthetic mesh: morton = what tools/renumber.py --method morton produces (default), "
+                         "bricks = --tile bricks aligned with the interior submesh (hand-fitted), lex = none")
+    ap.add_argument("--no-parity", action="store_true", help="skip the NCCL-transport parity check of the multi-GPU runs")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sub-records (fp32 arm, other numberings) of the N = 1 line")
+    ap.add_argument("--extras-n", type=int, default=128, help="cells per side of the block the numbering variants are timed on")
     args = ap.parse_args()
     if args.gpus not in BLOCKS:
         raise SystemExit("--gpus must be 1, 2, 4 or 8")

@@ -169,6 +169,7 @@ template <class R, int D> __device__ __forceinline__ void make_geo(const R* S, c
 // in registers (unfused kernels) and values staged in shared memory (tile kernels, loaded where they are used to
 // keep the register footprint small).
 template <class R, int D> struct RegSide {
+	static constexpr bool kHasTrace = false;   // the side carries -(tr dudx) precomputed (trace_neg()) instead of forming it per face
 	const CellState<R, D>& s;
 	__device__ __forceinline__ R q(int k) const { return s.q[k]; }
 	__device__ __forceinline__ R rho_inv() const { return s.rho_inv; }
@@ -329,10 +330,15 @@ __device__ __forceinline__ void face_flux(const Consts<R>& k, const SideC& c, co
 	const R dmag_inv = g.dmag_inv;
 	// diagonal part of tauMC of each side: (-tr dudx) * (mu*2/3)
 	R cdiag = ZERO, ndiag = ZERO;
+	if constexpr (SideC::kHasTrace && SideN::kHasTrace) {
+		cdiag = c.trace_neg();   // ((0 - d00) - d11) - d22, formed once per cell by whoever wrote the V record
+		ndiag = n.trace_neg();
+	} else {
 #pragma unroll
-	for (int nD = 0; nD < D; nD++) {
-		cdiag -= c.dudx(nD, nD);
-		ndiag -= n.dudx(nD, nD);
+		for (int nD = 0; nD < D; nD++) {
+			cdiag -= c.dudx(nD, nD);
+			ndiag -= n.dudx(nD, nD);
+		}
 	}
 	cdiag *= k.c_diag;
 	ndiag *= k.c_diag;

@@ -20,8 +20,30 @@
 
 namespace lfm {
 
-// Device view of one rank (all pointers are device pointers).  SoA: component k of cell c lives at
-// base[k * ncs + c]; per-face arrays at base[k * nfs + f].
+// Record layout of the per-cell state the stage kernels stage in shared memory (one contiguous, sector-aligned record
+// per cell, so that a halo cell is one or two long copies instead of one element per staged row):
+//   Q record, QW = 8 values : q[0 .. NQ) conservatives | 1/rho | R*psi | c (M1) or H (M2)      (2D: one value of padding)
+//   V record, VW = 16 / 8   : dudx[D*D] | dTdx[D] | sigmaU[D] | 3D only: tr = ((0 - d00) - d11) - d22 (the diagonal sum the
+//                             flux loops form from dudx before scaling it into tauMC; stored so that a face reads it once)
+// Record sizes in bytes (32, 64 or 128) are the TMA swizzle spans, see stage_pipe.cuh.
+template <int D> struct Rec {
+	static constexpr int NQ = D + 2;
+	static constexpr int QW = 8;
+	static constexpr int VW = D == 3 ? 16 : 8;
+	static constexpr int RHO_INV = NQ, RPSI = NQ + 1, AUX = NQ + 2;
+	static constexpr int DUDX = 0, DTDX = D * D, SIGMAU = D * D + D, TR = D * D + 2 * D;   // TR exists in 3D only
+};
+// tr of a finished dudx (3D): the expression of the flux loops' `diagSum -= dudx[nD][nD]` (cfd_v0.cpp:2716-2720)
+template <class R, int D> __host__ __device__ __forceinline__ R dudx_trace_neg(const R* dudx_rowmajor) {
+	R t = R(0);
+#pragma unroll
+	for (int nD = 0; nD < D; nD++) t -= dudx_rowmajor[nD * D + nD];
+	return t;
+}
+
+// Device view of one rank (all pointers are device pointers).  Per-cell state lives in records (Rec<D>): value k of cell
+// x at base[x * QW + k] / vis[x * VW + k]; the other per-cell arrays are SoA (base[k * n_cells + c]), per-face arrays
+// base[k * nfs + f].
 template <class R> struct DevMesh {
 	int n_cells, n_faces, n_bc, n_mpi, n_tot, F;
 	size_t ncs, nfs, ngs;              // strides: cells(+ghosts), faces, mpi ghosts
@@ -32,9 +54,7 @@ template <class R> struct DevMesh {
 	const int* slot;                   // [F][n_cells] signed (face+1) in the reference's slot order
 	R* dq;                             // [NQ][n_cells]
 	R* RES;                            // [NQ][n_cells]
-	R* dudx;                           // [D*D][ncs]
-	R* dTdx;                           // [D][ncs]
-	R* sigmaU;                         // [D][ncs]    U.tau of calc_VIS (real cells: k_*grad*; MPI ghosts: as received)
+	R* vis;                            // [ncs][VW]   V records: dudx, dTdx, sigmaU = U.tau of calc_VIS (real cells: k_*grad*; MPI ghosts: as received)
 	R* tauMC;                          // [D*D][ncs]  only with the Smagorinsky closure (laminar: rebuilt from dudx where needed)
 	const R* smag_c;                   // [n_cells]   -2 (Cs Delta)^2 of the cell whose face loop leaves the cell's final tauMC
 	int les;                           // calc_VIS_Smagorinsky instead of calc_VIS
@@ -53,7 +73,7 @@ constexpr int kBlock = 256;
 // The three derived values that travel with the conservatives of a cell (tile kernels copy them instead of
 // recomputing them per staged cell): 1/rho, R*psi (cfdv0_solver.h:252-261) and, per scheme, the speed of sound
 // sqrt(gamma R psi) (M1, cfd_v0.cpp:2600-2603) or the total enthalpy rhoE/rho + R psi (M2, cfd_v0.cpp:1975-1978).
-template <class R, int D> __device__ __forceinline__ void store_derived(const Consts<R>& k, const R* cq, int scheme, R* __restrict__ drv, size_t ncs, size_t x) {
+template <class R, int D> __device__ __forceinline__ void store_derived(const Consts<R>& k, const R* cq, int scheme, R* __restrict__ q, size_t x) {
 	CellState<R, D> s;
 #pragma unroll
 	for (int i = 0; i < D + 2; i++) s.q[i] = cq[i];
@@ -61,22 +81,23 @@ template <class R, int D> __device__ __forceinline__ void store_derived(const Co
 		derive_state<R, D, 0>(k, s);
 	else
 		derive_state<R, D, 1>(k, s);
-	drv[x] = s.rho_inv;
-	drv[ncs + x] = s.Rpsi;
-	drv[2 * ncs + x] = s.aux;
+	R* rec = q + x * Rec<D>::QW;
+	rec[Rec<D>::RHO_INV] = s.rho_inv;
+	rec[Rec<D>::RPSI] = s.Rpsi;
+	rec[Rec<D>::AUX] = s.aux;
 }
 
 // derived values of cells [c0, c1) (after an upload, or when the scheme changes)
-template <class R, int D> __global__ void __launch_bounds__(kBlock) k_derive(DevMesh<R> m, const R* __restrict__ q, R* __restrict__ drv, int c0, int c1, int scheme) {
+template <class R, int D> __global__ void __launch_bounds__(kBlock) k_derive(DevMesh<R> m, R* __restrict__ q, int c0, int c1, int scheme) {
 	const int x = c0 + blockIdx.x * blockDim.x + threadIdx.x;
 	if (x >= c1) return;
 	R cq[D + 2];
 #pragma unroll
-	for (int i = 0; i < D + 2; i++) cq[i] = q[i * m.ncs + x];
-	store_derived<R, D>(m.k, cq, scheme, drv, m.ncs, (size_t)x);
+	for (int i = 0; i < D + 2; i++) cq[i] = q[(size_t)x * Rec<D>::QW + i];
+	store_derived<R, D>(m.k, cq, scheme, q, (size_t)x);
 }
 
-template <class R, int D> __global__ void __launch_bounds__(kBlock) k_set_bc(DevMesh<R> m, R* __restrict__ q, R* __restrict__ drv, int scheme) {
+template <class R, int D> __global__ void __launch_bounds__(kBlock) k_set_bc(DevMesh<R> m, R* __restrict__ q, int scheme) {
 	const int g = blockIdx.x * blockDim.x + threadIdx.x;
 	if (g >= m.n_bc) return;
 	const int b = m.bc_cell[g];
@@ -84,7 +105,7 @@ template <class R, int D> __global__ void __launch_bounds__(kBlock) k_set_bc(Dev
 	const size_t gi = (size_t)m.n_cells + g;
 	R cq[D + 2];
 #pragma unroll
-	for (int i = 0; i < D + 2; i++) cq[i] = q[i * m.ncs + b];
+	for (int i = 0; i < D + 2; i++) cq[i] = q[(size_t)b * Rec<D>::QW + i];
 	R gq[D + 2];
 	if (kind == 1) {          // wall
 		gq[0] = cq[0];
@@ -126,8 +147,21 @@ template <class R, int D> __global__ void __launch_bounds__(kBlock) k_set_bc(Dev
 		return;               // unknown role: the reference leaves the ghost untouched
 	}
 #pragma unroll
-	for (int i = 0; i < D + 2; i++) q[i * m.ncs + gi] = gq[i];
-	store_derived<R, D>(m.k, gq, scheme, drv, m.ncs, gi);
+	for (int i = 0; i < D + 2; i++) q[gi * Rec<D>::QW + i] = gq[i];
+	store_derived<R, D>(m.k, gq, scheme, q, gi);
+}
+
+// writes the V record of cell x (dudx, dTdx, sigmaU and, in 3D, the diagonal sum tr)
+template <class R, int D> __device__ __forceinline__ void store_vis_record(R* __restrict__ vis, size_t x, const R (*dudx)[D], const R* dTdx, const R* sigmaU) {
+	R* rec = vis + x * Rec<D>::VW;
+#pragma unroll
+	for (int i = 0; i < D; i++) {
+#pragma unroll
+		for (int j = 0; j < D; j++) rec[Rec<D>::DUDX + i * D + j] = dudx[i][j];
+		rec[Rec<D>::DTDX + i] = dTdx[i];
+		rec[Rec<D>::SIGMAU + i] = sigmaU[i];
+	}
+	if (D == 3) rec[Rec<D>::TR] = dudx_trace_neg<R, D>(&dudx[0][0]);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -138,7 +172,7 @@ template <class R, int D> __global__ void __launch_bounds__(kBlock) k_grad_cell(
 	if (c >= c1) return;
 	R cq[D + 2], cU[D], c_rho_inv, c_Rpsi, c_T;
 #pragma unroll
-	for (int i = 0; i < D + 2; i++) cq[i] = q[i * m.ncs + c];
+	for (int i = 0; i < D + 2; i++) cq[i] = q[(size_t)c * Rec<D>::QW + i];
 	primitives<R, D>(m.k, cq, c_rho_inv, cU, c_Rpsi, c_T);
 	const R vinv = m.vol_inv[c];
 	R dudx[D][D], dTdx[D];
@@ -156,7 +190,7 @@ template <class R, int D> __global__ void __launch_bounds__(kBlock) k_grad_cell(
 		const int o = own ? m.face_neigh[f] : m.face_owner[f];
 		R oq[D + 2], oU[D], o_rho_inv, o_Rpsi, o_T;
 #pragma unroll
-		for (int i = 0; i < D + 2; i++) oq[i] = q[i * m.ncs + o];
+		for (int i = 0; i < D + 2; i++) oq[i] = q[(size_t)o * Rec<D>::QW + i];
 		primitives<R, D>(m.k, oq, o_rho_inv, oU, o_Rpsi, o_T);
 		const R w = m.w[f];
 		R face_U[D], face_T, sov[D];
@@ -178,13 +212,7 @@ template <class R, int D> __global__ void __launch_bounds__(kBlock) k_grad_cell(
 	}
 	R tauMC[D][D], sigmaU[D];
 	vis_cell_terms<R, D>(m.k, cq, dudx, tauMC, sigmaU);
-#pragma unroll
-	for (int i = 0; i < D; i++) {
-#pragma unroll
-		for (int j = 0; j < D; j++) m.dudx[(size_t)(i * D + j) * m.ncs + c] = dudx[i][j];
-		m.dTdx[(size_t)i * m.ncs + c] = dTdx[i];
-		m.sigmaU[(size_t)i * m.ncs + c] = sigmaU[i];
-	}
+	store_vis_record<R, D>(m.vis, (size_t)c, dudx, dTdx, sigmaU);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -204,7 +232,7 @@ template <class R, int D> __global__ void __launch_bounds__(kBlock) k_grad_ausm(
 	if (c >= c1) return;
 	R cq[D + 2];
 #pragma unroll
-	for (int i = 0; i < D + 2; i++) cq[i] = q[i * m.ncs + c];
+	for (int i = 0; i < D + 2; i++) cq[i] = q[(size_t)c * Rec<D>::QW + i];
 	const R cp = pressure_of<R, D>(m.k, cq);
 	const R vinv = m.vol_inv[c];
 	R g_rho[D], g_p[D], g_U[D][D];
@@ -222,7 +250,7 @@ template <class R, int D> __global__ void __launch_bounds__(kBlock) k_grad_ausm(
 		const int o = own ? m.face_neigh[f] : m.face_owner[f];
 		R oq[D + 2];
 #pragma unroll
-		for (int i = 0; i < D + 2; i++) oq[i] = q[i * m.ncs + o];
+		for (int i = 0; i < D + 2; i++) oq[i] = q[(size_t)o * Rec<D>::QW + i];
 		const R op = pressure_of<R, D>(m.k, oq);
 		const R w = m.w[f];
 		// face values seen from the face's owner: INTERP_LINEAR(w, owner, neighbour)
@@ -256,7 +284,7 @@ template <class R, int D> __global__ void __launch_bounds__(kBlock) k_grad_ausm(
 // Loads everything face_flux needs about cell x (real cell, physical ghost or MPI ghost).
 template <class R, int D, int SCHEME> __device__ __forceinline__ void load_state(const DevMesh<R>& m, const R* __restrict__ q, int x, CellState<R, D>& s) {
 #pragma unroll
-	for (int i = 0; i < D + 2; i++) s.q[i] = q[i * m.ncs + x];
+	for (int i = 0; i < D + 2; i++) s.q[i] = q[(size_t)x * Rec<D>::QW + i];
 	const bool bc_ghost = x >= m.n_cells && x < m.n_cells + m.n_bc;
 	if (bc_ghost) {
 #pragma unroll
@@ -266,12 +294,13 @@ template <class R, int D, int SCHEME> __device__ __forceinline__ void load_state
 			for (int j = 0; j < D; j++) s.dudx[i][j] = R(0);
 		}
 	} else {
+		const R* rec = m.vis + (size_t)x * Rec<D>::VW;
 #pragma unroll
 		for (int i = 0; i < D; i++) {
 #pragma unroll
-			for (int j = 0; j < D; j++) s.dudx[i][j] = m.dudx[(size_t)(i * D + j) * m.ncs + x];
-			s.dTdx[i] = m.dTdx[(size_t)i * m.ncs + x];
-			s.sigmaU[i] = m.sigmaU[(size_t)i * m.ncs + x];
+			for (int j = 0; j < D; j++) s.dudx[i][j] = rec[Rec<D>::DUDX + i * D + j];
+			s.dTdx[i] = rec[Rec<D>::DTDX + i];
+			s.sigmaU[i] = rec[Rec<D>::SIGMAU + i];
 		}
 	}
 	derive_state<R, D, SCHEME>(m.k, s);
@@ -356,7 +385,7 @@ template <class R, int D> __global__ void __launch_bounds__(kBlock) k_update_cel
 	}
 	R cq[NQ];
 #pragma unroll
-	for (int i = 0; i < NQ; i++) cq[i] = q[i * m.ncs + c];
+	for (int i = 0; i < NQ; i++) cq[i] = q[(size_t)c * Rec<D>::QW + i];
 	const R sg = m.sigma[c];
 	dq[0] += dt * sg * (m.k.rhoInf - cq[0]);
 #pragma unroll
@@ -365,16 +394,54 @@ template <class R, int D> __global__ void __launch_bounds__(kBlock) k_update_cel
 #pragma unroll
 	for (int i = 0; i < NQ; i++) {
 		m.dq[(size_t)i * m.n_cells + c] = dq[i];
-		qn[i * m.ncs + c] = cq[i] + Bk * dq[i];
+		qn[(size_t)c * Rec<D>::QW + i] = cq[i] + Bk * dq[i];
 		if (res) m.RES[(size_t)i * m.n_cells + c] = RES[i];
 	}
 }
 
 // copies q of cells [c0,c1) between the two buffers (used when only part of the submeshes is advanced)
-template <class R> __global__ void __launch_bounds__(kBlock) k_copy_q(const R* __restrict__ src, R* __restrict__ dst, size_t ncs, int NQ, int c0, int c1) {
+template <class R> __global__ void __launch_bounds__(kBlock) k_copy_q(const R* __restrict__ src, R* __restrict__ dst, int QW, int c0, int c1) {
 	const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
 	if (c >= c1) return;
-	for (int i = 0; i < NQ; i++) dst[i * ncs + c] = src[i * ncs + c];
+	for (int i = 0; i < QW; i++) dst[(size_t)c * QW + i] = src[(size_t)c * QW + i];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// record <-> dense array converters of the data-movement entry points (lfmgpu_download / _upload_q / _pipe_*)
+// ---------------------------------------------------------------------------------------------------
+// out[i * comps + k] = rec[(x0 + i) * W + comp0 + k]      (AoS, the layout lfmgpu_download hands to the host)
+template <class R> __global__ void __launch_bounds__(kBlock) k_rec_gather(const R* __restrict__ rec, int W, int comp0, int comps, size_t x0, size_t n, R* __restrict__ out) {
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	for (int k = 0; k < comps; k++) out[i * comps + k] = rec[(x0 + i) * W + comp0 + k];
+}
+// rec[i * W + k] = in[i * comps + k]   (aos != 0)   or   in[k * n + i]   (component-major host arrays of the end-to-end path)
+template <class R> __global__ void __launch_bounds__(kBlock) k_rec_scatter(const R* __restrict__ in, int aos, size_t n, int comps, R* __restrict__ rec, int W) {
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	for (int k = 0; k < comps; k++) rec[i * W + k] = aos ? in[i * comps + k] : in[(size_t)k * n + i];
+}
+// out[k * n + i] = rec[i * W + k]
+template <class R> __global__ void __launch_bounds__(kBlock) k_rec_to_soa(const R* __restrict__ rec, int W, size_t n, int comps, R* __restrict__ out) {
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	for (int k = 0; k < comps; k++) out[(size_t)k * n + i] = rec[i * W + k];
+}
+// laminar tauMC of cells [0, n) rebuilt from the stored dudx with the expression of calc_VIS (cfd_v0.cpp:1838-1850): AoS [n][D][D]
+template <class R, int D> __global__ void __launch_bounds__(kBlock) k_taumc_laminar(DevMesh<R> m, size_t n, R* __restrict__ out) {
+	const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= n) return;
+	R dudx[D][D], tauMC[D][D];
+	const R* rec = m.vis + c * Rec<D>::VW;
+#pragma unroll
+	for (int i = 0; i < D; i++)
+#pragma unroll
+		for (int j = 0; j < D; j++) dudx[i][j] = rec[Rec<D>::DUDX + i * D + j];
+	tauMC_from<R, D>(m.k, dudx, tauMC);
+#pragma unroll
+	for (int i = 0; i < D; i++)
+#pragma unroll
+		for (int j = 0; j < D; j++) out[(c * D + i) * D + j] = tauMC[i][j];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -390,18 +457,19 @@ template <class R, int D> __global__ void __launch_bounds__(kBlock) k_pack(DevMe
 	R* o = buf + (size_t)i * spc;
 	R cq[NQ];
 #pragma unroll
-	for (int k = 0; k < NQ; k++) cq[k] = q[k * m.ncs + c];
+	for (int k = 0; k < NQ; k++) cq[k] = q[(size_t)c * Rec<D>::QW + k];
 	if (mode & 1) {
 #pragma unroll
 		for (int k = 0; k < NQ; k++) *o++ = cq[k];
 	}
 	if (mode & 2) {
 		R dudx[D][D], dTdx[D], tauMC[D][D], sigmaU[D];
+		const R* rec = m.vis + (size_t)c * Rec<D>::VW;
 #pragma unroll
 		for (int a = 0; a < D; a++) {
 #pragma unroll
-			for (int b = 0; b < D; b++) dudx[a][b] = m.dudx[(size_t)(a * D + b) * m.ncs + c];
-			dTdx[a] = m.dTdx[(size_t)a * m.ncs + c];
+			for (int b = 0; b < D; b++) dudx[a][b] = rec[Rec<D>::DUDX + a * D + b];
+			dTdx[a] = rec[Rec<D>::DTDX + a];
 		}
 		if (m.les) {
 #pragma unroll
@@ -412,7 +480,7 @@ template <class R, int D> __global__ void __launch_bounds__(kBlock) k_pack(DevMe
 			tauMC_from<R, D>(m.k, dudx, tauMC);
 		}
 #pragma unroll
-		for (int a = 0; a < D; a++) sigmaU[a] = m.sigmaU[(size_t)a * m.ncs + c];
+		for (int a = 0; a < D; a++) sigmaU[a] = rec[Rec<D>::SIGMAU + a];
 #pragma unroll
 		for (int a = 0; a < D; a++)
 #pragma unroll
@@ -428,7 +496,7 @@ template <class R, int D> __global__ void __launch_bounds__(kBlock) k_pack(DevMe
 	}
 }
 
-template <class R, int D> __global__ void __launch_bounds__(kBlock) k_unpack(DevMesh<R> m, R* __restrict__ q, R* __restrict__ drv, int scheme, int n_recv, int mode, const R* __restrict__ buf) {
+template <class R, int D> __global__ void __launch_bounds__(kBlock) k_unpack(DevMesh<R> m, R* __restrict__ q, int scheme, int n_recv, int mode, const R* __restrict__ buf) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n_recv) return;
 	constexpr int NQ = D + 2, NV = 2 * D * D + 2 * D;
@@ -440,22 +508,25 @@ template <class R, int D> __global__ void __launch_bounds__(kBlock) k_unpack(Dev
 #pragma unroll
 		for (int k = 0; k < NQ; k++) {
 			gq[k] = *o++;
-			q[k * m.ncs + g] = gq[k];
+			q[g * Rec<D>::QW + k] = gq[k];
 		}
-		store_derived<R, D>(m.k, gq, scheme, drv, m.ncs, g);
+		store_derived<R, D>(m.k, gq, scheme, q, g);
 	}
 	if (mode & 2) {
+		R* rec = m.vis + g * Rec<D>::VW;
+		R du[D * D];
 #pragma unroll
-		for (int a = 0; a < D * D; a++) m.dudx[(size_t)a * m.ncs + g] = *o++;
+		for (int a = 0; a < D * D; a++) rec[Rec<D>::DUDX + a] = du[a] = *o++;
+		if (D == 3) rec[Rec<D>::TR] = dudx_trace_neg<R, D>(du);
 #pragma unroll
-		for (int a = 0; a < D; a++) m.dTdx[(size_t)a * m.ncs + g] = *o++;
+		for (int a = 0; a < D; a++) rec[Rec<D>::DTDX + a] = *o++;
 		if (m.les) {   // with the Smagorinsky closure tauMC is not a function of dudx alone: keep what the neighbour computed
 #pragma unroll
 			for (int a = 0; a < D * D; a++) m.tauMC[(size_t)a * m.ncs + g] = o[a];
 		}
 		o += D * D;   // laminar: tauMC is a function of the dudx just stored (same expression on both ranks): not kept
 #pragma unroll
-		for (int a = 0; a < D; a++) m.sigmaU[(size_t)a * m.ncs + g] = *o++;
+		for (int a = 0; a < D; a++) rec[Rec<D>::SIGMAU + a] = *o++;
 	}
 }
 
@@ -470,7 +541,7 @@ template <class R, int D> __global__ void __launch_bounds__(kBlock) k_cfl_dt(Dev
 	if (c < m.n_cells) {
 		R cq[D + 1];
 #pragma unroll
-		for (int i = 0; i < D + 1; i++) cq[i] = q[i * m.ncs + c];
+		for (int i = 0; i < D + 1; i++) cq[i] = q[(size_t)c * Rec<D>::QW + i];
 		R acc = R(0);
 		for (int s = 0; s < m.F; s++) {
 			const int e = m.slot[(size_t)s * m.n_cells + c];
@@ -539,14 +610,15 @@ template <class R> __global__ void k_reduce_minmax(const R* __restrict__ partial
 template <class R, int D> __global__ void __launch_bounds__(kBlock) k_average(DevMesh<R> m, const R* __restrict__ q, int time_step) {
 	const int c = blockIdx.x * blockDim.x + threadIdx.x;
 	if (c >= m.n_cells) return;
-	const R r = q[c];
+	const R* rec = q + (size_t)c * Rec<D>::QW;
+	const R r = rec[0];
 	R velMag = R(0);
 #pragma unroll
 	for (int nD = 1; nD <= D; nD++) {
-		const R vel = q[nD * m.ncs + c] / r;
+		const R vel = rec[nD] / r;
 		velMag += vel * vel;
 	}
-	const R E = q[(D + 1) * m.ncs + c] / r;
+	const R E = rec[D + 1] / r;
 	const R p = (r * m.k.gm1) * (E - R(0.5) * velMag);
 	const R avg = m.pAVG[c] + p;
 	m.pAVG[c] = avg;
@@ -612,8 +684,8 @@ template <class R, int D> __global__ void __launch_bounds__(kBlock) k_forces_fac
 	}
 #pragma unroll
 	for (int i = 0; i < D + 2; i++) {
-		cq[i] = q[i * m.ncs + t];
-		nq[i] = qghost[i * m.ncs + n];
+		cq[i] = q[(size_t)t * Rec<D>::QW + i];
+		nq[i] = qghost[n * Rec<D>::QW + i];
 	}
 	const R r = cq[0], rE = cq[D + 1];
 	R Umag = R(0);

@@ -18,6 +18,7 @@
 
 #include "kernels.cuh"
 #include "lfmgpu.h"
+#include "stage_pipe.cuh"
 #include "tile_kernels.cuh"
 
 #ifndef LFM_AUSM_MINB64
@@ -111,9 +112,8 @@ struct lfmgpu_ctx {
 	std::vector<void*> allocs;
 	DevMesh<double> md{};
 	DevMesh<float> mf{};
-	void* q[2] = {nullptr, nullptr};
-	void* drv[2] = {nullptr, nullptr};   // [3][ncs] derived values (1/rho, Rpsi, c|H) of q[b] (tile kernels)
-	bool drv_valid[2] = {false, false};  // real cells of drv[b] match q[b]
+	void* q[2] = {nullptr, nullptr};     // [ncs][QW] Q records (Rec<D>): conservatives + the derived values 1/rho, Rpsi, c|H
+	bool drv_valid[2] = {false, false};  // the derived values in the records of q[b] match its conservatives
 	bool drv_dirty_next = false;         // a submesh of the running stage was advanced without writing drv
 	int drv_scheme = -1;                 // scheme the third derived value was computed for
 	int cur = 0;
@@ -161,6 +161,18 @@ struct lfmgpu_ctx {
 	bool ausm_zero = false;            // g_rho / g_p / g_U hold what prepare_for_RKstep leaves (zeros)
 	std::vector<int> smag_owner;       // cell whose face loop leaves each cell's final tauMC (Smagorinsky constant)
 	int tile_smem_budget = 75 * 1024;  // bytes of shared memory one tile CTA may use
+	// persistent TMA-fed stage kernel (stage_pipe.cuh)
+	bool pipe_ok = false;              // tensor maps and ring geometry are in place
+	int pipe_enable = 3;               // LFMGPU_PIPE: bit 0 stage kernel, bit 1 gradient kernel; 0: the tile kernels of round 1 serve everything
+	int pipe_slots_cap = 4;            // LFMGPU_PIPE_SLOTS
+	int pipe_spare_sms = 8;            // SMs left to the halo stream's kernels on a rank with neighbours (LFMGPU_PIPE_SPARE)
+	int n_sms = 0;
+	PipeGeom pipe{};
+	size_t pipe_smem = 0;
+	bool grad_pipe_ok = false;
+	GradGeom gpipe{};
+	size_t gpipe_smem = 0;
+	CUtensorMap map_q[2], map_v;       // record arrays as 2D tensors [ncs][QW | VW], box = one tile of own cells, swizzled
 	int smem_pad_kb = 0;               // extra shared memory requested per stage CTA (occupancy experiments)
 	// introspection
 	uint64_t launches = 0;
@@ -279,21 +291,19 @@ template <class R> int build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
 		TRY(upload<int>(h, &p, csr.data(), csr.size()));
 		m.csr = p;
 	}
-	for (int b = 0; b < 2; b++) TRY(dev_alloc(h, &h->q[b], (size_t)NQ * h->ncs * sizeof(R)));
-	for (int b = 0; b < 2; b++) TRY(dev_alloc(h, &h->drv[b], (size_t)3 * h->ncs * sizeof(R)));
+	const int QW = Rec<3>::QW, VW = D == 3 ? Rec<3>::VW : Rec<2>::VW;
+	for (int b = 0; b < 2; b++) TRY(dev_alloc(h, &h->q[b], (size_t)QW * h->ncs * sizeof(R)));
 	{
-		std::vector<R> tmp((size_t)NQ * h->ncs, R(0));
+		std::vector<R> tmp((size_t)QW * h->ncs, R(0));
 		const R* q0 = (const R*)ds->q0;
 		for (int c = 0; c < h->n_cells; c++)
-			for (int i = 0; i < NQ; i++) tmp[(size_t)i * h->ncs + c] = q0[(size_t)c * NQ + i];
+			for (int i = 0; i < NQ; i++) tmp[(size_t)c * QW + i] = q0[(size_t)c * NQ + i];
 		CU(cudaMemcpy(h->q[0], tmp.data(), tmp.size() * sizeof(R), cudaMemcpyHostToDevice));
 		CU(cudaMemcpy(h->q[1], tmp.data(), tmp.size() * sizeof(R), cudaMemcpyHostToDevice));
 	}
 	TRY(dev_alloc(h, (void**)&m.dq, (size_t)NQ * h->n_cells * sizeof(R)));
 	TRY(dev_alloc(h, (void**)&m.RES, (size_t)NQ * h->n_cells * sizeof(R)));
-	TRY(dev_alloc(h, (void**)&m.dudx, (size_t)D * D * h->ncs * sizeof(R)));
-	TRY(dev_alloc(h, (void**)&m.dTdx, (size_t)D * h->ncs * sizeof(R)));
-	TRY(dev_alloc(h, (void**)&m.sigmaU, (size_t)D * h->ncs * sizeof(R)));
+	TRY(dev_alloc(h, (void**)&m.vis, (size_t)VW * h->ncs * sizeof(R)));
 	m.tauMC = nullptr;   // allocated when the Smagorinsky closure is first used
 	m.g_rho = m.g_p = m.g_U = nullptr;   // allocated when solver 2 (M2-AUSM) is first used
 	m.les = 0;
@@ -385,12 +395,10 @@ int halo_spc(const lfmgpu_ctx* h, int step) {
 
 // buffer that holds the latest conservatives of cell range of submesh 0 (for packing)
 void* q_for_pack(lfmgpu_ctx* h) { return (h->updated_mask & 1u) ? h->q[1 - h->cur] : h->q[h->cur]; }
-// buffer that holds the conservatives the latest calc_VIS used (sigmaU of the packed payload is U.tau of THAT state)
-void* q_of_vis(lfmgpu_ctx* h) { return ((h->updated_mask & 1u) || h->vis_on_cur) ? h->q[h->cur] : h->q[1 - h->cur]; }
 
 template <class R, int D> int t_set_bc(lfmgpu_ctx* h) {
 	if (!h->n_bc) return 0;
-	LAUNCH(h, "k_set_bc", h->s_main, (k_set_bc<R, D><<<blocks_for(h->n_bc), kBlock, 0, h->s_main>>>(h->mesh<R>(), (R*)h->q[h->cur], (R*)h->drv[h->cur], h->drv_scheme < 0 ? 1 : h->drv_scheme)));
+	LAUNCH(h, "k_set_bc", h->s_main, (k_set_bc<R, D><<<blocks_for(h->n_bc), kBlock, 0, h->s_main>>>(h->mesh<R>(), (R*)h->q[h->cur], h->drv_scheme < 0 ? 1 : h->drv_scheme)));
 	CHECK_LAUNCH();
 	return 0;
 }
@@ -415,7 +423,7 @@ void sub_range(const lfmgpu_ctx* h, int sub, int& c0, int& c1, int& f0, int& f1)
 template <class R, int D> int ensure_drv(lfmgpu_ctx* h, int scheme) {
 	const int want = scheme >= 0 ? scheme : (h->drv_scheme >= 0 ? h->drv_scheme : 1);
 	if (h->drv_valid[h->cur] && want == h->drv_scheme) return 0;
-	LAUNCH(h, "k_derive", h->s_main, (k_derive<R, D><<<blocks_for(h->n_tot), kBlock, 0, h->s_main>>>(h->mesh<R>(), (const R*)h->q[h->cur], (R*)h->drv[h->cur], 0, h->n_tot, want)));
+	LAUNCH(h, "k_derive", h->s_main, (k_derive<R, D><<<blocks_for(h->n_tot), kBlock, 0, h->s_main>>>(h->mesh<R>(), (R*)h->q[h->cur], 0, h->n_tot, want)));
 	CHECK_LAUNCH();
 	h->drv_valid[h->cur] = true;
 	h->drv_scheme = want;
@@ -542,7 +550,7 @@ template <class R, int D> int t_pack(lfmgpu_ctx* h, int step, cudaStream_t s) {
 template <class R, int D> int t_unpack(lfmgpu_ctx* h, int step) {
 	const int nr = h->recv_start[(size_t)h->n_nbr];
 	if (!nr) return 0;
-	LAUNCH(h, "k_unpack", h->s_main, (k_unpack<R, D><<<blocks_for(nr), kBlock, 0, h->s_main>>>(h->mesh<R>(), (R*)h->q[h->cur], (R*)h->drv[h->cur], h->drv_scheme < 0 ? 1 : h->drv_scheme, nr, halo_mode(h, step), (const R*)h->recv_buf[step])));
+	LAUNCH(h, "k_unpack", h->s_main, (k_unpack<R, D><<<blocks_for(nr), kBlock, 0, h->s_main>>>(h->mesh<R>(), (R*)h->q[h->cur], h->drv_scheme < 0 ? 1 : h->drv_scheme, nr, halo_mode(h, step), (const R*)h->recv_buf[step])));
 	CHECK_LAUNCH();
 	return 0;
 }
@@ -598,7 +606,6 @@ template <class R> TileView<R> tile_view(lfmgpu_ctx* h, int smax, int fmax) {
 	v.fSmag = (const R*)p.d_fSmag;
 	v.T = p.T;
 	v.csr_local = p.d_csr_local;
-	v.staged_cell = p.d_staged_cell;
 	v.smax = smax;
 	v.fmax = fmax;
 	return v;
@@ -636,7 +643,14 @@ bool all_fixed(const lfmgpu_ctx* h) {
 template <class R, int D> size_t stage_smem(int smax, int fmax) { return ((size_t)StagedLayout<D>::NS * smax + (size_t)(D + 2) * fmax) * sizeof(R); }
 template <class R, int D> size_t grad_smem(int smax, int fmax) { return ((size_t)(D + 2) * smax + (size_t)(D + 1) * fmax) * sizeof(R) + (size_t)fmax * sizeof(uint32_t); }
 
+template <class R, int D> int grad_pipe(lfmgpu_ctx* h, int t0, int t1);
 template <class R, int D> int tile_grad(lfmgpu_ctx* h, int sub) {
+	if (h->grad_pipe_ok && !h->les) {   // the persistent TMA-fed kernel: laminar closure
+		int t0, t1, smax, fmax;
+		tile_range(h, sub, t0, t1, smax, fmax);
+		if (t1 <= t0) return 0;
+		return grad_pipe<R, D>(h, t0, t1);
+	}
 	// every submesh at once (a rank without neighbours): one launch when all of them fit the compile-time strides (same
 	// shared-memory size anyway), else one launch each so that each gets its own shared-memory size
 	if (sub < 0 && !all_fixed(h)) {
@@ -655,7 +669,134 @@ template <class R, int D> int tile_grad(lfmgpu_ctx* h, int sub) {
 	auto kern = h->les ? (fixed ? k_tile_grad<R, D, kGradThreads, kFixedSmax, kFixedFmax, 1> : k_tile_grad<R, D, kGradThreads, 0, 0, 1>)
 	                   : (fixed ? k_tile_grad<R, D, kGradThreads, kFixedSmax, kFixedFmax, 0> : k_tile_grad<R, D, kGradThreads, 0, 0, 0>);
 	if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	LAUNCH(h, "tile_grad", h->s_main, (kern<<<t1 - t0, kGradThreads, smem, h->s_main>>>(h->mesh<R>(), tile_view<R>(h, smax, fmax), (const R*)h->q[h->cur], (const R*)h->drv[h->cur], t0)));
+	LAUNCH(h, "tile_grad", h->s_main, (kern<<<t1 - t0, kGradThreads, smem, h->s_main>>>(h->mesh<R>(), tile_view<R>(h, smax, fmax), (const R*)h->q[h->cur], t0)));
+	CHECK_LAUNCH();
+	return 0;
+}
+
+// ---- persistent TMA-fed stage kernel: tensor maps, ring geometry, launch -----------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// records [rows][width] of `prec`-byte values as a 2D tensor whose box is `box_rows` whole records, written to shared memory
+// with the swizzle whose span is the record size (32, 64 or 128 bytes)
+int make_record_map(CUtensorMap* out, void* base, int prec, int width, size_t rows, int box_rows) {
+	static EncodeTiledFn encode = nullptr;
+	if (!encode) {
+		void* fn = nullptr;
+		cudaDriverEntryPointQueryResult qres;
+		CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+		if (!fn || qres != cudaDriverEntryPointSuccess) return fail("cuTensorMapEncodeTiled is not available in this driver");
+		encode = (EncodeTiledFn)fn;
+	}
+	const int bytes = width * prec;
+	const CUtensorMapSwizzle sw = bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+	if (bytes != 128 && bytes != 64 && bytes != 32) return fail("record of %d bytes has no TMA swizzle mode", bytes);
+	const cuuint64_t gdim[2] = {(cuuint64_t)width, (cuuint64_t)rows};
+	const cuuint64_t gstride[1] = {(cuuint64_t)bytes};
+	const cuuint32_t box[2] = {(cuuint32_t)width, (cuuint32_t)box_rows};
+	const cuuint32_t estr[2] = {1, 1};
+	const CUresult r = encode(out, prec == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+	                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) for %d-byte records, box of %d rows", (int)r, bytes, box_rows);
+	return 0;
+}
+
+inline uint32_t round_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
+
+// Called once the tile plan exists: decides whether the persistent kernel can serve this rank (every submesh cut with the
+// same tile size <= 256 -- the height of the TMA box -- halos of at most 256 cells, at least two ring slots in shared memory)
+int pipe_setup(lfmgpu_ctx* h) {
+	h->pipe_ok = false;
+	const TilePlan& p = h->tiles;
+	if (!h->pipe_enable || !p.ready) return 0;
+	int hmax = 0, fmax = 0;
+	for (int s = 0; s < h->n_sub; s++) {
+		if (p.sub_tile_start[s + 1] > p.sub_tile_start[s] && p.sub_tc[s] != h->tile_cells) return 0;
+		hmax = std::max(hmax, p.sub_hmax[s]);
+		fmax = std::max(fmax, p.sub_fmax[s]);
+	}
+	const int TC = h->tile_cells;
+	if (TC > 256 || TC % 2 || hmax > 32 * kPipeMaxHaloRegs) return 0;
+	hmax = std::max(hmax, 4);
+	const int D = h->D, QW = Rec<3>::QW, VW = D == 3 ? Rec<3>::VW : Rec<2>::VW;
+	const uint32_t QB = (uint32_t)(QW * h->prec), VB = (uint32_t)(VW * h->prec);
+	int dev_smem = 0;
+	CU(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+	CU(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, h->device));
+	PipeGeom g{};
+	g.box_cells = TC;
+	g.hmax = hmax;
+	g.smax = TC + hmax;
+	g.fmax = (fmax + 3) / 4 * 4;
+	g.q_bytes = round_up((uint32_t)g.smax * QB, 1024);
+	g.slot_bytes = g.q_bytes + round_up((uint32_t)g.smax * VB, 1024);
+	for (int ns = std::min(4, h->pipe_slots_cap); ns >= 2; ns--) {
+		g.n_slots = ns;
+		g.off_bar = 0;
+		g.off_ids = 128;
+		g.off_out = round_up(g.off_ids + (uint32_t)ns * hmax * 4u, 128);
+		g.off_fl = round_up(g.off_out + 2u * TC * QB, 128);
+		g.off_slot = round_up(g.off_fl + 2u * (uint32_t)h->NQ * g.fmax * (uint32_t)h->prec, 1024);
+		const size_t total = (size_t)g.off_slot + (size_t)ns * g.slot_bytes + 1024;   // + slack to align the base to 1024
+		if (total <= (size_t)dev_smem) {
+			h->pipe = g;
+			h->pipe_smem = total;
+			h->pipe_ok = true;
+			break;
+		}
+	}
+	// the gradient kernel's ring: Q records only + the tile's face slice; its four groups need at least four slots
+	h->grad_pipe_ok = false;
+	if (TC <= kGradGroupThreads) {
+		GradGeom gg{};
+		gg.box_cells = TC;
+		gg.hmax = hmax;
+		gg.smax = TC + hmax;
+		gg.fmax = g.fmax;
+		gg.q_bytes = round_up(std::max((uint32_t)gg.smax * QB, (uint32_t)TC * VB), 1024);
+		gg.slot_bytes = gg.q_bytes + round_up((uint32_t)gg.fmax * (uint32_t)((D + 1) * h->prec + 4), 1024);
+		for (int ns = 8; ns >= kGradGroups; ns--) {
+			gg.n_slots = ns;
+			gg.off_bar = 0;
+			gg.off_ids = 128;
+			gg.off_slot = round_up(gg.off_ids + (uint32_t)ns * hmax * 4u, 1024);
+			const size_t total = (size_t)gg.off_slot + (size_t)ns * gg.slot_bytes + 1024;
+			if (total <= (size_t)dev_smem) {
+				h->gpipe = gg;
+				h->gpipe_smem = total;
+				h->grad_pipe_ok = h->pipe_ok;
+				break;
+			}
+		}
+	}
+	if (!h->pipe_ok) return 0;
+	for (int b = 0; b < 2; b++) TRY(make_record_map(&h->map_q[b], h->q[b], h->prec, QW, h->ncs, TC));
+	const void* vis = h->prec == 8 ? (const void*)h->md.vis : (const void*)h->mf.vis;
+	TRY(make_record_map(&h->map_v, (void*)vis, h->prec, VW, h->ncs, TC));
+	return 0;
+}
+
+template <class R, int D> int grad_pipe(lfmgpu_ctx* h, int t0, int t1) {
+	auto kern = k_grad_pipe<R, D>;
+	CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->gpipe_smem));
+	const int sms = std::max(1, h->n_sms - (h->n_nbr ? h->pipe_spare_sms : 0));
+	const int grid = std::min(t1 - t0, sms);
+	LAUNCH(h, "tile_grad", h->s_main,
+	       (kern<<<grid, kGradThreadsTotal, h->gpipe_smem, h->s_main>>>(h->mesh<R>(), tile_view<R>(h, h->gpipe.smax, h->gpipe.fmax), h->map_q[h->cur], h->gpipe, (const R*)h->q[h->cur], t0, t1 - t0)));
+	CHECK_LAUNCH();
+	return 0;
+}
+
+template <class R, int D, int SCHEME> int stage_pipe(lfmgpu_ctx* h, int t0, int t1, R dt, R Ak, R Bk, int first, int res) {
+	auto kern = k_stage_pipe<R, D, SCHEME>;
+	CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->pipe_smem));
+	// a rank with neighbours keeps a few SMs free: the halo stream's pack / NCCL / unpack kernels must be able to start while
+	// the interior submesh's persistent CTAs hold every register of the SMs they run on
+	const int sms = std::max(1, h->n_sms - (h->n_nbr ? h->pipe_spare_sms : 0));
+	const int grid = std::min(t1 - t0, sms);
+	LAUNCH(h, "tile_stage", h->s_main,
+	       (kern<<<grid, kPipeThreads, h->pipe_smem, h->s_main>>>(h->mesh<R>(), tile_view<R>(h, h->pipe.smax, h->pipe.fmax), h->map_q[h->cur], h->map_v, h->pipe, (const R*)h->q[h->cur],
+	                                                              (R*)h->q[1 - h->cur], t0, t1 - t0, dt, Ak, Bk, first, res)));
 	CHECK_LAUNCH();
 	return 0;
 }
@@ -664,6 +805,14 @@ template <class R, int D> int tile_grad(lfmgpu_ctx* h, int sub) {
 template <class R> constexpr int kAusmMinBlocks = sizeof(R) == 8 ? LFM_AUSM_MINB64 : 2;
 
 template <class R, int D, int SCHEME> int tile_stage_s(lfmgpu_ctx* h, int sub, R dt, R Ak, R Bk, int first, int res) {
+	if constexpr (SCHEME != 2) {
+		if (h->pipe_ok && !h->les) {   // the persistent TMA-fed kernel: laminar M1 / M2
+			int t0, t1, smax, fmax;
+			tile_range(h, sub, t0, t1, smax, fmax);
+			if (t1 <= t0) return 0;
+			return stage_pipe<R, D, SCHEME>(h, t0, t1, dt, Ak, Bk, first, res);
+		}
+	}
 	if (sub < 0 && (!all_fixed(h) || SCHEME == 2)) {
 		for (int s = 0; s < h->n_sub; s++) TRY((tile_stage_s<R, D, SCHEME>(h, s, dt, Ak, Bk, first, res)));
 		return 0;
@@ -693,7 +842,7 @@ template <class R, int D, int SCHEME> int tile_stage_s(lfmgpu_ctx* h, int sub, R
 		auto kern = k_tile_stage<R, D, SCHEME, 256, kAusmMinBlocks<R>, 0, 0, 2>;
 		if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		LAUNCH(h, "tile_stage", h->s_main,
-		       (kern<<<t1 - t0, nt_, smem, h->s_main>>>(h->mesh<R>(), tview, (const R*)h->q[h->cur], (const R*)h->drv[h->cur], (R*)h->q[1 - h->cur], (R*)h->drv[1 - h->cur], t0, dt, Ak, Bk,
+		       (kern<<<t1 - t0, nt_, smem, h->s_main>>>(h->mesh<R>(), tview, (const R*)h->q[h->cur], (R*)h->q[1 - h->cur], t0, dt, Ak, Bk,
 		                                              first, res)));
 		CHECK_LAUNCH();
 		return 0;
@@ -708,7 +857,7 @@ template <class R, int D, int SCHEME> int tile_stage_s(lfmgpu_ctx* h, int sub, R
 			auto kern = k_tile_stage<R, D, SCHEME, 256, 2, SM_, FM_, 1>; \
 			if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
 			LAUNCH(h, "tile_stage", h->s_main, \
-			       (kern<<<t1 - t0, nt_, smem, h->s_main>>>(h->mesh<R>(), tview, (const R*)h->q[h->cur], (const R*)h->drv[h->cur], (R*)h->q[1 - h->cur], (R*)h->drv[1 - h->cur], t0, dt, Ak, \
+			       (kern<<<t1 - t0, nt_, smem, h->s_main>>>(h->mesh<R>(), tview, (const R*)h->q[h->cur], (R*)h->q[1 - h->cur], t0, dt, Ak, \
 			                                              Bk, first, res))); \
 		}
 		if (fixed)
@@ -724,7 +873,7 @@ template <class R, int D, int SCHEME> int tile_stage_s(lfmgpu_ctx* h, int sub, R
 		auto kern = k_tile_stage<R, D, SCHEME, __VA_ARGS__>; \
 		if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
 		LAUNCH(h, "tile_stage", h->s_main, \
-		       (kern<<<t1 - t0, nt_, smem, h->s_main>>>(h->mesh<R>(), tview, (const R*)h->q[h->cur], (const R*)h->drv[h->cur], (R*)h->q[1 - h->cur], (R*)h->drv[1 - h->cur], t0, dt, Ak, Bk, \
+		       (kern<<<t1 - t0, nt_, smem, h->s_main>>>(h->mesh<R>(), tview, (const R*)h->q[h->cur], (R*)h->q[1 - h->cur], t0, dt, Ak, Bk, \
 		                                              first, res))); \
 	}
 #define LFM_STAGE_CFG(NT_, MB_) \
@@ -735,40 +884,9 @@ template <class R, int D, int SCHEME> int tile_stage_s(lfmgpu_ctx* h, int sub, R
 		else \
 			LFM_STAGE_LAUNCH(NT_, MB_, 0, 0) \
 	}
-#define LFM_STAGE_PERSISTENT(NT_, MB_) \
-	{ \
-		auto kern = k_tile_stage_p<R, D, SCHEME, NT_, MB_, kFixedSmax, kFixedFmax>; \
-		const size_t psmem = ((size_t)(StagedLayout<D>::NS + D + 2) * kFixedSmax + (size_t)(D + 2) * kFixedFmax) * sizeof(R) + 3 * sizeof(TileDesc); \
-		CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem)); \
-		int per_sm = 0, sms = 0; \
-		CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT_, psmem)); \
-		CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device)); \
-		const int grid = std::max(1, std::min(t1 - t0, per_sm * sms)); \
-		LAUNCH(h, "tile_stage", h->s_main, \
-		       (kern<<<grid, NT_, psmem, h->s_main>>>(h->mesh<R>(), tview, (const R*)h->q[h->cur], (const R*)h->drv[h->cur], (R*)h->q[1 - h->cur], (R*)h->drv[1 - h->cur], t0, t1 - t0, dt, Ak, \
-		                                              Bk, first, res))); \
-	}
-	if (fixed && h->stage_cfg >= 20) {
-		switch (h->stage_cfg) {
-			case 21: LFM_STAGE_PERSISTENT(128, 4) break;
-			case 22: LFM_STAGE_PERSISTENT(512, 1) break;
-			case 23: LFM_STAGE_PERSISTENT(256, 3) break;
-			default: LFM_STAGE_PERSISTENT(256, 2) break;
-		}
-		CHECK_LAUNCH();
-		return 0;
-	}
-#undef LFM_STAGE_PERSISTENT
 	switch (h->stage_cfg) {
 		case 1: LFM_STAGE_CFG(128, 4) break;
 		case 6: LFM_STAGE_CFG(256, 2) break;
-		case 7:   // 256 x 2 with the EARLY copy-in (needs the staged-cell table: compile-time strides only)
-			if (fixed && h->tiles.d_staged_cell) {
-				const int nt_ = 256;
-				LFM_STAGE_LAUNCH(256, 2, kFixedSmax, kFixedFmax, 0, 1)
-			} else
-				LFM_STAGE_CFG(256, 2)
-			break;
 		case 12: LFM_STAGE_CFG(512, 1) break;
 		default: LFM_STAGE_CFG(256, 3) break;
 	}
@@ -892,7 +1010,8 @@ int tile_plan_host(lfmgpu_ctx* h, const lfmgpu_desc* ds, int dev_smem, HostPlan&
 				break;
 			}
 			p.sub_tile_start[s] = (int)tiles.size();
-			int smax = 0, fmax = 0;
+			p.sub_tc[s] = TC;
+			int smax = 0, fmax = 0, hmax = 0;
 			for (int c0 = h->sub_cell_start[s], c1 = 0; c0 < h->sub_cell_start[s + 1]; c0 = c1) {
 				const int cmax = std::min(c0 + TC, h->sub_cell_start[s + 1]);
 				// Choose the cut: grow the run cell by cell, tracking halo cells and incoming faces incrementally, and
@@ -919,7 +1038,7 @@ int tile_plan_host(lfmgpu_ctx* h, const lfmgpu_desc* ds, int dev_smem, HostPlan&
 							}
 						}
 						const int nt = c + 1 - c0;
-						const bool fits = nt + nh <= s_cap && (cfs[(size_t)c + 1] - cfs[(size_t)c0]) + ninc <= f_cap;
+						const bool fits = TC + nh <= s_cap && (cfs[(size_t)c + 1] - cfs[(size_t)c0]) + ninc <= f_cap;   // halo cells are staged from slot TC on
 						if (!fits) continue;   // (not monotone: a later prefix may fit again once halo cells join the tile)
 						longest_fit = c + 1;
 						if (c + 1 >= cmin) {
@@ -932,7 +1051,8 @@ int tile_plan_host(lfmgpu_ctx* h, const lfmgpu_desc* ds, int dev_smem, HostPlan&
 					}
 					c1 = best_in_window > 0 ? best_in_window : longest_fit;
 					if (c1 <= c0) {
-						ok = false;   // a single cell does not fit: not tileable
+						ok = false;   // not even one cell fits behind a halo base of TC slots: retry with shorter tiles
+						failed_sub = s;
 						break;
 					}
 				}
@@ -943,6 +1063,10 @@ int tile_plan_host(lfmgpu_ctx* h, const lfmgpu_desc* ds, int dev_smem, HostPlan&
 				const int fo0 = cfs[(size_t)c0];
 				td.nfo = cfs[(size_t)c1] - fo0;
 				td.halo_off = (int)halo_cell.size();
+				while (f_gface.size() % 4) {   // a tile's slice of the face tables starts on a 16-byte boundary (bulk copies)
+					f_gface.push_back(0);
+					f_idx.push_back(0);
+				}
 				td.f_off = (int)f_gface.size();
 				// halo cells and incoming faces
 				inc.clear();
@@ -963,8 +1087,9 @@ int tile_plan_host(lfmgpu_ctx* h, const lfmgpu_desc* ds, int dev_smem, HostPlan&
 				std::sort(halo_cell.begin() + td.halo_off, halo_cell.end());
 				td.nh = (int)halo_cell.size() - td.halo_off;
 				td.ninc = (int)inc.size();
-				for (int i = 0; i < td.nh; i++) local_of[(size_t)halo_cell[(size_t)td.halo_off + i]] = td.nt + i;
-				if (td.nt + td.nh >= 32768 || td.nfo + td.ninc >= 32767 || f_gface.size() + (size_t)td.nfo + td.ninc >= (size_t)0x7fffffff) {
+				td.hb = TC;
+				for (int i = 0; i < td.nh; i++) local_of[(size_t)halo_cell[(size_t)td.halo_off + i]] = td.hb + i;
+				if (td.hb + td.nh >= 32768 || td.nfo + td.ninc >= 32767 || f_gface.size() + (size_t)td.nfo + td.ninc >= (size_t)0x7fffffff) {
 					ok = false;
 					failed_sub = s;
 					break;
@@ -1006,7 +1131,8 @@ int tile_plan_host(lfmgpu_ctx* h, const lfmgpu_desc* ds, int dev_smem, HostPlan&
 						csr_local[(size_t)k * nc + c] = (int16_t)(e > 0 ? lf + 1 : -(lf + 1));
 					}
 				}
-				smax = std::max(smax, td.nt + td.nh);
+				smax = std::max(smax, td.hb + td.nh);
+				hmax = std::max(hmax, td.nh);
 				fmax = std::max(fmax, td.nfo + td.ninc);
 				tot_own += td.nfo;
 				tot_inc += td.ninc;
@@ -1018,6 +1144,7 @@ int tile_plan_host(lfmgpu_ctx* h, const lfmgpu_desc* ds, int dev_smem, HostPlan&
 			fmax = (fmax + 3) / 4 * 4;
 			p.sub_smax[s] = smax;
 			p.sub_fmax[s] = fmax;
+			p.sub_hmax[s] = hmax;
 			if (ok && ((size_t)NS * smax + (size_t)NQ * fmax) * es > budget) {
 				ok = false;
 				failed_sub = s;
@@ -1057,7 +1184,7 @@ int tile_plan_build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
 		for (int sb = 0; sb < h->n_sub; sb++) {
 			std::vector<int> a, b, c;
 			for (int t = p.sub_tile_start[sb]; t < p.sub_tile_start[sb + 1]; t++) {
-				a.push_back(tiles[(size_t)t].nt + tiles[(size_t)t].nh);
+				a.push_back(tiles[(size_t)t].hb + tiles[(size_t)t].nh);
 				b.push_back(tiles[(size_t)t].nfo + tiles[(size_t)t].ninc);
 				c.push_back(tiles[(size_t)t].nt);
 			}
@@ -1087,17 +1214,6 @@ int tile_plan_build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
 	TRY(upload<int>(h, &p.d_f_gface, f_gface.data(), f_gface.size()));
 	TRY(upload<uint32_t>(h, &p.d_f_idx, f_idx.data(), f_idx.size()));
 	TRY(upload<int16_t>(h, &p.d_csr_local, csr_local.data(), csr_local.size()));
-	p.d_staged_cell = nullptr;
-	if (h->stage_cfg == 7 && all_fixed(h)) {   // experiment (DESIGN.md 9 a'): fixed-pitch staged-cell table for the EARLY stage kernel
-		std::vector<int> staged((size_t)tiles.size() * kFixedSmax, -1);
-		for (size_t t = 0; t < tiles.size(); t++) {
-			const TileDesc& td = tiles[t];
-			int* row = &staged[t * kFixedSmax];
-			for (int i = 0; i < td.nt; i++) row[i] = td.c0 + i;
-			for (int i = 0; i < td.nh; i++) row[td.nt + i] = halo_cell[(size_t)td.halo_off + i];
-		}
-		TRY(upload<int>(h, &p.d_staged_cell, staged.data(), staged.size()));
-	}
 	TRY(h->prec == 8 ? (D == 3 ? tile_geo<double, 3>(h) : tile_geo<double, 2>(h)) : (D == 3 ? tile_geo<float, 3>(h) : tile_geo<float, 2>(h)));
 	p.ready = true;
 	return 0;
@@ -1316,14 +1432,20 @@ int lfmgpu_create(const lfmgpu_desc* ds, int device, lfmgpu_t* out) {
 		}
 		rc = h->prec == 8 ? build<double>(h, ds) : build<float>(h, ds);
 	}
-	h->stage_cfg = h->prec == 8 ? 6 : 23;  // fp64: 256 threads x 2 CTAs/SM (128 registers, no spills); fp32: persistent 256 x 3
+	h->stage_cfg = 6;   // tile kernels (fallback of the persistent kernel): 256 threads x 2 CTAs/SM (128 registers, no spills)
 	if (const char* e = getenv("LFMGPU_TILE_CELLS")) h->tile_cells = std::max(16, atoi(e));
 	if (const char* e = getenv("LFMGPU_STAGE_CFG")) h->stage_cfg = atoi(e);
 	if (const char* e = getenv("LFMGPU_USE_TILES")) h->use_tiles = atoi(e);
 	if (const char* e = getenv("LFMGPU_FIXED_STRIDES")) h->fixed_strides = atoi(e);
 	if (const char* e = getenv("LFMGPU_TILE_SMEM")) h->tile_smem_budget = std::max(16, atoi(e)) * 1024;
 	if (const char* e = getenv("LFMGPU_SMEM_PAD")) h->smem_pad_kb = std::max(0, atoi(e));
+	if (const char* e = getenv("LFMGPU_PIPE")) h->pipe_enable = atoi(e);   // bit 0: stage kernel, bit 1: gradient kernel
+	if (const char* e = getenv("LFMGPU_PIPE_SLOTS")) h->pipe_slots_cap = std::max(2, atoi(e));
+	if (const char* e = getenv("LFMGPU_PIPE_SPARE")) h->pipe_spare_sms = std::max(0, atoi(e));
 	if (!rc) rc = tile_plan_build(h, ds);
+	if (!rc) rc = pipe_setup(h);
+	if (!(h->pipe_enable & 2)) h->grad_pipe_ok = false;
+	if (!(h->pipe_enable & 1)) h->pipe_ok = false;
 	if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = fail("upload failed: %s", cudaGetErrorString(cudaGetLastError()));
 	if (rc) {
 		lfmgpu_destroy(h);
@@ -1372,7 +1494,8 @@ int lfmgpu_plan_check(const lfmgpu_desc* ds, int tile_cells, int smem_limit_byte
 			if (c0 != next || td.nt < 1) return bad("tiles do not tile the cells", t);
 			next = c1;
 			if (c0 < h->sub_cell_start[s] || c1 > h->sub_cell_start[s + 1]) return bad("tile straddles a submesh", t);
-			if (td.nt + td.nh > p.sub_smax[s] || td.nfo + td.ninc > p.sub_fmax[s]) return bad("tile larger than the strides of its launch", t);
+			if (td.hb != p.sub_tc[s] || td.nt > td.hb) return bad("halo base is not the submesh's tile size", t);
+			if (td.hb + td.nh > p.sub_smax[s] || td.nfo + td.ninc > p.sub_fmax[s]) return bad("tile larger than the strides of its launch", t);
 			const int* hc = hp.halo_cell.data() + td.halo_off;
 			for (int i = 0; i < td.nh; i++) {
 				if (i && hc[i] <= hc[i - 1]) return bad("halo not strictly ascending", t);
@@ -1381,7 +1504,7 @@ int lfmgpu_plan_check(const lfmgpu_desc* ds, int tile_cells, int smem_limit_byte
 				if (!i || hc[i] != hc[i - 1] + 1) halo_runs++;
 			}
 			used.assign((size_t)td.nh, 0);
-			auto cell_of = [&](int staged) { return staged < td.nt ? c0 + staged : hc[staged - td.nt]; };
+			auto cell_of = [&](int staged) { return staged < td.nt ? c0 + staged : hc[staged - td.hb]; };
 			int n_own = 0;
 			for (int c = c0; c < c1; c++)
 				for (int k = 0; k < F; k++) n_own += ds->cell_slot_face[(size_t)c * F + k] > 0 ? 1 : 0;
@@ -1391,7 +1514,8 @@ int lfmgpu_plan_check(const lfmgpu_desc* ds, int tile_cells, int smem_limit_byte
 				const uint32_t idx = hp.f_idx[(size_t)td.f_off + j];
 				const int lo = (int)(idx & 0xffffu), ln = (int)((idx >> 16) & 0x7fffu);
 				const bool ghost = (idx >> 31) != 0;
-				if (f < 0 || f >= h->n_faces || lo >= td.nt + td.nh || ln >= td.nt + td.nh) return bad("face table entry out of range", t);
+				auto staged_ok = [&](int x) { return (x >= 0 && x < td.nt) || (x >= td.hb && x < td.hb + td.nh); };
+				if (f < 0 || f >= h->n_faces || !staged_ok(lo) || !staged_ok(ln)) return bad("face table entry out of range", t);
 				if (cell_of(lo) != ds->face_owner[f] || cell_of(ln) != ds->face_neigh[f]) return bad("staged owner/neighbour of a table face is not the mesh's", t);
 				const int n = ds->face_neigh[f];
 				if (ghost != (n >= nc && n < nc + h->n_bc)) return bad("physical-ghost flag wrong", t);
@@ -1400,8 +1524,8 @@ int lfmgpu_plan_check(const lfmgpu_desc* ds, int tile_cells, int smem_limit_byte
 				} else {
 					if (lo < td.nt || ln >= td.nt || ghost) return bad("incoming face not from a halo cell into the tile", t);
 				}
-				if (lo >= td.nt) used[(size_t)(lo - td.nt)] = 1;
-				if (ln >= td.nt) used[(size_t)(ln - td.nt)] = 1;
+				if (lo >= td.nt) used[(size_t)(lo - td.hb)] = 1;
+				if (ln >= td.nt) used[(size_t)(ln - td.hb)] = 1;
 			}
 			for (int i = 0; i < td.nh; i++)
 				if (!used[(size_t)i]) return bad("halo cell no face refers to", t);
@@ -1434,7 +1558,7 @@ int lfmgpu_plan_check(const lfmgpu_desc* ds, int tile_cells, int smem_limit_byte
 				}
 			}
 			if (n_inc != td.ninc) return bad("incoming-face count differs from the gather lists", t);
-			smax_all = std::max(smax_all, td.nt + td.nh);
+			smax_all = std::max(smax_all, td.hb + td.nh);
 			fmax_all = std::max(fmax_all, td.nfo + td.ninc);
 			own += td.nfo;
 			incoming += td.ninc;
@@ -1619,145 +1743,96 @@ int lfmgpu_step_multi(const lfmgpu_t* hs, int n_ranks, int scheme, double dt, in
 }
 
 // ---- data movement ---------------------------------------------------------------------------------
-int lfmgpu_download(lfmgpu_t h, int field, void* dst, size_t dst_bytes) {
-	TRY(use(h));
-	TRY(lfmgpu_sync(h));
-	const int D = h->D, NQ = h->NQ, nc = h->n_cells;
-	const size_t es = (size_t)h->prec;
-	const char* base = nullptr;
+}  // extern "C" (templates below)
+namespace {
+// dense device scratch of the data-movement entry points
+struct DevTmp {
+	void* p = nullptr;
+	~DevTmp() {
+		if (p) cudaFree(p);
+	}
+};
+template <class R, int D> int t_download(lfmgpu_ctx* h, int field, void* dst, size_t dst_bytes) {
+	const int NQ = h->NQ, nc = h->n_cells;
+	constexpr int QW = Rec<D>::QW, VW = Rec<D>::VW;
+	DevMesh<R>& m = h->mesh<R>();
+	// record fields: (records, width, first value, values); SoA fields: (base, stride)
+	const R* rec = nullptr;
+	int W = 0, comp0 = 0, comps = 1;
+	const R* soa = nullptr;
 	size_t stride = 0, n = (size_t)nc, off = 0;
-	int comps = 1;
-	bool derived = false;
-	const char *dudx = h->prec == 8 ? (const char*)h->md.dudx : (const char*)h->mf.dudx;
+	bool taumc_laminar = false;
 	switch (field) {
-		case LFMGPU_FIELD_Q: base = (const char*)h->q[h->cur]; stride = h->ncs; comps = NQ; break;
-		case LFMGPU_FIELD_DQ: base = h->prec == 8 ? (const char*)h->md.dq : (const char*)h->mf.dq; stride = (size_t)nc; comps = NQ; break;
-		case LFMGPU_FIELD_RES: base = h->prec == 8 ? (const char*)h->md.RES : (const char*)h->mf.RES; stride = (size_t)nc; comps = NQ; break;
-		case LFMGPU_FIELD_DUDX: base = dudx; stride = h->ncs; comps = D * D; break;
-		case LFMGPU_FIELD_DTDX: base = h->prec == 8 ? (const char*)h->md.dTdx : (const char*)h->mf.dTdx; stride = h->ncs; comps = D; break;
-		case LFMGPU_FIELD_PAVG: base = h->prec == 8 ? (const char*)h->md.pAVG : (const char*)h->mf.pAVG; stride = (size_t)nc; break;
-		case LFMGPU_FIELD_PRMS: base = h->prec == 8 ? (const char*)h->md.pRMS : (const char*)h->mf.pRMS; stride = (size_t)nc; break;
-		case LFMGPU_FIELD_QGHOST: base = (const char*)h->q[h->cur]; stride = h->ncs; comps = NQ; off = (size_t)nc; n = (size_t)(h->n_bc + h->n_mpi); break;
+		case LFMGPU_FIELD_Q: rec = (const R*)h->q[h->cur]; W = QW; comps = NQ; break;
+		case LFMGPU_FIELD_QGHOST: rec = (const R*)h->q[h->cur]; W = QW; comps = NQ; off = (size_t)nc; n = (size_t)(h->n_bc + h->n_mpi); break;
+		case LFMGPU_FIELD_DUDX: rec = m.vis; W = VW; comp0 = Rec<D>::DUDX; comps = D * D; break;
+		case LFMGPU_FIELD_DTDX: rec = m.vis; W = VW; comp0 = Rec<D>::DTDX; comps = D; break;
+		case LFMGPU_FIELD_SIGMAU: rec = m.vis; W = VW; comp0 = Rec<D>::SIGMAU; comps = D; break;
+		case LFMGPU_FIELD_DQ: soa = m.dq; stride = (size_t)nc; comps = NQ; break;
+		case LFMGPU_FIELD_RES: soa = m.RES; stride = (size_t)nc; comps = NQ; break;
+		case LFMGPU_FIELD_PAVG: soa = m.pAVG; stride = (size_t)nc; break;
+		case LFMGPU_FIELD_PRMS: soa = m.pRMS; stride = (size_t)nc; break;
 		case LFMGPU_FIELD_TAUMC:
 			comps = D * D;
 			if (h->les) {
-				base = h->prec == 8 ? (const char*)h->md.tauMC : (const char*)h->mf.tauMC;
+				soa = m.tauMC;
 				stride = h->ncs;
 			} else {
-				derived = true;
+				taumc_laminar = true;   // a function of the stored dudx (calc_VIS does not keep it): rebuilt on the device
 			}
 			break;
-		case LFMGPU_FIELD_SIGMAU: base = h->prec == 8 ? (const char*)h->md.sigmaU : (const char*)h->mf.sigmaU; stride = h->ncs; comps = D; break;
 		default: return fail("unknown field %d", field);
 	}
-	if (dst_bytes < n * comps * es) return fail("lfmgpu_download: destination too small (%zu < %zu)", dst_bytes, n * comps * es);
+	const size_t bytes = n * comps * sizeof(R);
+	if (dst_bytes < bytes) return fail("lfmgpu_download: destination too small (%zu < %zu)", dst_bytes, bytes);
 	if (n == 0) return 0;
-	if (derived) {
-		// tauMC / sigmaU are not stored: rebuild them from q and dudx with the calc_VIS expressions on the host
-		std::vector<char> qh((size_t)NQ * n * es), gh((size_t)D * D * n * es);
-		// calc_VIS saw the conservatives of the stage it ran in: after a completed stage those are in the other buffer
-		const char* qsrc = (const char*)q_of_vis(h);
-		for (int i = 0; i < NQ; i++) CU(cudaMemcpy(qh.data() + (size_t)i * n * es, qsrc + (size_t)i * h->ncs * es, n * es, cudaMemcpyDeviceToHost));
-		for (int i = 0; i < D * D; i++) CU(cudaMemcpy(gh.data() + (size_t)i * n * es, dudx + (size_t)i * h->ncs * es, n * es, cudaMemcpyDeviceToHost));
-		auto run = [&](auto zero) {
-			using R = decltype(zero);
-			const R* q = (const R*)qh.data();
-			const R* g = (const R*)gh.data();
-			const R mu = (R)h->c.mu;
-			const R c_tau = (R)(2.0 / 3.0 * (double)mu), c_diag = (R)((double)mu * 2.0 / 3.0);
-			R* o = (R*)dst;
-			for (size_t c = 0; c < n; c++) {
-				R du[3][3], tau[3][3], U[3];
-				for (int i = 0; i < D; i++) {
-					U[i] = q[(size_t)(i + 1) * n + c] / q[c];
-					for (int j = 0; j < D; j++) du[i][j] = g[(size_t)(i * D + j) * n + c];
-				}
-				for (int nD = 0; nD < D; nD++) {
-					tau[nD][nD] = R(2.0) * du[nD][nD];
-					for (int nD1 = nD + 1; nD1 < D + nD; nD1++) {
-						const int nD2 = nD1 % D;
-						tau[nD][nD2] = mu * (du[nD][nD2] + du[nD2][nD]);
-						tau[nD][nD] -= du[nD2][nD2];
-					}
-					tau[nD][nD] *= c_tau;
-				}
-				R diag = 0;
-				for (int nD = 0; nD < D; nD++) diag -= du[nD][nD];
-				diag *= c_diag;
-				for (int i = 0; i < D; i++) {
-					if (field == LFMGPU_FIELD_SIGMAU) {
-						volatile R s = U[0] * tau[i][0];
-						for (int j = 1; j < D; j++) {
-							volatile R t = U[j] * tau[i][j];
-							s = s + t;
-						}
-						o[c * D + i] = s;
-					} else {
-						for (int j = 0; j < D; j++) {
-							volatile R t = mu * du[j][i];
-							o[(c * D + i) * D + j] = t;
-						}
-						o[(c * D + i) * D + i] += diag;
-					}
-				}
-			}
-		};
-		if (h->prec == 8) run(double(0)); else run(float(0));
+	if (soa) {
+		std::vector<R> tmp((size_t)comps * n);
+		for (int i = 0; i < comps; i++) CU(cudaMemcpy(tmp.data() + (size_t)i * n, soa + (size_t)i * stride, n * sizeof(R), cudaMemcpyDeviceToHost));
+		R* o = (R*)dst;
+		for (size_t c = 0; c < n; c++)
+			for (int i = 0; i < comps; i++) o[c * comps + i] = tmp[(size_t)i * n + c];
 		return 0;
 	}
-	std::vector<char> tmp((size_t)comps * n * es);
-	for (int i = 0; i < comps; i++) CU(cudaMemcpy(tmp.data() + (size_t)i * n * es, base + ((size_t)i * stride + off) * es, n * es, cudaMemcpyDeviceToHost));
-	if (field == LFMGPU_FIELD_QGHOST && h->n_bc && h->stage_done) {
-		// physical ghosts were last written by set_boundary_conditions of the latest stage, i.e. into the other buffer
-		const char* old = (const char*)h->q[1 - h->cur];
-		for (int i = 0; i < comps; i++) CU(cudaMemcpy(tmp.data() + (size_t)i * n * es, old + ((size_t)i * stride + off) * es, (size_t)h->n_bc * es, cudaMemcpyDeviceToHost));
+	DevTmp t;
+	CU(cudaMalloc(&t.p, bytes));
+	const unsigned nb = (unsigned)((n + kBlock - 1) / kBlock);
+	if (taumc_laminar) {
+		k_taumc_laminar<R, D><<<nb, kBlock, 0, h->s_main>>>(m, n, (R*)t.p);
+	} else {
+		k_rec_gather<R><<<nb, kBlock, 0, h->s_main>>>(rec, W, comp0, comps, off, n, (R*)t.p);
+		if (field == LFMGPU_FIELD_QGHOST && h->n_bc && h->stage_done) {
+			// physical ghosts were last written by set_boundary_conditions of the latest stage, i.e. into the other buffer
+			k_rec_gather<R><<<(unsigned)((h->n_bc + kBlock - 1) / kBlock), kBlock, 0, h->s_main>>>((const R*)h->q[1 - h->cur], W, comp0, comps, off, (size_t)h->n_bc, (R*)t.p);
+		}
 	}
-	// SoA -> AoS
-	char* o = (char*)dst;
-	for (size_t c = 0; c < n; c++)
-		for (int i = 0; i < comps; i++) memcpy(o + (c * comps + i) * es, tmp.data() + ((size_t)i * n + c) * es, es);
+	CHECK_LAUNCH();
+	CU(cudaMemcpyAsync(dst, t.p, bytes, cudaMemcpyDeviceToHost, h->s_main));
+	CU(cudaStreamSynchronize(h->s_main));
 	return 0;
 }
 
-int lfmgpu_upload_q(lfmgpu_t h, const void* q, size_t bytes) {
-	TRY(use(h));
-	TRY(lfmgpu_sync(h));
-	const size_t es = (size_t)h->prec, n = (size_t)h->n_cells;
-	if (bytes != n * h->NQ * es) return fail("lfmgpu_upload_q: expected %zu bytes", n * h->NQ * es);
-	std::vector<char> tmp(bytes);
-	for (size_t c = 0; c < n; c++)
-		for (int i = 0; i < h->NQ; i++) memcpy(tmp.data() + ((size_t)i * n + c) * es, (const char*)q + (c * h->NQ + i) * es, es);
-	for (int i = 0; i < h->NQ; i++) CU(cudaMemcpy((char*)h->q[h->cur] + (size_t)i * h->ncs * es, tmp.data() + (size_t)i * n * es, n * es, cudaMemcpyHostToDevice));
+// conservatives of the real cells from a dense device array (AoS [n][NQ] or component-major [NQ][n]) into the records of q[cur]
+template <class R, int D> int t_scatter_q(lfmgpu_ctx* h, const void* dev_src, int aos, cudaStream_t s) {
+	const size_t n = (size_t)h->n_cells;
+	if (!n) return 0;
+	k_rec_scatter<R><<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, s>>>((const R*)dev_src, aos, n, h->NQ, (R*)h->q[h->cur], Rec<D>::QW);
+	CHECK_LAUNCH();
+	return 0;
+}
+template <class R, int D> int t_gather_q_soa(lfmgpu_ctx* h, void* dev_dst, cudaStream_t s) {
+	const size_t n = (size_t)h->n_cells;
+	if (!n) return 0;
+	k_rec_to_soa<R><<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, s>>>((const R*)h->q[h->cur], Rec<D>::QW, n, h->NQ, (R*)dev_dst);
+	CHECK_LAUNCH();
+	return 0;
+}
+// a new state was uploaded into q[cur]: nothing of the previous run describes it any more
+void mark_uploaded(lfmgpu_ctx* h) {
 	h->stage_done = false;
+	h->vis_on_cur = true;
 	h->drv_valid[h->cur] = false;
-	return 0;
 }
-
-// SoA variants for the end-to-end path: host arrays are [NQ][n_cells] (component-major), pinned or not;
-// asynchronous on the compute stream.
-int lfmgpu_upload_q_soa_async(lfmgpu_t h, const void* q, size_t bytes) {
-	TRY(use(h));
-	const size_t es = (size_t)h->prec, n = (size_t)h->n_cells;
-	if (bytes != n * h->NQ * es) return fail("lfmgpu_upload_q_soa_async: expected %zu bytes", n * h->NQ * es);
-	CU(cudaMemcpy2DAsync(h->q[h->cur], h->ncs * es, q, n * es, n * es, (size_t)h->NQ, cudaMemcpyHostToDevice, h->s_main));
-	h->drv_valid[h->cur] = false;
-	return 0;
-}
-int lfmgpu_download_q_soa_async(lfmgpu_t h, void* q, size_t bytes) {
-	TRY(use(h));
-	const size_t es = (size_t)h->prec, n = (size_t)h->n_cells;
-	if (bytes != n * h->NQ * es) return fail("lfmgpu_download_q_soa_async: expected %zu bytes", n * h->NQ * es);
-	CU(cudaMemcpy2DAsync(q, n * es, h->q[h->cur], h->ncs * es, n * es, (size_t)h->NQ, cudaMemcpyDeviceToHost, h->s_main));
-	return 0;
-}
-
-// Pipelined host I/O for back-to-back batches: the upload of the next batch and the download of the previous result run
-// on their own streams, through device staging buffers, while the compute stream advances the current batch.
-//   pipe_in_start(host)  : H2D host -> staging (copy-in stream), once the previous commit has drained the staging buffer
-//   pipe_in_commit()     : compute stream waits for that upload, then staging -> q (device copy)
-//   pipe_out_start()     : compute stream copies q -> out staging, once the previous fetch has drained it
-//   pipe_out_fetch(host) : D2H out staging -> host (copy-out stream)
-namespace {
 int pipe_init(lfmgpu_ctx* h) {
 	if (h->s_in) return 0;
 	const size_t bytes = (size_t)h->NQ * h->n_cells * (size_t)h->prec;
@@ -1768,10 +1843,66 @@ int pipe_init(lfmgpu_ctx* h) {
 	cudaEvent_t* evs[4] = {&h->ev_in_ready, &h->ev_in_free, &h->ev_out_ready, &h->ev_out_free};
 	for (auto* e : evs) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
 	CU(cudaEventRecord(h->ev_in_free, h->s_main));
+	CU(cudaEventRecord(h->ev_in_ready, h->s_in));
 	CU(cudaEventRecord(h->ev_out_free, h->s_out));
+	CU(cudaEventRecord(h->ev_out_ready, h->s_main));
 	return 0;
 }
 }  // namespace
+extern "C" {
+
+int lfmgpu_download(lfmgpu_t h, int field, void* dst, size_t dst_bytes) {
+	TRY(use(h));
+	TRY(lfmgpu_sync(h));
+	return DISPATCH(h, t_download, h, field, dst, dst_bytes);
+}
+
+int lfmgpu_upload_q(lfmgpu_t h, const void* q, size_t bytes) {
+	TRY(use(h));
+	TRY(lfmgpu_sync(h));
+	const size_t es = (size_t)h->prec, n = (size_t)h->n_cells;
+	if (bytes != n * h->NQ * es) return fail("lfmgpu_upload_q: expected %zu bytes", n * h->NQ * es);
+	DevTmp t;
+	CU(cudaMalloc(&t.p, std::max<size_t>(bytes, 16)));
+	CU(cudaMemcpyAsync(t.p, q, bytes, cudaMemcpyHostToDevice, h->s_main));
+	TRY(DISPATCH(h, t_scatter_q, h, t.p, 1, h->s_main));
+	CU(cudaStreamSynchronize(h->s_main));
+	mark_uploaded(h);
+	return 0;
+}
+
+// Component-major variants for the end-to-end path: host arrays are [NQ][n_cells], pinned or not; asynchronous on the
+// compute stream (through the device staging buffers of the pipelined path: the records are filled by a kernel).
+int lfmgpu_upload_q_soa_async(lfmgpu_t h, const void* q, size_t bytes) {
+	TRY(use(h));
+	TRY(pipe_init(h));
+	const size_t es = (size_t)h->prec, n = (size_t)h->n_cells;
+	if (bytes != n * h->NQ * es) return fail("lfmgpu_upload_q_soa_async: expected %zu bytes", n * h->NQ * es);
+	CU(cudaStreamWaitEvent(h->s_main, h->ev_in_ready, 0));   // a pipelined upload still filling the staging buffer
+	CU(cudaMemcpyAsync(h->stage_in, q, bytes, cudaMemcpyHostToDevice, h->s_main));
+	TRY(DISPATCH(h, t_scatter_q, h, h->stage_in, 0, h->s_main));
+	CU(cudaEventRecord(h->ev_in_free, h->s_main));
+	mark_uploaded(h);
+	return 0;
+}
+int lfmgpu_download_q_soa_async(lfmgpu_t h, void* q, size_t bytes) {
+	TRY(use(h));
+	TRY(pipe_init(h));
+	const size_t es = (size_t)h->prec, n = (size_t)h->n_cells;
+	if (bytes != n * h->NQ * es) return fail("lfmgpu_download_q_soa_async: expected %zu bytes", n * h->NQ * es);
+	CU(cudaStreamWaitEvent(h->s_main, h->ev_out_free, 0));
+	TRY(DISPATCH(h, t_gather_q_soa, h, h->stage_out, h->s_main));
+	CU(cudaMemcpyAsync(q, h->stage_out, bytes, cudaMemcpyDeviceToHost, h->s_main));
+	CU(cudaEventRecord(h->ev_out_ready, h->s_main));
+	return 0;
+}
+
+// Pipelined host I/O for back-to-back batches: the upload of the next batch and the download of the previous result run
+// on their own streams, through device staging buffers, while the compute stream advances the current batch.
+//   pipe_in_start(host)  : H2D host -> staging (copy-in stream), once the previous commit has drained the staging buffer
+//   pipe_in_commit()     : compute stream waits for that upload, then staging -> q (device copy)
+//   pipe_out_start()     : compute stream copies q -> out staging, once the previous fetch has drained it
+//   pipe_out_fetch(host) : D2H out staging -> host (copy-out stream)
 int lfmgpu_pipe_in_start(lfmgpu_t h, const void* q, size_t bytes) {
 	TRY(use(h));
 	TRY(pipe_init(h));
@@ -1785,19 +1916,17 @@ int lfmgpu_pipe_in_start(lfmgpu_t h, const void* q, size_t bytes) {
 int lfmgpu_pipe_in_commit(lfmgpu_t h) {
 	TRY(use(h));
 	TRY(pipe_init(h));
-	const size_t es = (size_t)h->prec, n = (size_t)h->n_cells;
 	CU(cudaStreamWaitEvent(h->s_main, h->ev_in_ready, 0));
-	CU(cudaMemcpy2DAsync(h->q[h->cur], h->ncs * es, h->stage_in, n * es, n * es, (size_t)h->NQ, cudaMemcpyDeviceToDevice, h->s_main));
+	TRY(DISPATCH(h, t_scatter_q, h, h->stage_in, 0, h->s_main));
 	CU(cudaEventRecord(h->ev_in_free, h->s_main));
-	h->drv_valid[h->cur] = false;
+	mark_uploaded(h);
 	return 0;
 }
 int lfmgpu_pipe_out_start(lfmgpu_t h) {
 	TRY(use(h));
 	TRY(pipe_init(h));
-	const size_t es = (size_t)h->prec, n = (size_t)h->n_cells;
 	CU(cudaStreamWaitEvent(h->s_main, h->ev_out_free, 0));
-	CU(cudaMemcpy2DAsync(h->stage_out, n * es, h->q[h->cur], h->ncs * es, n * es, (size_t)h->NQ, cudaMemcpyDeviceToDevice, h->s_main));
+	TRY(DISPATCH(h, t_gather_q_soa, h, h->stage_out, h->s_main));
 	CU(cudaEventRecord(h->ev_out_ready, h->s_main));
 	return 0;
 }

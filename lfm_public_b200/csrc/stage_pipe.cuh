@@ -1,0 +1,645 @@
+// Persistent, warp-specialised, TMA-fed RK-stage kernel ("v4"): one_rk_step_M1/_M2 (cfd_v0.cpp:2530/1897) +
+// prepare_for_RKstep (1339) on the record layout (kernels.cuh, Rec<D>).
+//
+// Why: the round-1 tile kernel (k_tile_stage) spends half of its cycles on a serial latency chain per tile -- tile
+// descriptor -> halo cell ids -> 6 624 eight-byte cp.async element copies -> first face constants -- with only two CTAs
+// per SM to hide it (profiles/r2a_stage128_stall_table.txt: 37 % long-scoreboard + 17 % barrier stalls).  Here one CTA per
+// SM lives for the whole launch and splits into
+//   * a PRODUCER warp that runs ahead of the arithmetic: per tile it fills the next free slot of a shared-memory ring with
+//       - the Q and V records of the tile's own cells: two TMA tensor loads (cp.async.bulk.tensor.2d, 128B/64B/32B
+//         hardware swizzle), completion counted in bytes on the slot's `full` mbarrier;
+//       - the records of the halo cells: 16-byte cp.async copies (a halo cell is 12 of them instead of 23 element copies
+//         from 23 different sectors), written with the same swizzle, completion signalled on the same mbarrier
+//         (cp.async.mbarrier.arrive.noinc);
+//     descriptors and halo ids are fetched one tile ahead, so the chain above is off the consumers' critical path;
+//   * two CONSUMER groups of 256 threads that take alternate tiles: wait on `full`, evaluate every face of the tile once
+//     (both sides read with conflict-free 16-byte LDS from the swizzled records: 24 loads per face instead of 46), ordered
+//     gather + sponge + RK update per cell, derived values, and hand the tile's new Q records to the TMA engine as ONE bulk
+//     store (cp.async.bulk.global.shared::cta); then release the slot on its `empty` mbarrier.
+// The arithmetic is device_math.cuh's, in the same order: results are bit-identical to k_tile_stage and to the reference.
+#pragma once
+#include <cuda.h>
+
+#include "tile_kernels.cuh"
+
+namespace lfm {
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+	uint32_t ok;
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+	    "selp.u32 %0, 1, 0, p;\n"
+	    "}"
+	    : "=r"(ok)
+	    : "r"(smem_u32(bar)), "r"(parity)
+	    : "memory");
+	return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+	while (!mbar_try_wait(bar, parity)) {
+	}
+}
+// this thread's earlier cp.async copies arrive on the mbarrier when they have landed (the arrival is pre-counted at init)
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) { asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+// (no "memory" clobber: the producers never touch the destination with ordinary accesses, and volatile asm statements keep
+// their order among themselves -- the mbarrier wait before and the arrive after; this lets the compiler batch the loads of
+// the halo ids of an unrolled copy loop instead of serialising id load -> address -> copy per element)
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src)); }
+// TMA: box of the 2D tensor map at (c0 = value index inside the record, c1 = first cell) -> shared memory, bytes counted on bar
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst_smem), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+	             : "memory");
+}
+// TMA: contiguous shared memory -> global memory (sizes and addresses multiples of 16 bytes)
+__device__ __forceinline__ void bulk_store(void* dst_global, uint32_t src_smem, uint32_t bytes) {
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_global), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+// ---- swizzled records in shared memory -----------------------------------------------------------------------------------
+// A region holds records of B = 32, 64 or 128 bytes at consecutive slots, laid out as the TMA engine writes a box of a
+// tensor map with CU_TENSOR_MAP_SWIZZLE_{32,64,128}B: the 16-byte chunk index (address bits 4..6) is XORed with address
+// bits 7..9 (128B; two bits for 64B, one for 32B).  Regions start on 1024-byte boundaries, so offsets stand for addresses.
+// Eight consecutive slots then cover all 32 banks with any one chunk: 16-byte loads of consecutive cells never conflict.
+__host__ __device__ constexpr uint32_t swz_mask(int record_bytes) { return (uint32_t)(record_bytes - 16) & 0x70u; }
+__device__ __forceinline__ uint32_t swz(uint32_t off, uint32_t mask) { return off ^ ((off >> 3) & mask); }
+
+template <class R> struct Chunk16;
+template <> struct Chunk16<double> {
+	using T = double2;
+	static constexpr int N = 2;
+	static __device__ __forceinline__ void unpack(const T& t, double* d) {
+		d[0] = t.x;
+		d[1] = t.y;
+	}
+	static __device__ __forceinline__ T pack(const double* d) { return make_double2(d[0], d[1]); }
+};
+template <> struct Chunk16<float> {
+	using T = float4;
+	static constexpr int N = 4;
+	static __device__ __forceinline__ void unpack(const T& t, float* d) {
+		d[0] = t.x;
+		d[1] = t.y;
+		d[2] = t.z;
+		d[3] = t.w;
+	}
+	static __device__ __forceinline__ T pack(const float* d) { return make_float4(d[0], d[1], d[2], d[3]); }
+};
+
+// one side of a face in registers, filled by 16-byte loads from the swizzled records of a ring slot
+template <class R, int D> struct RecSide {
+	using RC = Rec<D>;
+	static constexpr bool kHasTrace = (D == 3);
+	R qv[RC::QW];
+	R vv[RC::VW];
+	__device__ __forceinline__ void load_q(const unsigned char* Qs, int slot) {
+		constexpr int QB = RC::QW * (int)sizeof(R);
+		const uint32_t p = swz((uint32_t)slot * QB, swz_mask(QB));
+#pragma unroll
+		for (int j = 0; j < QB / 16; j++) Chunk16<R>::unpack(*reinterpret_cast<const typename Chunk16<R>::T*>(Qs + (p ^ (uint32_t)(j << 4))), qv + j * Chunk16<R>::N);
+	}
+	__device__ __forceinline__ void load_v(const unsigned char* Vs, int slot) {
+		constexpr int VB = RC::VW * (int)sizeof(R);
+		const uint32_t p = swz((uint32_t)slot * VB, swz_mask(VB));
+#pragma unroll
+		for (int j = 0; j < VB / 16; j++) Chunk16<R>::unpack(*reinterpret_cast<const typename Chunk16<R>::T*>(Vs + (p ^ (uint32_t)(j << 4))), vv + j * Chunk16<R>::N);
+	}
+	__device__ __forceinline__ R q(int k) const { return qv[k]; }
+	__device__ __forceinline__ R rho_inv() const { return qv[RC::RHO_INV]; }
+	__device__ __forceinline__ R Rpsi() const { return qv[RC::RPSI]; }
+	__device__ __forceinline__ R aux() const { return qv[RC::AUX]; }
+	__device__ __forceinline__ R dudx(int a, int b) const { return vv[RC::DUDX + a * D + b]; }
+	__device__ __forceinline__ R dTdx(int a) const { return vv[RC::DTDX + a]; }
+	__device__ __forceinline__ R sigmaU(int a) const { return vv[RC::SIGMAU + a]; }
+	__device__ __forceinline__ R trace_neg() const { return vv[D == 3 ? RC::TR : 0]; }
+	__device__ __forceinline__ R tauMC(int, int) const { return R(0); }   // laminar closure only
+};
+
+// what the host passes about the ring (all byte offsets from the 1024-aligned start of dynamic shared memory)
+struct PipeGeom {
+	int n_slots;            // ring depth
+	int box_cells;          // rows of the TMA box = first halo slot
+	int smax;               // slots per region (box_cells + largest halo)
+	int fmax;               // faces per tile (stride of the flux rows)
+	int hmax;               // largest halo
+	uint32_t off_bar;       // full[n_slots], empty[n_slots]
+	uint32_t off_ids;       // [n_slots][hmax] int
+	uint32_t off_out;       // [2][box_cells * QB] un-swizzled Q records of the finished tile (source of the bulk store)
+	uint32_t off_fl;        // [2][NQ][fmax] R face fluxes
+	uint32_t off_slot;      // first ring slot
+	uint32_t slot_bytes;    // Q region + V region (each a multiple of 1024)
+	uint32_t q_bytes;       // Q region
+};
+
+constexpr int kPipeGroupThreads = 256;                      // one consumer group (two warpgroups)
+constexpr int kPipeProducerThreads = 128;                   // one warpgroup: setmaxnreg is a warpgroup-wide instruction
+constexpr int kPipeThreads = 2 * kPipeGroupThreads + kPipeProducerThreads;   // 20 warps: five per scheduler, 96 registers each at launch
+constexpr int kPipeMaxHaloRegs = 8;                         // halo ids warp 0 of the producers prefetches per lane (hmax <= 256)
+// Register budget: five warps per scheduler cap the launch at 96 registers per thread (640 x 96 = 61 440: what the CTA owns
+// for its whole life -- setmaxnreg only moves registers between its warps).  The producer warpgroup gives back all but 32 per
+// thread and the consumers grow to 112: 128 x 32 + 512 x 112 = 61 440.
+constexpr int kPipeProducerRegs = 32, kPipeConsumerRegs = 112;
+static_assert(kPipeProducerThreads * kPipeProducerRegs + 2 * kPipeGroupThreads * kPipeConsumerRegs <= kPipeThreads * 96, "setmaxnreg.inc would wait for registers the CTA does not own");
+
+// Phase C for components [I0, I1) of tile cell lc on the record layout (gather_update of tile_kernels.cuh): the cell's
+// conservatives are read from, and the new ones written back to, its Q record in the ring slot.
+template <class R, int D, int I0, int I1>
+__device__ __forceinline__ void gather_update_rec(const DevMesh<R>& m, const TileView<R>& tv, const TileDesc& td, unsigned char* Qs, const R* fl, int fmax, int lc, bool active, int bar_id, R dt, R Ak,
+                                                  R Bk, int first, int res) {
+	constexpr int NQ = D + 2, QB = Rec<D>::QW * (int)sizeof(R), EPC = Chunk16<R>::N;
+	const int c = td.c0 + (active ? lc : 0);
+	int e[kMaxSlots];
+	R dq[NQ], vinv = R(0), sg = R(0);
+#pragma unroll
+	for (int s = 0; s < kMaxSlots; s++) e[s] = 0;
+#pragma unroll
+	for (int i = 0; i < NQ; i++) dq[i] = R(0);
+	if (active) {
+#pragma unroll
+		for (int s = 0; s < kMaxSlots; s++)
+			if (s < m.F) e[s] = (int)tv.csr_local[(size_t)s * m.n_cells + c];
+		if (!first) {
+#pragma unroll
+			for (int i = I0; i < I1; i++) dq[i] = m.dq[(size_t)i * m.n_cells + c];
+		}
+		vinv = m.vol_inv[c];
+		sg = m.sigma[c];
+	}
+	if (bar_id >= 0) named_bar(bar_id, kPipeGroupThreads);   // every face flux of the tile is in fl (the loads above travel meanwhile)
+	if (!active) return;
+	R RES[NQ];
+#pragma unroll
+	for (int i = I0; i < I1; i++) {
+		dq[i] *= Ak;
+		RES[i] = R(0);
+	}
+#pragma unroll
+	for (int s = 0; s < kMaxSlots; s++) {
+		if (e[s] == 0) break;
+		const bool own = e[s] > 0;
+		const int lfc = (own ? e[s] : -e[s]) - 1;
+#pragma unroll
+		for (int i = I0; i < I1; i++) {
+			const R v = fl[i * fmax + lfc];
+			const R rr = own ? v : -v;
+			if (res) RES[i] += rr;
+			dq[i] += dt * rr * vinv;
+		}
+	}
+	const uint32_t p = swz((uint32_t)lc * QB, swz_mask(QB));
+#pragma unroll
+	for (int i = I0; i < I1; i++) {
+		R* slot_q = reinterpret_cast<R*>(Qs + (p ^ (uint32_t)((i / EPC) << 4))) + (i % EPC);
+		const R cqi = *slot_q;
+		const R target = i == 0 ? m.k.rhoInf : (i == NQ - 1 ? m.k.rhoEInf : m.k.rhoUInf[i > 0 && i < NQ - 1 ? i - 1 : 0]);
+		dq[i] += dt * sg * (target - cqi);
+		m.dq[(size_t)i * m.n_cells + c] = dq[i];
+		*slot_q = cqi + Bk * dq[i];      // only this cell's own threads touch its record after phase B
+		if (res) m.RES[(size_t)i * m.n_cells + c] = RES[i];
+	}
+}
+
+template <class R, int D, int SCHEME>
+__global__ void __launch_bounds__(kPipeThreads, 1)
+    k_stage_pipe(DevMesh<R> m, TileView<R> tv, const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_v, PipeGeom pg, const R* __restrict__ q, R* __restrict__ qn, int tile0,
+                 int n_tiles, R dt, R Ak, R Bk, int first, int res) {
+	using RC = Rec<D>;
+	constexpr int NQ = D + 2, QB = RC::QW * (int)sizeof(R), VB = RC::VW * (int)sizeof(R), CQ = QB / 16, CV = VB / 16;
+	constexpr int GT = kPipeGroupThreads;
+	extern __shared__ unsigned char smem_dyn[];
+	unsigned char* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+	uint64_t* full = reinterpret_cast<uint64_t*>(sm + pg.off_bar);
+	uint64_t* empty = full + pg.n_slots;
+	const int NS = pg.n_slots, G = gridDim.x;
+	const int lane = threadIdx.x & 31;
+
+	if (threadIdx.x == 0) {
+		for (int s = 0; s < NS; s++) {
+			mbar_init(full + s, 1 + kPipeProducerThreads);   // the expect_tx arrival + one cp.async arrival per producer thread
+			mbar_init(empty + s, 1);                         // one elected consumer thread
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+
+	if (threadIdx.x >= 2 * GT) {
+		// ============================ producers (one warpgroup) ===================================================
+		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kPipeProducerRegs));
+		if ((int)blockIdx.x >= n_tiles) return;
+		const int ptid = threadIdx.x - 2 * GT, pwarp = ptid >> 5;
+		int* ids_all = reinterpret_cast<int*>(sm + pg.off_ids);
+		const unsigned char* qsrc = reinterpret_cast<const unsigned char*>(q);
+		const unsigned char* vsrc = reinterpret_cast<const unsigned char*>(m.vis);
+		// of a tile descriptor the producers need the first cell, the halo list and its length (the first 16 bytes)
+		struct Need {
+			int c0, nt, halo_off, nh;
+		};
+		auto need_of = [&](int tile) {
+			const int4 v = *reinterpret_cast<const int4*>(tv.tiles + tile0 + tile);
+			return Need{v.x, v.y, v.z, v.w};
+		};
+		int t = blockIdx.x;
+		Need td = need_of(t);
+		int idr[kPipeMaxHaloRegs];
+#pragma unroll
+		for (int k = 0; k < kPipeMaxHaloRegs; k++) idr[k] = (pwarp == 0 && (lane + 32 * k) < td.nh) ? tv.halo_cell[td.halo_off + lane + 32 * k] : 0;
+		Need tdn = td;
+		if (t + G < n_tiles) tdn = need_of(t + G);
+		for (int i = 0;; i++, t += G) {
+			const int slot = i % NS;
+			const uint32_t use = (uint32_t)(i / NS);
+			int* ids = ids_all + slot * pg.hmax;
+			if (pwarp == 0) {
+#pragma unroll
+				for (int k = 0; k < kPipeMaxHaloRegs; k++)
+					if (lane + 32 * k < td.nh) ids[lane + 32 * k] = idr[k];
+			}
+			named_bar(3, kPipeProducerThreads);   // the halo ids of this tile are in shared memory (the ring of id lists is the producers' own)
+			// the next tile's halo ids and the descriptor after it: in flight while this tile's copies are issued
+			const bool has_next = t + G < n_tiles;
+			Need tdnn = tdn;
+			if (has_next) {
+				if (pwarp == 0) {
+#pragma unroll
+					for (int k = 0; k < kPipeMaxHaloRegs; k++) idr[k] = (lane + 32 * k) < tdn.nh ? tv.halo_cell[tdn.halo_off + lane + 32 * k] : 0;
+				}
+				if (t + 2 * G < n_tiles) tdnn = need_of(t + 2 * G);
+			}
+			mbar_wait(empty + slot, (use & 1u) ^ 1u);   // the consumers have released this slot (passes at once on its first use)
+			unsigned char* Qs = sm + pg.off_slot + (size_t)slot * pg.slot_bytes;
+			unsigned char* Vs = Qs + pg.q_bytes;
+			if (ptid == 0) {
+				mbar_arrive_expect_tx(full + slot, (uint32_t)pg.box_cells * (QB + VB));
+				tma_load_2d(smem_u32(Qs), &map_q, 0, td.c0, full + slot);
+				tma_load_2d(smem_u32(Vs), &map_v, 0, td.c0, full + slot);
+			}
+			const uint32_t q0 = smem_u32(Qs), v0 = smem_u32(Vs);
+			const int nq = td.nh * CQ, nv = td.nh * CV;
+#pragma unroll 4
+			for (int it = ptid; it < nq; it += kPipeProducerThreads) {
+				const int cell = it / CQ, ch = it % CQ;
+				const size_t x = (size_t)ids[cell];
+				cp_async16(q0 + swz((uint32_t)(pg.box_cells + cell) * QB + (uint32_t)ch * 16u, swz_mask(QB)), qsrc + x * QB + ch * 16);
+			}
+#pragma unroll 4
+			for (int it = ptid; it < nv; it += kPipeProducerThreads) {
+				const int cell = it / CV, ch = it % CV;
+				const size_t x = (size_t)ids[cell];
+				cp_async16(v0 + swz((uint32_t)(pg.box_cells + cell) * VB + (uint32_t)ch * 16u, swz_mask(VB)), vsrc + x * VB + ch * 16);
+			}
+			cp_async_mbar_arrive_noinc(full + slot);
+			if (!has_next) break;
+			td = tdn;
+			tdn = tdnn;
+		}
+		asm volatile("cp.async.wait_all;" ::: "memory");
+		return;
+	}
+
+	// ============================ consumers ====================================================================
+	asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kPipeConsumerRegs));
+	if ((int)blockIdx.x >= n_tiles) return;
+	const int g = threadIdx.x / GT;           // consumer group
+	const int tid = threadIdx.x % GT;         // thread inside the group
+	const int bar_id = 1 + g;
+	R* fl = reinterpret_cast<R*>(sm + pg.off_fl) + (size_t)g * NQ * pg.fmax;
+	unsigned char* outb = sm + pg.off_out + (size_t)g * pg.box_cells * QB;
+	const int fmax = pg.fmax;
+	int t = blockIdx.x + g * G;
+	if (t >= n_tiles) return;
+	TileDesc td = tv.tiles[tile0 + t];
+	FaceIn<R, D> cur;
+	if (tid < td.nfo + td.ninc) fetch_face<R, D, SCHEME>(tv, (size_t)td.f_off + tid, cur);
+	for (int i = g;; i += 2, t += 2 * G) {
+		const int slot = i % NS;
+		const uint32_t use = (uint32_t)(i / NS);
+		const bool has_next = t + 2 * G < n_tiles;
+		TileDesc tdn = td;
+		if (has_next) tdn = tv.tiles[tile0 + t + 2 * G];   // in flight during this tile
+		unsigned char* Qs = sm + pg.off_slot + (size_t)slot * pg.slot_bytes;
+		const unsigned char* Vs = Qs + pg.q_bytes;
+		const int nf = td.nfo + td.ninc;
+		// The two groups take alternate tiles, so this group can reach a slot while its previous user (a tile of the OTHER group)
+		// still waits for its data: one phase behind, which the parity of `full` alone cannot tell from "already filled again".
+		// The slot's previous fill was issued before this group's last tile was, so the slot is never further behind than that:
+		// wait until its previous user has released it (phase use-1 of `empty`; from then on `full` is either filling or
+		// filled for THIS use, nothing else), then for this fill.
+		if (use) mbar_wait(empty + slot, (use - 1u) & 1u);
+		mbar_wait(full + slot, use & 1u);
+
+		// ---- B: every face of the tile once ----------------------------------------------------------------
+		for (int lf = tid; lf < nf; lf += GT) {
+			FaceIn<R, D> nxt;
+			if (lf + GT < nf) fetch_face<R, D, SCHEME>(tv, (size_t)td.f_off + lf + GT, nxt);
+			const int lo = (int)(cur.idx & 0xffffu), ln = (int)((cur.idx >> 16) & 0x7fffu);
+			const bool ghost = (cur.idx >> 31) != 0;
+			R dv[D];
+#pragma unroll
+			for (int k = 0; k < D; k++) dv[k] = R(0);
+			if (ghost) {
+				const int f = tv.f_gface[(size_t)td.f_off + lf];
+#pragma unroll
+				for (int k = 0; k < D; k++) dv[k] = m.d[k * m.nfs + f];
+			}
+			RecSide<R, D> c, n;
+			c.load_q(Qs, lo);
+			n.load_q(Qs, ln);
+			c.load_v(Vs, lo);
+			n.load_v(Vs, ln);
+			R rhs[NQ];
+			face_flux<R, D, SCHEME>(m.k, c, n, cur.g, ghost, dv, rhs);
+#pragma unroll
+			for (int k = 0; k < NQ; k++) fl[k * fmax + lf] = rhs[k];
+			if (lf + GT < nf) cur = nxt;
+		}
+
+		// ---- C: ordered gather, sponge, RK update (components split between the halves of the group when the tile leaves
+		// half of it idle; the ordered sums are per component, so the split changes no result) -------------------
+		const bool split = 2 * td.nt <= GT;
+		const int rounds = split ? 1 : (td.nt + GT - 1) / GT;
+		for (int r = 0; r < rounds; r++) {
+			constexpr int H = (NQ + 1) / 2;
+			const int part = split ? (tid >= GT / 2 ? 1 : 0) : 2;
+			const int lc = split ? tid - (part ? GT / 2 : 0) : tid + r * GT;
+			const bool active = lc < td.nt;
+			// the barrier that closes phase B sits inside (a named barrier: defined for any call site); later rounds need none
+			const int bid = r == 0 ? bar_id : -1;
+			if (part == 0)
+				gather_update_rec<R, D, 0, H>(m, tv, td, Qs, fl, fmax, lc, active, bid, dt, Ak, Bk, first, res);
+			else if (part == 1)
+				gather_update_rec<R, D, H, NQ>(m, tv, td, Qs, fl, fmax, lc, active, bid, dt, Ak, Bk, first, res);
+			else
+				gather_update_rec<R, D, 0, NQ>(m, tv, td, Qs, fl, fmax, lc, active, bid, dt, Ak, Bk, first, res);
+		}
+		// the first face of this group's next tile travels during the epilogue and the wait for its slot
+		if (has_next && tid < tdn.nfo + tdn.ninc) fetch_face<R, D, SCHEME>(tv, (size_t)tdn.f_off + tid, cur);
+		if (tid == 0) bulk_wait_read0();   // the previous tile's bulk store has read the staging buffer
+		named_bar(bar_id, GT);              // all new conservatives are in the slot; the staging buffer is free
+
+		// ---- derived values of the new state, the finished Q records -> staging (un-swizzled) -> one bulk store ----
+		for (int lc = tid; lc < td.nt; lc += GT) {
+			RecSide<R, D> s;
+			s.load_q(Qs, lc);
+			CellState<R, D> cs;
+#pragma unroll
+			for (int k = 0; k < NQ; k++) cs.q[k] = s.qv[k];
+			derive_state<R, D, SCHEME>(m.k, cs);
+			s.qv[RC::RHO_INV] = cs.rho_inv;
+			s.qv[RC::RPSI] = cs.Rpsi;
+			s.qv[RC::AUX] = cs.aux;
+			if (RC::AUX + 1 < RC::QW) s.qv[RC::QW - 1] = R(0);
+#pragma unroll
+			for (int j = 0; j < CQ; j++) *reinterpret_cast<typename Chunk16<R>::T*>(outb + (size_t)lc * QB + j * 16) = Chunk16<R>::pack(s.qv + j * Chunk16<R>::N);
+		}
+		fence_proxy_async();   // the staging writes above become visible to the TMA engine
+		named_bar(bar_id, GT);
+		if (tid == 0) {
+			bulk_store(reinterpret_cast<unsigned char*>(qn) + (size_t)td.c0 * QB, smem_u32(outb), (uint32_t)td.nt * QB);
+			bulk_commit();
+			mbar_arrive(empty + slot);   // every thread of the group is past its last access to the slot
+		}
+		if (!has_next) break;
+		td = tdn;
+	}
+	if (tid == 0) bulk_wait0();   // the last store has left shared memory and is performed before the CTA exits
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// calc_VIS (cfd_v0.cpp:1744-1860) as a persistent, TMA-fed kernel: same producer / ring as k_stage_pipe, with
+//   * per slot: the Q records of tile + halo (TMA box + 16-byte cp.async, swizzled) and the tile's slice of the tile-ordered
+//     face tables S[D], w, idx (contiguous per tile: D + 2 linear bulk copies, cp.async.bulk.shared::cta.global);
+//   * four consumer groups of 128 threads on alternate tiles: one thread per cell walks the cell's faces in ascending face
+//     id (the reference's summation order), forms dudx / dTdx / sigmaU / tr and writes the cell's V record into the slot's
+//     (by then dead) Q region, from where ONE bulk store takes the tile's V records to HBM.
+// ---------------------------------------------------------------------------------------------------------------------
+struct GradGeom {
+	int n_slots, box_cells, smax, fmax, hmax;
+	uint32_t off_bar, off_ids, off_slot;
+	uint32_t slot_bytes;    // Q region (also the V staging of the finished tile) + face region
+	uint32_t q_bytes;       // Q region: max(smax * QB, box_cells * VB) rounded up to 1024
+};
+constexpr int kGradGroupThreads = 128, kGradGroups = 4;
+constexpr int kGradThreadsTotal = kGradGroups * kGradGroupThreads + kPipeProducerThreads;
+
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <class R, int D>
+__global__ void __launch_bounds__(kGradThreadsTotal, 1)
+    k_grad_pipe(DevMesh<R> m, TileView<R> tv, const __grid_constant__ CUtensorMap map_q, GradGeom pg, const R* __restrict__ q, int tile0, int n_tiles) {
+	using RC = Rec<D>;
+	constexpr int QB = RC::QW * (int)sizeof(R), VB = RC::VW * (int)sizeof(R), CQ = QB / 16, CVC = VB / 16;
+	constexpr int GT = kGradGroupThreads, NG = kGradGroups;
+	extern __shared__ unsigned char smem_dyn[];
+	unsigned char* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+	uint64_t* full = reinterpret_cast<uint64_t*>(sm + pg.off_bar);
+	uint64_t* empty = full + pg.n_slots;
+	const int NS = pg.n_slots, G = gridDim.x;
+	const int lane = threadIdx.x & 31;
+	const uint32_t frow = (uint32_t)pg.fmax * (uint32_t)sizeof(R);   // one face row: S_k or w
+
+	if (threadIdx.x == 0) {
+		for (int s = 0; s < NS; s++) {
+			mbar_init(full + s, 1 + kPipeProducerThreads);
+			mbar_init(empty + s, 1);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	if ((int)blockIdx.x >= n_tiles) return;
+
+	if (threadIdx.x >= NG * GT) {
+		// ============================ producers ==================================================================
+		const int ptid = threadIdx.x - NG * GT, pwarp = ptid >> 5;
+		int* ids_all = reinterpret_cast<int*>(sm + pg.off_ids);
+		const unsigned char* qsrc = reinterpret_cast<const unsigned char*>(q);
+		struct Need {
+			int c0, halo_off, nh, f_off, nf;
+		};
+		auto need_of = [&](int tile) {
+			const TileDesc d = tv.tiles[tile0 + tile];
+			return Need{d.c0, d.halo_off, d.nh, d.f_off, d.nfo + d.ninc};
+		};
+		int t = blockIdx.x;
+		Need td = need_of(t);
+		int idr[kPipeMaxHaloRegs];
+#pragma unroll
+		for (int k = 0; k < kPipeMaxHaloRegs; k++) idr[k] = (pwarp == 0 && (lane + 32 * k) < td.nh) ? tv.halo_cell[td.halo_off + lane + 32 * k] : 0;
+		Need tdn = td;
+		if (t + G < n_tiles) tdn = need_of(t + G);
+		for (int i = 0;; i++, t += G) {
+			const int slot = i % NS;
+			const uint32_t use = (uint32_t)(i / NS);
+			int* ids = ids_all + slot * pg.hmax;
+			if (pwarp == 0) {
+#pragma unroll
+				for (int k = 0; k < kPipeMaxHaloRegs; k++)
+					if (lane + 32 * k < td.nh) ids[lane + 32 * k] = idr[k];
+			}
+			named_bar(1 + NG, kPipeProducerThreads);
+			const bool has_next = t + G < n_tiles;
+			Need tdnn = tdn;
+			if (has_next) {
+				if (pwarp == 0) {
+#pragma unroll
+					for (int k = 0; k < kPipeMaxHaloRegs; k++) idr[k] = (lane + 32 * k) < tdn.nh ? tv.halo_cell[tdn.halo_off + lane + 32 * k] : 0;
+				}
+				if (t + 2 * G < n_tiles) tdnn = need_of(t + 2 * G);
+			}
+			mbar_wait(empty + slot, (use & 1u) ^ 1u);
+			unsigned char* Qs = sm + pg.off_slot + (size_t)slot * pg.slot_bytes;
+			unsigned char* Fs = Qs + pg.q_bytes;
+			if (ptid == 0) {
+				// the tile's slice of the face tables starts on a 16-byte boundary (the plan pads f_off to a multiple of 4) and is
+				// copied in whole 16-byte units (the tables are padded behind the last tile)
+				const uint32_t nf4 = (uint32_t)(td.nf + 3) & ~3u;
+				mbar_arrive_expect_tx(full + slot, (uint32_t)pg.box_cells * QB + nf4 * (uint32_t)((D + 1) * sizeof(R) + 4));
+				tma_load_2d(smem_u32(Qs), &map_q, 0, td.c0, full + slot);
+				if (nf4) {
+#pragma unroll
+					for (int k = 0; k < D; k++) bulk_load(smem_u32(Fs) + (uint32_t)k * frow, tv.fS + (size_t)k * tv.T + td.f_off, nf4 * (uint32_t)sizeof(R), full + slot);
+					bulk_load(smem_u32(Fs) + (uint32_t)D * frow, tv.fw + td.f_off, nf4 * (uint32_t)sizeof(R), full + slot);
+					bulk_load(smem_u32(Fs) + (uint32_t)(D + 1) * frow, tv.f_idx + td.f_off, nf4 * 4u, full + slot);
+				}
+			}
+			const uint32_t q0 = smem_u32(Qs);
+			const int nq = td.nh * CQ;
+#pragma unroll 4
+			for (int it = ptid; it < nq; it += kPipeProducerThreads) {
+				const int cell = it / CQ, ch = it % CQ;
+				const size_t x = (size_t)ids[cell];
+				cp_async16(q0 + swz((uint32_t)(pg.box_cells + cell) * QB + (uint32_t)ch * 16u, swz_mask(QB)), qsrc + x * QB + ch * 16);
+			}
+			cp_async_mbar_arrive_noinc(full + slot);
+			if (!has_next) break;
+			td = tdn;
+			tdn = tdnn;
+		}
+		asm volatile("cp.async.wait_all;" ::: "memory");
+		return;
+	}
+
+	// ============================ consumers ====================================================================
+	const int g = threadIdx.x / GT, tid = threadIdx.x % GT;
+	const int bar_id = 1 + g;
+	int t = blockIdx.x + g * G;
+	if (t >= n_tiles) return;
+	for (int i = g;; i += NG, t += NG * G) {
+		const int slot = i % NS;
+		const uint32_t use = (uint32_t)(i / NS);
+		const bool has_next = t + NG * G < n_tiles;
+		const TileDesc td = tv.tiles[tile0 + t];
+		unsigned char* Qs = sm + pg.off_slot + (size_t)slot * pg.slot_bytes;
+		const unsigned char* Fs = Qs + pg.q_bytes;
+		const R* fg = reinterpret_cast<const R*>(Fs);                                         // [D+1][fmax]: S, w
+		const uint32_t* fi = reinterpret_cast<const uint32_t*>(Fs + (size_t)(D + 1) * frow);  // [fmax]
+		const int fmax = pg.fmax;
+		if (use) mbar_wait(empty + slot, (use - 1u) & 1u);   // see k_stage_pipe: the groups run up to NG - 1 tiles apart (NS >= NG)
+		// one thread per cell (the host launches this kernel for tiles of at most GT cells)
+		const int lc = tid;
+		const bool active = lc < td.nt;
+		const int c = td.c0 + (active ? lc : 0);
+		// what the gather needs from global memory, requested before the wait
+		int e[kMaxSlots];
+		R vinv = R(0);
+#pragma unroll
+		for (int s = 0; s < kMaxSlots; s++) e[s] = (active && s < m.F) ? (int)tv.csr_local[(size_t)s * m.n_cells + c] : 0;
+		if (active) vinv = m.vol_inv[c];
+		mbar_wait(full + slot, use & 1u);
+		R rec[RC::VW];
+		if (active) {
+			RecSide<R, D> own;
+			own.load_q(Qs, lc);
+			R cU[D];
+#pragma unroll
+			for (int k = 0; k < D; k++) cU[k] = own.q(k + 1) * own.rho_inv();
+			const R c_Rpsi = own.Rpsi();
+			R dudx[D][D], dTdx[D], sigmaU[D];
+#pragma unroll
+			for (int a = 0; a < D; a++) {
+				dTdx[a] = R(0);
+#pragma unroll
+				for (int b = 0; b < D; b++) dudx[a][b] = R(0);
+			}
+#pragma unroll
+			for (int s = 0; s < kMaxSlots; s++) {
+				if (e[s] == 0) break;
+				const bool is_own = e[s] > 0;
+				const int lf = (is_own ? e[s] : -e[s]) - 1;
+				const uint32_t idx = fi[lf];
+				const int lo = is_own ? (int)((idx >> 16) & 0x7fffu) : (int)(idx & 0xffffu);   // the other side
+				RecSide<R, D> oth;
+				oth.load_q(Qs, lo);
+				R oU[D];
+#pragma unroll
+				for (int k = 0; k < D; k++) oU[k] = oth.q(k + 1) * oth.rho_inv();
+				const R o_Rpsi = oth.Rpsi();
+				const R w = fg[D * fmax + lf];
+				R face_U[D], face_T, sov[D];
+				if (is_own) {
+					grad_face_values<R, D>(m.k, w, cU, c_Rpsi, oU, o_Rpsi, face_U, face_T);
+#pragma unroll
+					for (int a = 0; a < D; a++) sov[a] = fg[a * fmax + lf] * vinv;
+				} else {
+					grad_face_values<R, D>(m.k, w, oU, o_Rpsi, cU, c_Rpsi, face_U, face_T);
+#pragma unroll
+					for (int a = 0; a < D; a++) sov[a] = -fg[a * fmax + lf] * vinv;
+				}
+#pragma unroll
+				for (int a = 0; a < D; a++) {
+#pragma unroll
+					for (int b = 0; b < D; b++) dudx[a][b] += face_U[a] * sov[b];
+					dTdx[a] += face_T * sov[a];
+				}
+			}
+			// the tau / sigmaU block of calc_VIS (U = rhoU / rho: a true division, cfd_v0.cpp:1806-1857)
+			R Ud[D], tau[D][D];
+#pragma unroll
+			for (int a = 0; a < D; a++) Ud[a] = own.q(a + 1) / own.q(0);
+			stress<R, D>(m.k, dudx, tau);
+#pragma unroll
+			for (int a = 0; a < D; a++) sigmaU[a] = dotD<R, D>(Ud, tau[a]);
+#pragma unroll
+			for (int k = 0; k < RC::VW; k++) rec[k] = R(0);
+#pragma unroll
+			for (int a = 0; a < D; a++) {
+#pragma unroll
+				for (int b = 0; b < D; b++) rec[RC::DUDX + a * D + b] = dudx[a][b];
+				rec[RC::DTDX + a] = dTdx[a];
+				rec[RC::SIGMAU + a] = sigmaU[a];
+			}
+			if (D == 3) rec[RC::TR] = dudx_trace_neg<R, D>(&dudx[0][0]);
+		}
+		named_bar(bar_id, GT);   // every thread of the group has read what it needs of the Q region: it becomes the V staging
+		if (active) {
+#pragma unroll
+			for (int j = 0; j < CVC; j++) *reinterpret_cast<typename Chunk16<R>::T*>(Qs + (size_t)lc * VB + j * 16) = Chunk16<R>::pack(rec + j * Chunk16<R>::N);
+		}
+		fence_proxy_async();
+		named_bar(bar_id, GT);
+		if (tid == 0) {
+			bulk_store(reinterpret_cast<unsigned char*>(m.vis) + (size_t)td.c0 * VB, smem_u32(Qs), (uint32_t)td.nt * VB);
+			bulk_commit();
+			bulk_wait_read0();   // the slot may be refilled once the store has read it
+			mbar_arrive(empty + slot);
+		}
+		if (!has_next) break;
+	}
+	if (tid == 0) bulk_wait0();
+}
+
+}  // namespace lfm

@@ -40,7 +40,8 @@ struct TileDesc {
 	int c0, nt;          // first cell, number of cells
 	int halo_off, nh;    // halo cells: halo_cell[halo_off .. +nh)
 	int f_off, nfo;      // tile faces: tables[f_off .. f_off+nfo+ninc), own faces first
-	int ninc, pad;
+	int ninc, hb;        // hb: staged index of the first halo cell (own cells are staged at [0, nt), halo cells at [hb, hb + nh);
+	                     // hb = the submesh's tile size, so that a fixed-height TMA box of own cells never lands on a halo slot)
 };
 
 template <class R> struct TileView {
@@ -53,8 +54,6 @@ template <class R> struct TileView {
 	size_t T;                        // stride of the face tables
 	const int16_t* csr_local;        // [F][n_cells] +-(tile-local face index + 1), ascending mesh face id, 0-padded
 	int smax, fmax;                  // shared-memory strides of this launch (staged cells, faces)
-	const int* staged_cell;          // [n_tiles][kFixedSmax] global cell id of every staged slot (own cells, then halo; -1 padding):
-	                                 // lets a CTA issue its copies without waiting for its descriptor (EARLY kernels); may be null
 };
 
 // per-face constants (make_geo) computed once on the device with the same expressions the flux loops use
@@ -108,6 +107,7 @@ template <int D> struct StagedLayout {
 
 // a side of a face staged in shared memory (SoA rows of stride smax); values are loaded where they are used
 template <class R, int D> struct SmemSide {
+	static constexpr bool kHasTrace = false;
 	const R* st;
 	int smax, i;
 	using L = StagedLayout<D>;
@@ -176,7 +176,8 @@ __device__ __forceinline__ void cp_async_wait_all() {
 constexpr int kFixedSmax = 320, kFixedFmax = 480;
 
 template <class R, int D, int NT, int SMAX = 0, int FMAX = 0, int LES = 0>
-__global__ void __launch_bounds__(NT) k_tile_grad(DevMesh<R> m, TileView<R> tv, const R* __restrict__ q, const R* __restrict__ drv, int tile0) {
+__global__ void __launch_bounds__(NT) k_tile_grad(DevMesh<R> m, TileView<R> tv, const R* __restrict__ q, int tile0) {
+	constexpr int QW = Rec<D>::QW;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int smax = SMAX ? SMAX : tv.smax, fmax = FMAX ? FMAX : tv.fmax;
 	R* pr = reinterpret_cast<R*>(smem_raw);      // [D+2][smax]: rhoU, 1/rho, Rpsi
@@ -185,12 +186,13 @@ __global__ void __launch_bounds__(NT) k_tile_grad(DevMesh<R> m, TileView<R> tv, 
 	const TileDesc td = tv.tiles[tile0 + blockIdx.x];
 	const int ns = td.nt + td.nh;
 	const int nf = td.nfo + td.ninc;
-	for (int i = threadIdx.x; i < ns; i += NT) {
-		const int x = i < td.nt ? td.c0 + i : tv.halo_cell[td.halo_off + i - td.nt];
+	for (int j = threadIdx.x; j < ns; j += NT) {
+		const int x = j < td.nt ? td.c0 + j : tv.halo_cell[td.halo_off + j - td.nt];
+		const int i = j < td.nt ? j : td.hb + j - td.nt;   // staged index
 #pragma unroll
-		for (int k = 0; k < D; k++) cp_async_elem(pr + k * smax + i, q + (size_t)(k + 1) * m.ncs + x);
-		cp_async_elem(pr + D * smax + i, drv + x);
-		cp_async_elem(pr + (D + 1) * smax + i, drv + m.ncs + x);
+		for (int k = 0; k < D; k++) cp_async_elem(pr + k * smax + i, q + (size_t)x * QW + k + 1);
+		cp_async_elem(pr + D * smax + i, q + (size_t)x * QW + Rec<D>::RHO_INV);
+		cp_async_elem(pr + (D + 1) * smax + i, q + (size_t)x * QW + Rec<D>::RPSI);
 	}
 	for (int lf = threadIdx.x; lf < nf; lf += NT) {
 		const size_t j = (size_t)td.f_off + lf;
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(NT) k_tile_grad(DevMesh<R> m, TileView<R> tv, 
 		for (int s = 0; s < kMaxSlots; s++) e0[s] = s < m.F ? (int)tv.csr_local[(size_t)s * m.n_cells + c] : 0;
 		vinv0 = m.vol_inv[c];
 #pragma unroll
-		for (int k = 0; k < D + 1; k++) cq0[k] = q[k * m.ncs + c];
+		for (int k = 0; k < D + 1; k++) cq0[k] = q[(size_t)c * QW + k];
 	}
 	cp_async_wait_all();
 	__syncthreads();
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(NT) k_tile_grad(DevMesh<R> m, TileView<R> tv, 
 			for (int s = 0; s < kMaxSlots; s++) e[s] = s < m.F ? (int)tv.csr_local[(size_t)s * m.n_cells + c] : 0;
 			vinv = m.vol_inv[c];
 #pragma unroll
-			for (int k = 0; k < D + 1; k++) cq[k] = q[k * m.ncs + c];
+			for (int k = 0; k < D + 1; k++) cq[k] = q[(size_t)c * QW + k];
 		}
 		R cU[D];
 		{
@@ -283,13 +285,7 @@ __global__ void __launch_bounds__(NT) k_tile_grad(DevMesh<R> m, TileView<R> tv, 
 		stress<R, D>(m.k, dudx, tau);
 #pragma unroll
 		for (int i = 0; i < D; i++) sigmaU[i] = dotD<R, D>(Ud, tau[i]);
-#pragma unroll
-		for (int i = 0; i < D; i++) {
-#pragma unroll
-			for (int j = 0; j < D; j++) m.dudx[(size_t)(i * D + j) * m.ncs + c] = dudx[i][j];
-			m.dTdx[(size_t)i * m.ncs + c] = dTdx[i];
-			m.sigmaU[(size_t)i * m.ncs + c] = sigmaU[i];
-		}
+		store_vis_record<R, D>(m.vis, (size_t)c, dudx, dTdx, sigmaU);
 		if (LES) {
 			R tauMC[D][D];
 			tauMC_smagorinsky<R, D>(m.k, m.smag_c[c], dudx, tauMC);
@@ -376,50 +372,37 @@ __device__ __forceinline__ void gather_update(const DevMesh<R>& m, const TileVie
 		dq[i] += dt * sg * (target - cqi);
 		m.dq[(size_t)i * m.n_cells + c] = dq[i];
 		const R qi = cqi + Bk * dq[i];
-		qn[i * m.ncs + c] = qi;
+		qn[(size_t)c * Rec<D>::QW + i] = qi;
 		st[i * smax + lc] = qi;      // only this cell's own threads touch these slots after phase B
 		if (res) m.RES[(size_t)i * m.n_cells + c] = RES[i];
 	}
 }
 
 // EXTRA: rows staged on top of StagedLayout::NS -- 0 none, 1 tauMC (Smagorinsky closure), 2 the minmod gradients of solver 2 (M2-AUSM)
-// EARLY (compile-time strides only): the staged cell ids come from the fixed-pitch table tv.staged_cell, so the copies are
-// two dependent round trips away from the kernel's start (ids, data) instead of three (descriptor, halo ids, data).
-template <class R, int D, int SCHEME, int NT, int MINB, int SMAX = 0, int FMAX = 0, int EXTRA = 0, int EARLY = 0>
+template <class R, int D, int SCHEME, int NT, int MINB, int SMAX = 0, int FMAX = 0, int EXTRA = 0>
 __global__ void __launch_bounds__(NT, MINB)
-    k_tile_stage(DevMesh<R> m, TileView<R> tv, const R* __restrict__ q, const R* __restrict__ drv, R* __restrict__ qn, R* __restrict__ drvn, int tile0, R dt, R Ak, R Bk, int first, int res) {
+    k_tile_stage(DevMesh<R> m, TileView<R> tv, const R* __restrict__ q, R* __restrict__ qn, int tile0, R dt, R Ak, R Bk, int first, int res) {
 	using L = StagedLayout<D>;
-	constexpr int NQ = D + 2;
+	constexpr int NQ = D + 2, QW = Rec<D>::QW, VW = Rec<D>::VW;
 	static_assert(NT % 64 == 0, "phase C splits the CTA into two halves of whole warps (a barrier sits inside each half's code path)");
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int smax = SMAX ? SMAX : tv.smax, fmax = FMAX ? FMAX : tv.fmax;
 	R* st = reinterpret_cast<R*>(smem_raw);      // [NS (+D*D)][smax]
 	R* fl = st + (size_t)L::rows(EXTRA) * smax;   // [NQ][fmax]
-	static_assert(!EARLY || SMAX > 0, "the staged-cell table has the pitch of the compile-time strides");
 	const TileDesc td = tv.tiles[tile0 + blockIdx.x];
-	const int ns = EARLY ? SMAX : td.nt + td.nh;
+	const int ns = td.nt + td.nh;
 	const int nf = td.nfo + td.ninc;
 
 	// ---- A: request the cell states (asynchronous copies, no registers) ----------------------------------
-	for (int i = threadIdx.x; i < ns; i += NT) {
-		int x;
-		if (EARLY) {
-			x = tv.staged_cell[(size_t)(tile0 + blockIdx.x) * SMAX + i];
-			if (x < 0) continue;
-		} else {
-			x = i < td.nt ? td.c0 + i : tv.halo_cell[td.halo_off + i - td.nt];
-		}
+	for (int j = threadIdx.x; j < ns; j += NT) {
+		const int x = j < td.nt ? td.c0 + j : tv.halo_cell[td.halo_off + j - td.nt];
+		const int i = j < td.nt ? j : td.hb + j - td.nt;   // staged index
+		// the staged rows [0, NS) are the values of the cell's Q record (q | 1/rho, Rpsi, aux) followed by its V record
+		// (dudx | dTdx | sigmaU): StagedLayout and Rec order them alike
 #pragma unroll
-		for (int k = 0; k < NQ; k++) cp_async_elem(st + k * smax + i, q + (size_t)k * m.ncs + x);
+		for (int k = 0; k < NQ + 3; k++) cp_async_elem(st + k * smax + i, q + (size_t)x * QW + (k < NQ ? k : Rec<D>::RHO_INV + k - NQ));
 #pragma unroll
-		for (int k = 0; k < 3; k++) cp_async_elem(st + (L::RHO_INV + k) * smax + i, drv + (size_t)k * m.ncs + x);
-#pragma unroll
-		for (int k = 0; k < D * D; k++) cp_async_elem(st + (L::DUDX + k) * smax + i, m.dudx + (size_t)k * m.ncs + x);
-#pragma unroll
-		for (int k = 0; k < D; k++) {
-			cp_async_elem(st + (L::DTDX + k) * smax + i, m.dTdx + (size_t)k * m.ncs + x);
-			cp_async_elem(st + (L::SIGMAU + k) * smax + i, m.sigmaU + (size_t)k * m.ncs + x);
-		}
+		for (int k = 0; k < D * D + 2 * D; k++) cp_async_elem(st + (L::DUDX + k) * smax + i, m.vis + (size_t)x * VW + k);
 		if (EXTRA == 1) {
 #pragma unroll
 			for (int k = 0; k < D * D; k++) cp_async_elem(st + (L::TAUMC + k) * smax + i, m.tauMC + (size_t)k * m.ncs + x);
@@ -488,224 +471,11 @@ __global__ void __launch_bounds__(NT, MINB)
 #pragma unroll
 		for (int i = 0; i < NQ; i++) s.q[i] = st[i * smax + lc];
 		derive_state<R, D, SCHEME>(m.k, s);
-		const int c = td.c0 + lc;
-		drvn[c] = s.rho_inv;
-		drvn[m.ncs + c] = s.Rpsi;
-		drvn[2 * m.ncs + c] = s.aux;
+		R* rec = qn + (size_t)(td.c0 + lc) * QW;
+		rec[Rec<D>::RHO_INV] = s.rho_inv;
+		rec[Rec<D>::RPSI] = s.Rpsi;
+		rec[Rec<D>::AUX] = s.aux;
 	}
-}
-
-// gather_update with compile-time strides and a hook that runs right behind the CTA barrier closing phase B (the
-// persistent kernel issues the next tile's copies there): same arithmetic as gather_update.
-template <class R, int D, int I0, int I1, int SMAX, int FMAX, class Hook>
-__device__ __forceinline__ void gather_update_p(const DevMesh<R>& m, const TileView<R>& tv, const TileDesc& td, R* sq, const R* fl, R* __restrict__ qn, int lc, bool active, bool sync, bool has_next,
-                                                Hook hook, R dt, R Ak, R Bk, int first, int res) {
-	constexpr int NQ = D + 2;
-	const int c = td.c0 + (active ? lc : 0);
-	int e[kMaxSlots];
-	R dq[NQ], vinv = R(0), sg = R(0);
-#pragma unroll
-	for (int s = 0; s < kMaxSlots; s++) e[s] = 0;
-#pragma unroll
-	for (int i = 0; i < NQ; i++) dq[i] = R(0);
-	if (active) {
-#pragma unroll
-		for (int s = 0; s < kMaxSlots; s++)
-			if (s < m.F) e[s] = (int)tv.csr_local[(size_t)s * m.n_cells + c];
-		if (!first) {
-#pragma unroll
-			for (int i = I0; i < I1; i++) dq[i] = m.dq[(size_t)i * m.n_cells + c];
-		}
-		vinv = m.vol_inv[c];
-		sg = m.sigma[c];
-	}
-	if (sync) {
-		asm volatile("cp.async.wait_group 0;" ::: "memory");   // the descriptor fetched two tiles ahead is in place
-		__syncthreads();
-		if (has_next) hook();
-		asm volatile("cp.async.commit_group;" ::: "memory");
-	}
-	if (!active) return;
-	R RES[NQ];
-#pragma unroll
-	for (int i = I0; i < I1; i++) {
-		dq[i] *= Ak;
-		RES[i] = R(0);
-	}
-#pragma unroll
-	for (int s = 0; s < kMaxSlots; s++) {
-		if (e[s] == 0) break;
-		const bool own = e[s] > 0;
-		const int lfc = (own ? e[s] : -e[s]) - 1;
-#pragma unroll
-		for (int i = I0; i < I1; i++) {
-			const R v = fl[i * FMAX + lfc];
-			const R rr = own ? v : -v;
-			if (res) RES[i] += rr;
-			dq[i] += dt * rr * vinv;
-		}
-	}
-#pragma unroll
-	for (int i = I0; i < I1; i++) {
-		const R cqi = sq[i * SMAX + lc];
-		const R target = i == 0 ? m.k.rhoInf : (i == NQ - 1 ? m.k.rhoEInf : m.k.rhoUInf[i > 0 && i < NQ - 1 ? i - 1 : 0]);
-		dq[i] += dt * sg * (target - cqi);
-		m.dq[(size_t)i * m.n_cells + c] = dq[i];
-		const R qi = cqi + Bk * dq[i];
-		qn[i * m.ncs + c] = qi;
-		sq[i * SMAX + lc] = qi;
-		if (res) m.RES[(size_t)i * m.n_cells + c] = RES[i];
-	}
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Persistent, software-pipelined variant of k_tile_stage (compile-time strides only).
-// One CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... of the launch.  While tile t is in its gather phase the
-// cell states of tile t+1 are already being copied: the conservatives are double-buffered in shared memory, the other
-// staged rows (derived + viscous, dead once phase B is done) are refilled in place; the tile descriptor is fetched
-// two tiles ahead and the halo cell ids one tile ahead, so in steady state no global-memory latency is exposed at the
-// start of a tile.  Same arithmetic, same order: results are bit-identical to k_tile_stage.
-// ---------------------------------------------------------------------------------------------------
-template <class R, int D, int SMAX> struct SmemSide2 {
-	const R *sq, *sv;   // conservatives rows [NQ][SMAX] of the current buffer; derived + viscous rows [NS-NQ][SMAX]
-	int i;
-	using L = StagedLayout<D>;
-	__device__ __forceinline__ R q(int k) const { return sq[k * SMAX + i]; }
-	__device__ __forceinline__ R rho_inv() const { return sv[(L::RHO_INV - L::NQ) * SMAX + i]; }
-	__device__ __forceinline__ R Rpsi() const { return sv[(L::RPSI - L::NQ) * SMAX + i]; }
-	__device__ __forceinline__ R aux() const { return sv[(L::AUX - L::NQ) * SMAX + i]; }
-	__device__ __forceinline__ R dudx(int a, int b) const { return sv[(L::DUDX - L::NQ + a * D + b) * SMAX + i]; }
-	__device__ __forceinline__ R dTdx(int a) const { return sv[(L::DTDX - L::NQ + a) * SMAX + i]; }
-	__device__ __forceinline__ R sigmaU(int a) const { return sv[(L::SIGMAU - L::NQ + a) * SMAX + i]; }
-	__device__ __forceinline__ R tauMC(int, int) const { return R(0); }   // the persistent kernel serves the laminar closure only
-};
-
-template <class R, int D, int SCHEME, int NT, int MINB, int SMAX, int FMAX>
-__global__ void __launch_bounds__(NT, MINB)
-    k_tile_stage_p(DevMesh<R> m, TileView<R> tv, const R* __restrict__ q, const R* __restrict__ drv, R* __restrict__ qn, R* __restrict__ drvn, int tile0, int n_tiles, R dt, R Ak, R Bk, int first,
-                   int res) {
-	using L = StagedLayout<D>;
-	constexpr int NQ = D + 2;
-	constexpr int KX = (SMAX + NT - 1) / NT;     // staged cells per thread
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	R* qb = reinterpret_cast<R*>(smem_raw);      // [2][NQ][SMAX]
-	R* sv = qb + 2 * NQ * SMAX;                  // [NS-NQ][SMAX]
-	R* fl = sv + (L::NS - NQ) * SMAX;            // [NQ][FMAX]
-	TileDesc* tdb = reinterpret_cast<TileDesc*>(fl + NQ * FMAX);   // [3] ring: current, next, the one after
-	const int G = gridDim.x;
-	int t = blockIdx.x;
-	if (t >= n_tiles) return;
-
-	auto load_x = [&](const TileDesc& d, int* xs) {
-#pragma unroll
-		for (int k = 0; k < KX; k++) {
-			const int i = threadIdx.x + k * NT;
-			xs[k] = i < d.nt ? d.c0 + i : (i < d.nt + d.nh ? tv.halo_cell[d.halo_off + i - d.nt] : -1);
-		}
-	};
-	auto issue_copies = [&](const int* xs, int buf) {
-		R* sq = qb + buf * NQ * SMAX;
-#pragma unroll
-		for (int kk = 0; kk < KX; kk++) {
-			const int i = threadIdx.x + kk * NT, x = xs[kk];
-			if (x < 0) continue;
-#pragma unroll
-			for (int k = 0; k < NQ; k++) cp_async_elem(sq + k * SMAX + i, q + (size_t)k * m.ncs + x);
-#pragma unroll
-			for (int k = 0; k < 3; k++) cp_async_elem(sv + (L::RHO_INV - NQ + k) * SMAX + i, drv + (size_t)k * m.ncs + x);
-#pragma unroll
-			for (int k = 0; k < D * D; k++) cp_async_elem(sv + (L::DUDX - NQ + k) * SMAX + i, m.dudx + (size_t)k * m.ncs + x);
-#pragma unroll
-			for (int k = 0; k < D; k++) {
-				cp_async_elem(sv + (L::DTDX - NQ + k) * SMAX + i, m.dTdx + (size_t)k * m.ncs + x);
-				cp_async_elem(sv + (L::SIGMAU - NQ + k) * SMAX + i, m.sigmaU + (size_t)k * m.ncs + x);
-			}
-		}
-	};
-
-	// ---- prologue: descriptors of the first two tiles, copies of the first ---------------------------------
-	if (threadIdx.x == 0) {
-		tdb[0] = tv.tiles[tile0 + t];
-		if (t + G < n_tiles) tdb[1] = tv.tiles[tile0 + t + G];
-	}
-	__syncthreads();
-	int xs[KX];
-	load_x(tdb[0], xs);
-	issue_copies(xs, 0);
-	asm volatile("cp.async.commit_group;" ::: "memory");
-	int buf = 0, slot = 0;
-	for (;; t += G) {
-		const TileDesc td = tdb[slot];
-		const int slot1 = slot == 2 ? 0 : slot + 1, slot2 = slot1 == 2 ? 0 : slot1 + 1;
-		const int nf = td.nfo + td.ninc;
-		const bool has_next = t + G < n_tiles;
-		// descriptor two tiles ahead (asynchronous), halo ids one tile ahead (registers), first face of this tile
-		if (threadIdx.x < 2 && t + 2 * G < n_tiles) {
-			const char* src = reinterpret_cast<const char*>(tv.tiles + tile0 + t + 2 * G) + 16 * threadIdx.x;
-			const unsigned dst = (unsigned)__cvta_generic_to_shared(reinterpret_cast<char*>(tdb + slot2) + 16 * threadIdx.x);
-			asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-		}
-		asm volatile("cp.async.commit_group;" ::: "memory");
-		if (has_next) load_x(tdb[slot1], xs);
-		FaceIn<R, D> cur;
-		if ((int)threadIdx.x < nf) fetch_face<R, D, SCHEME>(tv, (size_t)td.f_off + threadIdx.x, cur);
-		asm volatile("cp.async.wait_group 1;" ::: "memory");   // the cell states of this tile have landed
-		__syncthreads();
-
-		// ---- B: every face of the tile once ----------------------------------------------------------------
-		const R* sq = qb + buf * NQ * SMAX;
-		for (int lf = threadIdx.x; lf < nf; lf += NT) {
-			FaceIn<R, D> nxt;
-			if (lf + NT < nf) fetch_face<R, D, SCHEME>(tv, (size_t)td.f_off + lf + NT, nxt);
-			const int lo = (int)(cur.idx & 0xffffu), ln = (int)((cur.idx >> 16) & 0x7fffu);
-			const bool ghost = (cur.idx >> 31) != 0;
-			R dv[D];
-#pragma unroll
-			for (int i = 0; i < D; i++) dv[i] = R(0);
-			if (ghost) {
-				const int f = tv.f_gface[(size_t)td.f_off + lf];
-#pragma unroll
-				for (int i = 0; i < D; i++) dv[i] = m.d[i * m.nfs + f];
-			}
-			R rhs[NQ];
-			face_flux<R, D, SCHEME>(m.k, SmemSide2<R, D, SMAX>{sq, sv, lo}, SmemSide2<R, D, SMAX>{sq, sv, ln}, cur.g, ghost, dv, rhs);
-#pragma unroll
-			for (int i = 0; i < NQ; i++) fl[i * FMAX + lf] = rhs[i];
-			if (lf + NT < nf) cur = nxt;
-		}
-
-		// ---- C: ordered gather, sponge, RK update; the next tile's copies start as soon as phase B is closed ----
-		const bool split = 2 * td.nt <= NT;
-		const int rounds = split ? 1 : (td.nt + NT - 1) / NT;
-		R* sqw = qb + buf * NQ * SMAX;
-		for (int r = 0; r < rounds; r++) {
-			constexpr int H = (NQ + 1) / 2;
-			const int part = split ? (threadIdx.x >= NT / 2 ? 1 : 0) : 2;
-			const int lc = split ? (int)threadIdx.x - (part ? NT / 2 : 0) : (int)threadIdx.x + r * NT;
-			const bool active = lc < td.nt;
-			if (part == 0)
-				gather_update_p<R, D, 0, H, SMAX, FMAX>(m, tv, td, sqw, fl, qn, lc, active, r == 0, has_next, [&] { issue_copies(xs, buf ^ 1); }, dt, Ak, Bk, first, res);
-			else if (part == 1)
-				gather_update_p<R, D, H, NQ, SMAX, FMAX>(m, tv, td, sqw, fl, qn, lc, active, r == 0, has_next, [&] { issue_copies(xs, buf ^ 1); }, dt, Ak, Bk, first, res);
-			else
-				gather_update_p<R, D, 0, NQ, SMAX, FMAX>(m, tv, td, sqw, fl, qn, lc, active, r == 0, has_next, [&] { issue_copies(xs, buf ^ 1); }, dt, Ak, Bk, first, res);
-		}
-		__syncthreads();
-		for (int lc = threadIdx.x; lc < td.nt; lc += NT) {
-			CellState<R, D> s;
-#pragma unroll
-			for (int i = 0; i < NQ; i++) s.q[i] = sqw[i * SMAX + lc];
-			derive_state<R, D, SCHEME>(m.k, s);
-			const int c = td.c0 + lc;
-			drvn[c] = s.rho_inv;
-			drvn[m.ncs + c] = s.Rpsi;
-			drvn[2 * m.ncs + c] = s.aux;
-		}
-		if (!has_next) break;
-		buf ^= 1;
-		slot = slot1;
-	}
-	asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // host-side description of the plan (device arrays are owned by the handle's allocation list)
@@ -714,6 +484,7 @@ struct TilePlan {
 	int n_tiles = 0, tile_cells = 0;
 	int sub_tile_start[LFMGPU_MAX_SUBMESH + 1] = {0};
 	int sub_smax[LFMGPU_MAX_SUBMESH] = {0}, sub_fmax[LFMGPU_MAX_SUBMESH] = {0};
+	int sub_tc[LFMGPU_MAX_SUBMESH] = {0}, sub_hmax[LFMGPU_MAX_SUBMESH] = {0};   // tile size (= halo base hb) and largest halo of each submesh
 	size_t smem_bytes = 0;            // largest k_tile_stage request
 	double halo_face_ratio = 0.0;     // incoming faces / own faces (redundant flux evaluations)
 	double halo_cell_ratio = 0.0;     // halo cells / tile cells
@@ -723,7 +494,6 @@ struct TilePlan {
 	uint32_t* d_f_idx = nullptr;
 	int* d_f_gface = nullptr;
 	int16_t* d_csr_local = nullptr;
-	int* d_staged_cell = nullptr;     // [n_tiles][kFixedSmax], only when every tile fits the compile-time strides
 	void *d_fS = nullptr, *d_fK = nullptr, *d_fw = nullptr, *d_fdm = nullptr, *d_fdi = nullptr, *d_fSmag = nullptr;
 };
 

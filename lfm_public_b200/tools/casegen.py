@@ -130,3 +130,14 @@ def write_case(case_dir, m, fields=None, ranks=None, cell_rank=None, two_d=False
 def _time_name(t):
     s = "%.12g" % t
     return s
+
+
+def set_end_time(case_dir, end_time):
+    """Rewrites `endTime` in system/controlDict of an existing case (the same case is advanced for a different number of steps)."""
+    import re
+    p = os.path.join(case_dir, "system", "controlDict")
+    s = open(p).read()
+    s, n = re.subn(r"^endTime\s+\S+;", f"endTime         {end_time!r};", s, flags=re.M)
+    if n != 1:
+        raise RuntimeError(f"{p}: no endTime entry")
+    open(p, "w").write(s)

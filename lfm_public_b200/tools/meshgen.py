@@ -381,7 +381,16 @@ def hex_block(n, blocks=(1, 1, 1), rank=0, cell_size=None, z_cyclic=None, tile=N
     for s in range(6):
         patch_id[side == s] = side_patch[s]
     new_of_old = None
-    if tile is not None:
+    if isinstance(tile, str) and tile == "morton":
+        # the numbering `python -m lfm_public_b200.tools.renumber --method morton` gives this block: cells along a Z-order curve
+        # through their centres (on a uniform block that is the curve through the cell indices)
+        c = np.arange(nx * ny * nz, dtype=np.int64)
+        order = np.argsort(_morton3(c % nx, (c // nx) % ny, c // (nx * ny)), kind="stable")
+        new_of_old = np.empty(len(c), dtype=np.int64)
+        new_of_old[order] = c
+        a = new_of_old[a]
+        b = np.where(b >= 0, new_of_old[np.maximum(b, 0)], -1)
+    elif tile is not None:
         new_of_old = blocked_order(nx, ny, nz, tile, offset=(1, 1, 1), brick_order=brick_order)
         a = new_of_old[a]
         b = np.where(b >= 0, new_of_old[np.maximum(b, 0)], -1)

@@ -31,7 +31,7 @@ def main():
     args = ap.parse_args()
     import bench
     from lfm_public_b200 import gpu_api
-    tile = tuple(int(x) for x in args.tile.split(",")) if args.tile != "none" else None
+    tile = "morton" if args.tile == "morton" else (tuple(int(x) for x in args.tile.split(",")) if args.tile != "none" else None)
     t0 = time.time()
     case, dt = bench.build_rank_case(args.n, (1, 1, 1), 0, 1, args.precision, args.scheme, tile, args.brick_order)
     case.finish()
