@@ -165,6 +165,8 @@ struct lfmgpu_ctx {
 	bool pipe_ok = false;              // tensor maps and ring geometry are in place
 	int pipe_enable = 3;               // LFMGPU_PIPE: bit 0 stage kernel, bit 1 gradient kernel; 0: the tile kernels of round 1 serve everything
 	int pipe_slots_cap = 4;            // LFMGPU_PIPE_SLOTS
+	int pipe_pf_dist = 0;              // L2 prefetch distance of the persistent kernels in tiles per CTA (LFMGPU_PIPE_PF, 0: off)
+	int pipe_grad_slots_cap = 8;       // LFMGPU_PIPE_GSLOTS
 	int pipe_spare_sms = 8;            // SMs left to the halo stream's kernels on a rank with neighbours (LFMGPU_PIPE_SPARE)
 	int n_sms = 0;
 	PipeGeom pipe{};
@@ -716,7 +718,7 @@ int pipe_setup(lfmgpu_ctx* h) {
 		fmax = std::max(fmax, p.sub_fmax[s]);
 	}
 	const int TC = h->tile_cells;
-	if (TC > 256 || TC % 2 || hmax > 32 * kPipeMaxHaloRegs) return 0;
+	if (TC > 256 || TC % 2 || hmax > kPipeMaxHalo) return 0;
 	hmax = std::max(hmax, 4);
 	const int D = h->D, QW = Rec<3>::QW, VW = D == 3 ? Rec<3>::VW : Rec<2>::VW;
 	const uint32_t QB = (uint32_t)(QW * h->prec), VB = (uint32_t)(VW * h->prec);
@@ -725,6 +727,7 @@ int pipe_setup(lfmgpu_ctx* h) {
 	CU(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, h->device));
 	PipeGeom g{};
 	g.box_cells = TC;
+	g.pf_dist = h->pipe_pf_dist;
 	g.hmax = hmax;
 	g.smax = TC + hmax;
 	g.fmax = (fmax + 3) / 4 * 4;
@@ -733,9 +736,9 @@ int pipe_setup(lfmgpu_ctx* h) {
 	for (int ns = std::min(4, h->pipe_slots_cap); ns >= 2; ns--) {
 		g.n_slots = ns;
 		g.off_bar = 0;
-		g.off_ids = 128;
-		g.off_out = round_up(g.off_ids + (uint32_t)ns * hmax * 4u, 128);
-		g.off_fl = round_up(g.off_out + 2u * TC * QB, 128);
+		g.off_meta = 128;   // barriers (16 bytes per slot) in front
+		g.off_ids = g.off_meta + kMetaRing * (uint32_t)sizeof(TileMeta);
+		g.off_fl = round_up(g.off_ids + (uint32_t)kMetaRing * ((hmax + 3) / 4 * 4) * 4u, 128);
 		g.off_slot = round_up(g.off_fl + 2u * (uint32_t)h->NQ * g.fmax * (uint32_t)h->prec, 1024);
 		const size_t total = (size_t)g.off_slot + (size_t)ns * g.slot_bytes + 1024;   // + slack to align the base to 1024
 		if (total <= (size_t)dev_smem) {
@@ -750,16 +753,18 @@ int pipe_setup(lfmgpu_ctx* h) {
 	if (TC <= kGradGroupThreads) {
 		GradGeom gg{};
 		gg.box_cells = TC;
+		gg.pf_dist = h->pipe_pf_dist;
 		gg.hmax = hmax;
 		gg.smax = TC + hmax;
 		gg.fmax = g.fmax;
 		gg.q_bytes = round_up(std::max((uint32_t)gg.smax * QB, (uint32_t)TC * VB), 1024);
 		gg.slot_bytes = gg.q_bytes + round_up((uint32_t)gg.fmax * (uint32_t)((D + 1) * h->prec + 4), 1024);
-		for (int ns = 8; ns >= kGradGroups; ns--) {
+		for (int ns = std::max(kGradGroups, std::min(8, h->pipe_grad_slots_cap)); ns >= kGradGroups; ns--) {
 			gg.n_slots = ns;
 			gg.off_bar = 0;
-			gg.off_ids = 128;
-			gg.off_slot = round_up(gg.off_ids + (uint32_t)ns * hmax * 4u, 1024);
+			gg.off_meta = 128;
+			gg.off_ids = gg.off_meta + kMetaRing * (uint32_t)sizeof(TileMeta);
+			gg.off_slot = round_up(gg.off_ids + (uint32_t)kMetaRing * ((hmax + 3) / 4 * 4) * 4u, 1024);
 			const size_t total = (size_t)gg.off_slot + (size_t)ns * gg.slot_bytes + 1024;
 			if (total <= (size_t)dev_smem) {
 				h->gpipe = gg;
@@ -769,6 +774,9 @@ int pipe_setup(lfmgpu_ctx* h) {
 			}
 		}
 	}
+	if (getenv("LFMGPU_PLAN_STATS"))
+		fprintf(stderr, "[lfmgpu pipe] stage kernel: %s, %d slots of %u bytes, %zu bytes of shared memory; gradient kernel: %s, %d slots of %u bytes, %zu bytes; halo <= %d cells, faces <= %d\n",
+		        h->pipe_ok ? "on" : "off", h->pipe.n_slots, h->pipe.slot_bytes, h->pipe_smem, h->grad_pipe_ok ? "on" : "off", h->gpipe.n_slots, h->gpipe.slot_bytes, h->gpipe_smem, hmax, g.fmax);
 	if (!h->pipe_ok) return 0;
 	for (int b = 0; b < 2; b++) TRY(make_record_map(&h->map_q[b], h->q[b], h->prec, QW, h->ncs, TC));
 	const void* vis = h->prec == 8 ? (const void*)h->md.vis : (const void*)h->mf.vis;
@@ -1062,6 +1070,7 @@ int tile_plan_host(lfmgpu_ctx* h, const lfmgpu_desc* ds, int dev_smem, HostPlan&
 				td.nt = c1 - c0;
 				const int fo0 = cfs[(size_t)c0];
 				td.nfo = cfs[(size_t)c1] - fo0;
+				while (halo_cell.size() % 4) halo_cell.push_back(0);   // a tile's halo list starts on a 16-byte boundary (16-byte async copies)
 				td.halo_off = (int)halo_cell.size();
 				while (f_gface.size() % 4) {   // a tile's slice of the face tables starts on a 16-byte boundary (bulk copies)
 					f_gface.push_back(0);
@@ -1208,6 +1217,7 @@ int tile_plan_build(lfmgpu_ctx* h, const lfmgpu_desc* ds) {
 	p.n_table = f_gface.size();
 	p.T = pad32(p.n_table + 1);
 	TRY(upload<TileDesc>(h, &p.d_tiles, tiles.data(), tiles.size()));
+	halo_cell.resize(halo_cell.size() + 4, 0);   // the last tile's 16-byte id copies may read up to three entries past its list
 	TRY(upload<int>(h, &p.d_halo_cell, halo_cell.data(), halo_cell.size()));
 	f_gface.resize(p.T, 0);
 	f_idx.resize(p.T, 0);
@@ -1442,6 +1452,8 @@ int lfmgpu_create(const lfmgpu_desc* ds, int device, lfmgpu_t* out) {
 	if (const char* e = getenv("LFMGPU_PIPE")) h->pipe_enable = atoi(e);   // bit 0: stage kernel, bit 1: gradient kernel
 	if (const char* e = getenv("LFMGPU_PIPE_SLOTS")) h->pipe_slots_cap = std::max(2, atoi(e));
 	if (const char* e = getenv("LFMGPU_PIPE_SPARE")) h->pipe_spare_sms = std::max(0, atoi(e));
+	if (const char* e = getenv("LFMGPU_PIPE_PF")) h->pipe_pf_dist = std::max(0, atoi(e));
+	if (const char* e = getenv("LFMGPU_PIPE_GSLOTS")) h->pipe_grad_slots_cap = atoi(e);
 	if (!rc) rc = tile_plan_build(h, ds);
 	if (!rc) rc = pipe_setup(h);
 	if (!(h->pipe_enable & 2)) h->grad_pipe_ok = false;

@@ -31,16 +31,19 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarr
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// The suspend-time hint lets the hardware park the thread until the phase completes (or the hint, in nanoseconds, runs out)
+// instead of returning at once: without it twenty warps polling their barriers issued a sixth of all instructions of the
+// kernel (profiles/r2j_*), taken from the warps that had arithmetic to do.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 	uint32_t ok;
 	asm volatile(
 	    "{\n"
 	    ".reg .pred p;\n"
-	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
 	    "selp.u32 %0, 1, 0, p;\n"
 	    "}"
 	    : "=r"(ok)
-	    : "r"(smem_u32(bar)), "r"(parity)
+	    : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
 	    : "memory");
 	return ok != 0;
 }
@@ -63,6 +66,8 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
 __device__ __forceinline__ void bulk_store(void* dst_global, uint32_t src_smem, uint32_t bytes) {
 	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_global), "r"(src_smem), "r"(bytes) : "memory");
 }
+// TMA: ask the L2 to fetch a contiguous piece of global memory (address and size multiples of 16 bytes); nothing waits for it
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) { asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes)); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -86,6 +91,7 @@ template <> struct Chunk16<double> {
 		d[1] = t.y;
 	}
 	static __device__ __forceinline__ T pack(const double* d) { return make_double2(d[0], d[1]); }
+	static __device__ __forceinline__ double get(const T& t, int i) { return i == 0 ? t.x : t.y; }
 };
 template <> struct Chunk16<float> {
 	using T = float4;
@@ -97,36 +103,90 @@ template <> struct Chunk16<float> {
 		d[3] = t.w;
 	}
 	static __device__ __forceinline__ T pack(const float* d) { return make_float4(d[0], d[1], d[2], d[3]); }
+	static __device__ __forceinline__ float get(const T& t, int i) { return i == 0 ? t.x : (i == 1 ? t.y : (i == 2 ? t.z : t.w)); }
 };
 
 // one side of a face in registers, filled by 16-byte loads from the swizzled records of a ring slot
 template <class R, int D> struct RecSide {
 	using RC = Rec<D>;
+	using C16 = Chunk16<R>;
 	static constexpr bool kHasTrace = (D == 3);
-	R qv[RC::QW];
-	R vv[RC::VW];
+	static constexpr int QB = RC::QW * (int)sizeof(R), VB = RC::VW * (int)sizeof(R);
+	typename C16::T qc[QB / 16];   // the chunks as loaded: the accessors name a half (quarter) of one, no value is moved
+	typename C16::T vc[VB / 16];
 	__device__ __forceinline__ void load_q(const unsigned char* Qs, int slot) {
-		constexpr int QB = RC::QW * (int)sizeof(R);
 		const uint32_t p = swz((uint32_t)slot * QB, swz_mask(QB));
 #pragma unroll
-		for (int j = 0; j < QB / 16; j++) Chunk16<R>::unpack(*reinterpret_cast<const typename Chunk16<R>::T*>(Qs + (p ^ (uint32_t)(j << 4))), qv + j * Chunk16<R>::N);
+		for (int j = 0; j < QB / 16; j++) qc[j] = *reinterpret_cast<const typename C16::T*>(Qs + (p ^ (uint32_t)(j << 4)));
 	}
 	__device__ __forceinline__ void load_v(const unsigned char* Vs, int slot) {
-		constexpr int VB = RC::VW * (int)sizeof(R);
 		const uint32_t p = swz((uint32_t)slot * VB, swz_mask(VB));
 #pragma unroll
-		for (int j = 0; j < VB / 16; j++) Chunk16<R>::unpack(*reinterpret_cast<const typename Chunk16<R>::T*>(Vs + (p ^ (uint32_t)(j << 4))), vv + j * Chunk16<R>::N);
+		for (int j = 0; j < VB / 16; j++) vc[j] = *reinterpret_cast<const typename C16::T*>(Vs + (p ^ (uint32_t)(j << 4)));
 	}
-	__device__ __forceinline__ R q(int k) const { return qv[k]; }
-	__device__ __forceinline__ R rho_inv() const { return qv[RC::RHO_INV]; }
-	__device__ __forceinline__ R Rpsi() const { return qv[RC::RPSI]; }
-	__device__ __forceinline__ R aux() const { return qv[RC::AUX]; }
-	__device__ __forceinline__ R dudx(int a, int b) const { return vv[RC::DUDX + a * D + b]; }
-	__device__ __forceinline__ R dTdx(int a) const { return vv[RC::DTDX + a]; }
-	__device__ __forceinline__ R sigmaU(int a) const { return vv[RC::SIGMAU + a]; }
-	__device__ __forceinline__ R trace_neg() const { return vv[D == 3 ? RC::TR : 0]; }
+	__device__ __forceinline__ R qval(int k) const { return C16::get(qc[k / C16::N], k % C16::N); }
+	__device__ __forceinline__ R vval(int k) const { return C16::get(vc[k / C16::N], k % C16::N); }
+	__device__ __forceinline__ R q(int k) const { return qval(k); }
+	__device__ __forceinline__ R rho_inv() const { return qval(RC::RHO_INV); }
+	__device__ __forceinline__ R Rpsi() const { return qval(RC::RPSI); }
+	__device__ __forceinline__ R aux() const { return qval(RC::AUX); }
+	__device__ __forceinline__ R dudx(int a, int b) const { return vval(RC::DUDX + a * D + b); }
+	__device__ __forceinline__ R dTdx(int a) const { return vval(RC::DTDX + a); }
+	__device__ __forceinline__ R sigmaU(int a) const { return vval(RC::SIGMAU + a); }
+	__device__ __forceinline__ R trace_neg() const { return vval(D == 3 ? RC::TR : 0); }
 	__device__ __forceinline__ R tauMC(int, int) const { return R(0); }   // laminar closure only
 };
+
+// Producer side of a halo: copies the B-byte records of the cells ids[0 .. nh) into slots first_slot.. of a swizzled region
+// with 16-byte cp.async.  Consecutive threads take consecutive 16-byte chunks (B/16 threads per record: whole sectors per
+// request); a thread keeps its chunk index for the whole loop and walks the halo list with a fixed cell stride, so that an
+// element costs one id load, one 64-bit multiply-add and the swizzle.
+template <int B, int NTHR> __device__ __forceinline__ void copy_halo_records(uint32_t region_smem, const unsigned char* src, const int* ids, int nh, int first_slot, int tid) {
+	constexpr int C = B / 16, CELLS_PER_PASS = NTHR / C;
+	static_assert(NTHR % C == 0, "the chunk index of a thread must not change between passes");
+	const int ch = tid % C;
+	const unsigned char* s0 = src + ch * 16;
+	const uint32_t d0 = (uint32_t)ch * 16u;
+#pragma unroll 4
+	for (int cell = tid / C; cell < nh; cell += CELLS_PER_PASS) {
+		const size_t x = (size_t)ids[cell];
+		const uint32_t off = (uint32_t)(first_slot + cell) * B + d0;
+		cp_async16(region_smem + swz(off, swz_mask(B)), s0 + x * B);
+	}
+}
+
+// ---- the descriptor warp's metadata ring --------------------------------------------------------------------------------
+// Warp 0 of the producers runs kMetaAhead tiles ahead of the fills: the descriptor of tile i + kMetaAhead (read from global
+// memory two more iterations earlier, so that no load is waited for) goes into a ring in shared memory and the tile's halo
+// cell ids follow it with 16-byte cp.async copies (the plan pads every halo list to a 16-byte boundary), one commit group
+// per tile; `cp.async.wait_group kMetaAhead - 1` at the top of iteration i then guarantees tile i's ids.  The lookahead is
+// what lets the fill rate exceed one tile per global-memory round trip (the gradient kernel's tiles take less than that).
+constexpr int kMetaAhead = 3, kMetaRing = kMetaAhead + 2;
+struct TileMeta {
+	int c0, nh, halo_off, f_off, nf, pad[3];   // 32 bytes
+};
+__device__ __forceinline__ TileMeta meta_of(const TileDesc* d) {
+	const int4 a = *reinterpret_cast<const int4*>(d);              // c0, nt, halo_off, nh
+	const int4 b = *reinterpret_cast<const int4*>(&d->f_off);      // f_off, nfo, ninc, hb
+	TileMeta mt;
+	mt.c0 = a.x;
+	mt.nh = a.w;
+	mt.halo_off = a.z;
+	mt.f_off = b.x;
+	mt.nf = b.y + b.z;
+	return mt;
+}
+// publishes the metadata of one tile: descriptor fields by lane 0, halo ids by asynchronous copies of the whole warp
+__device__ __forceinline__ void meta_publish(const TileMeta& mt, TileMeta* ring_meta, int* ring_ids, const int* __restrict__ halo_cell, int lane) {
+	if (lane == 0) {
+		ring_meta->c0 = mt.c0;
+		ring_meta->nh = mt.nh;
+		ring_meta->f_off = mt.f_off;
+		ring_meta->nf = mt.nf;
+	}
+	const uint32_t dst = smem_u32(ring_ids);
+	for (int k = lane * 4; k < mt.nh; k += 128) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)k * 4u), "l"(halo_cell + mt.halo_off + k));
+}
 
 // what the host passes about the ring (all byte offsets from the 1024-aligned start of dynamic shared memory)
 struct PipeGeom {
@@ -136,18 +196,20 @@ struct PipeGeom {
 	int fmax;               // faces per tile (stride of the flux rows)
 	int hmax;               // largest halo
 	uint32_t off_bar;       // full[n_slots], empty[n_slots]
-	uint32_t off_ids;       // [n_slots][hmax] int
-	uint32_t off_out;       // [2][box_cells * QB] un-swizzled Q records of the finished tile (source of the bulk store)
+	uint32_t off_ids;       // [kMetaRing][hmax4] int halo ids, preceded by [kMetaRing] TileMeta (off_meta)
+	uint32_t off_meta;
 	uint32_t off_fl;        // [2][NQ][fmax] R face fluxes
 	uint32_t off_slot;      // first ring slot
 	uint32_t slot_bytes;    // Q region + V region (each a multiple of 1024)
 	uint32_t q_bytes;       // Q region
+	int pf_dist;            // L2 prefetch distance in tiles of this CTA (0: none): own-cell records and face-table slices of the tile
+	                        // pf_dist fills ahead are requested into the L2, so that a fill costs an L2 round trip, not a DRAM one
 };
 
 constexpr int kPipeGroupThreads = 256;                      // one consumer group (two warpgroups)
 constexpr int kPipeProducerThreads = 128;                   // one warpgroup: setmaxnreg is a warpgroup-wide instruction
 constexpr int kPipeThreads = 2 * kPipeGroupThreads + kPipeProducerThreads;   // 20 warps: five per scheduler, 96 registers each at launch
-constexpr int kPipeMaxHaloRegs = 8;                         // halo ids warp 0 of the producers prefetches per lane (hmax <= 256)
+constexpr int kPipeMaxHalo = 256;                           // largest halo the id ring is laid out for
 // Register budget: five warps per scheduler cap the launch at 96 registers per thread (640 x 96 = 61 440: what the CTA owns
 // for its whole life -- setmaxnreg only moves registers between its warps).  The producer warpgroup gives back all but 32 per
 // thread and the consumers grow to 112: 128 x 32 + 512 x 112 = 61 440.
@@ -228,8 +290,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 
 	if (threadIdx.x == 0) {
 		for (int s = 0; s < NS; s++) {
-			mbar_init(full + s, 1 + kPipeProducerThreads);   // the expect_tx arrival + one cp.async arrival per producer thread
-			mbar_init(empty + s, 1);                         // one elected consumer thread
+			mbar_init(full + s, 1 + kPipeProducerThreads - 32);   // the expect_tx arrival + one cp.async arrival per gather thread
+			mbar_init(empty + s, 1);                              // one elected consumer thread
 		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
@@ -237,75 +299,85 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 
 	if (threadIdx.x >= 2 * GT) {
 		// ============================ producers (one warpgroup) ===================================================
+		// Two roles, so that neither needs more than a handful of live registers (the producers run on 32; a spill costs an L2
+		// round trip here, because shared memory leaves the L1 almost no capacity):
+		//   warp 0     descriptors and halo ids one tile ahead -> shared memory, the TMA loads of the own cells, L2 prefetch;
+		//   warps 1-3  the 16-byte cp.async copies of the halo records.
 		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kPipeProducerRegs));
 		if ((int)blockIdx.x >= n_tiles) return;
 		const int ptid = threadIdx.x - 2 * GT, pwarp = ptid >> 5;
 		int* ids_all = reinterpret_cast<int*>(sm + pg.off_ids);
+		TileMeta* meta_all = reinterpret_cast<TileMeta*>(sm + pg.off_meta);
+		const int hpitch = (pg.hmax + 3) & ~3;
 		const unsigned char* qsrc = reinterpret_cast<const unsigned char*>(q);
 		const unsigned char* vsrc = reinterpret_cast<const unsigned char*>(m.vis);
-		// of a tile descriptor the producers need the first cell, the halo list and its length (the first 16 bytes)
-		struct Need {
-			int c0, nt, halo_off, nh;
-		};
-		auto need_of = [&](int tile) {
-			const int4 v = *reinterpret_cast<const int4*>(tv.tiles + tile0 + tile);
-			return Need{v.x, v.y, v.z, v.w};
-		};
-		int t = blockIdx.x;
-		Need td = need_of(t);
-		int idr[kPipeMaxHaloRegs];
-#pragma unroll
-		for (int k = 0; k < kPipeMaxHaloRegs; k++) idr[k] = (pwarp == 0 && (lane + 32 * k) < td.nh) ? tv.halo_cell[td.halo_off + lane + 32 * k] : 0;
-		Need tdn = td;
-		if (t + G < n_tiles) tdn = need_of(t + G);
-		for (int i = 0;; i++, t += G) {
-			const int slot = i % NS;
-			const uint32_t use = (uint32_t)(i / NS);
-			int* ids = ids_all + slot * pg.hmax;
-			if (pwarp == 0) {
-#pragma unroll
-				for (int k = 0; k < kPipeMaxHaloRegs; k++)
-					if (lane + 32 * k < td.nh) ids[lane + 32 * k] = idr[k];
+		const int my_tiles = (n_tiles - (int)blockIdx.x + G - 1) / G;
+		const TileDesc* my_desc = tv.tiles + tile0 + blockIdx.x;   // tile i of this CTA: my_desc[i * G]
+		if (pwarp == 0) {
+			// prologue: the metadata of the first kMetaAhead tiles; descriptors of the next two in registers
+			for (int j = 0; j < kMetaAhead; j++) {
+				if (j < my_tiles) meta_publish(meta_of(my_desc + (size_t)j * G), meta_all + j % kMetaRing, ids_all + (j % kMetaRing) * hpitch, tv.halo_cell, lane);
+				asm volatile("cp.async.commit_group;" ::: "memory");
 			}
-			named_bar(3, kPipeProducerThreads);   // the halo ids of this tile are in shared memory (the ring of id lists is the producers' own)
-			// the next tile's halo ids and the descriptor after it: in flight while this tile's copies are issued
-			const bool has_next = t + G < n_tiles;
-			Need tdnn = tdn;
-			if (has_next) {
-				if (pwarp == 0) {
-#pragma unroll
-					for (int k = 0; k < kPipeMaxHaloRegs; k++) idr[k] = (lane + 32 * k) < tdn.nh ? tv.halo_cell[tdn.halo_off + lane + 32 * k] : 0;
+			TileMeta mA{}, mB{};
+			if (kMetaAhead < my_tiles) mA = meta_of(my_desc + (size_t)kMetaAhead * G);
+			if (kMetaAhead + 1 < my_tiles) mB = meta_of(my_desc + (size_t)(kMetaAhead + 1) * G);
+			const int PD = pg.pf_dist;
+			for (int i = 0; i < my_tiles; i++) {
+				const int slot = i % NS;
+				const uint32_t use = (uint32_t)(i / NS);
+				asm volatile("cp.async.wait_group %0;" ::"n"(kMetaAhead - 1) : "memory");   // this lane's share of tile i's ids has landed
+				__syncwarp();
+				named_bar(3, kPipeProducerThreads);   // tile i's metadata is published to the gather warps
+				const int c0 = meta_all[i % kMetaRing].c0;
+				// metadata of tile i + kMetaAhead (its descriptor was read two iterations ago), descriptor of tile i + kMetaAhead + 2
+				if (i + kMetaAhead < my_tiles) meta_publish(mA, meta_all + (i + kMetaAhead) % kMetaRing, ids_all + ((i + kMetaAhead) % kMetaRing) * hpitch, tv.halo_cell, lane);
+				asm volatile("cp.async.commit_group;" ::: "memory");
+				mA = mB;
+				if (i + kMetaAhead + 2 < my_tiles) mB = meta_of(my_desc + (size_t)(i + kMetaAhead + 2) * G);
+				mbar_wait(empty + slot, (use & 1u) ^ 1u);   // the consumers have released this slot (passes at once on its first use)
+				if (lane == 0) {
+					unsigned char* Qs = sm + pg.off_slot + (size_t)slot * pg.slot_bytes;
+					mbar_arrive_expect_tx(full + slot, (uint32_t)pg.box_cells * (QB + VB));
+					tma_load_2d(smem_u32(Qs), &map_q, 0, c0, full + slot);
+					tma_load_2d(smem_u32(Qs + pg.q_bytes), &map_v, 0, c0, full + slot);
 				}
-				if (t + 2 * G < n_tiles) tdnn = need_of(t + 2 * G);
+				// L2 prefetch of the tile PD fills ahead: its own-cell records (two contiguous pieces) and its slice of each face table
+				if (PD > 0 && lane < 16 && i + PD < my_tiles) {
+					const TileMeta pm = meta_of(my_desc + (size_t)(i + PD) * G);
+					const int ac0 = pm.c0, af = pm.f_off;
+					const uint32_t nf4 = (uint32_t)(pm.nf + 3) & ~3u;
+					if (lane == 0) bulk_prefetch_l2(qsrc + (size_t)ac0 * QB, (uint32_t)pg.box_cells * QB);
+					if (lane == 1) bulk_prefetch_l2(vsrc + (size_t)ac0 * VB, (uint32_t)pg.box_cells * VB);
+					if (nf4) {
+						if (lane == 2) bulk_prefetch_l2(tv.f_idx + af, nf4 * 4u);
+						if (lane >= 3 && lane < 3 + D) bulk_prefetch_l2(tv.fS + (size_t)(lane - 3) * tv.T + af, nf4 * (uint32_t)sizeof(R));
+						if (lane >= 3 + D && lane < 3 + 2 * D) bulk_prefetch_l2(tv.fK + (size_t)(lane - 3 - D) * tv.T + af, nf4 * (uint32_t)sizeof(R));
+						if (lane == 3 + 2 * D) bulk_prefetch_l2(tv.fw + af, nf4 * (uint32_t)sizeof(R));
+						if (lane == 4 + 2 * D) bulk_prefetch_l2(tv.fdm + af, nf4 * (uint32_t)sizeof(R));
+						if (lane == 5 + 2 * D) bulk_prefetch_l2(tv.fdi + af, nf4 * (uint32_t)sizeof(R));
+						if (SCHEME == 0 && lane == 6 + 2 * D) bulk_prefetch_l2(tv.fSmag + af, nf4 * (uint32_t)sizeof(R));
+					}
+				}
 			}
-			mbar_wait(empty + slot, (use & 1u) ^ 1u);   // the consumers have released this slot (passes at once on its first use)
-			unsigned char* Qs = sm + pg.off_slot + (size_t)slot * pg.slot_bytes;
-			unsigned char* Vs = Qs + pg.q_bytes;
-			if (ptid == 0) {
-				mbar_arrive_expect_tx(full + slot, (uint32_t)pg.box_cells * (QB + VB));
-				tma_load_2d(smem_u32(Qs), &map_q, 0, td.c0, full + slot);
-				tma_load_2d(smem_u32(Vs), &map_v, 0, td.c0, full + slot);
+			asm volatile("cp.async.wait_all;" ::: "memory");
+		} else {
+			constexpr int NG_ = kPipeProducerThreads - 32;   // gather threads
+			const int gtid = ptid - 32;
+			for (int i = 0; i < my_tiles; i++) {
+				const int slot = i % NS;
+				const uint32_t use = (uint32_t)(i / NS);
+				named_bar(3, kPipeProducerThreads);
+				const int nh = meta_all[i % kMetaRing].nh;
+				const int* ids = ids_all + (i % kMetaRing) * hpitch;
+				mbar_wait(empty + slot, (use & 1u) ^ 1u);
+				const uint32_t q0 = smem_u32(sm + pg.off_slot + (size_t)slot * pg.slot_bytes);
+				copy_halo_records<QB, NG_>(q0, qsrc, ids, nh, pg.box_cells, gtid);
+				copy_halo_records<VB, NG_>(q0 + pg.q_bytes, vsrc, ids, nh, pg.box_cells, gtid);
+				cp_async_mbar_arrive_noinc(full + slot);
 			}
-			const uint32_t q0 = smem_u32(Qs), v0 = smem_u32(Vs);
-			const int nq = td.nh * CQ, nv = td.nh * CV;
-#pragma unroll 4
-			for (int it = ptid; it < nq; it += kPipeProducerThreads) {
-				const int cell = it / CQ, ch = it % CQ;
-				const size_t x = (size_t)ids[cell];
-				cp_async16(q0 + swz((uint32_t)(pg.box_cells + cell) * QB + (uint32_t)ch * 16u, swz_mask(QB)), qsrc + x * QB + ch * 16);
-			}
-#pragma unroll 4
-			for (int it = ptid; it < nv; it += kPipeProducerThreads) {
-				const int cell = it / CV, ch = it % CV;
-				const size_t x = (size_t)ids[cell];
-				cp_async16(v0 + swz((uint32_t)(pg.box_cells + cell) * VB + (uint32_t)ch * 16u, swz_mask(VB)), vsrc + x * VB + ch * 16);
-			}
-			cp_async_mbar_arrive_noinc(full + slot);
-			if (!has_next) break;
-			td = tdn;
-			tdn = tdnn;
+			asm volatile("cp.async.wait_all;" ::: "memory");
 		}
-		asm volatile("cp.async.wait_all;" ::: "memory");
 		return;
 	}
 
@@ -316,7 +388,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 	const int tid = threadIdx.x % GT;         // thread inside the group
 	const int bar_id = 1 + g;
 	R* fl = reinterpret_cast<R*>(sm + pg.off_fl) + (size_t)g * NQ * pg.fmax;
-	unsigned char* outb = sm + pg.off_out + (size_t)g * pg.box_cells * QB;
 	const int fmax = pg.fmax;
 	int t = blockIdx.x + g * G;
 	if (t >= n_tiles) return;
@@ -331,6 +402,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 		if (has_next) tdn = tv.tiles[tile0 + t + 2 * G];   // in flight during this tile
 		unsigned char* Qs = sm + pg.off_slot + (size_t)slot * pg.slot_bytes;
 		const unsigned char* Vs = Qs + pg.q_bytes;
+		unsigned char* outb = Qs + pg.q_bytes;   // the V region is dead once phase B is over: it stages the finished Q records (un-swizzled)
 		const int nf = td.nfo + td.ninc;
 		// The two groups take alternate tiles, so this group can reach a slot while its previous user (a tile of the OTHER group)
 		// still waits for its data: one phase behind, which the parity of `full` alone cannot tell from "already filled again".
@@ -386,29 +458,30 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 		}
 		// the first face of this group's next tile travels during the epilogue and the wait for its slot
 		if (has_next && tid < tdn.nfo + tdn.ninc) fetch_face<R, D, SCHEME>(tv, (size_t)tdn.f_off + tid, cur);
-		if (tid == 0) bulk_wait_read0();   // the previous tile's bulk store has read the staging buffer
-		named_bar(bar_id, GT);              // all new conservatives are in the slot; the staging buffer is free
+		named_bar(bar_id, GT);   // all new conservatives are in the slot
 
 		// ---- derived values of the new state, the finished Q records -> staging (un-swizzled) -> one bulk store ----
 		for (int lc = tid; lc < td.nt; lc += GT) {
 			RecSide<R, D> s;
 			s.load_q(Qs, lc);
 			CellState<R, D> cs;
+			R rec[RC::QW];
 #pragma unroll
-			for (int k = 0; k < NQ; k++) cs.q[k] = s.qv[k];
+			for (int k = 0; k < NQ; k++) rec[k] = cs.q[k] = s.q(k);
 			derive_state<R, D, SCHEME>(m.k, cs);
-			s.qv[RC::RHO_INV] = cs.rho_inv;
-			s.qv[RC::RPSI] = cs.Rpsi;
-			s.qv[RC::AUX] = cs.aux;
-			if (RC::AUX + 1 < RC::QW) s.qv[RC::QW - 1] = R(0);
+			rec[RC::RHO_INV] = cs.rho_inv;
+			rec[RC::RPSI] = cs.Rpsi;
+			rec[RC::AUX] = cs.aux;
+			if (RC::AUX + 1 < RC::QW) rec[RC::QW - 1] = R(0);
 #pragma unroll
-			for (int j = 0; j < CQ; j++) *reinterpret_cast<typename Chunk16<R>::T*>(outb + (size_t)lc * QB + j * 16) = Chunk16<R>::pack(s.qv + j * Chunk16<R>::N);
+			for (int j = 0; j < CQ; j++) *reinterpret_cast<typename Chunk16<R>::T*>(outb + (size_t)lc * QB + j * 16) = Chunk16<R>::pack(rec + j * Chunk16<R>::N);
 		}
 		fence_proxy_async();   // the staging writes above become visible to the TMA engine
 		named_bar(bar_id, GT);
 		if (tid == 0) {
 			bulk_store(reinterpret_cast<unsigned char*>(qn) + (size_t)td.c0 * QB, smem_u32(outb), (uint32_t)td.nt * QB);
 			bulk_commit();
+			bulk_wait_read0();           // the store has read its source: the slot may be refilled
 			mbar_arrive(empty + slot);   // every thread of the group is past its last access to the slot
 		}
 		if (!has_next) break;
@@ -427,9 +500,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 // ---------------------------------------------------------------------------------------------------------------------
 struct GradGeom {
 	int n_slots, box_cells, smax, fmax, hmax;
-	uint32_t off_bar, off_ids, off_slot;
+	uint32_t off_bar, off_meta, off_ids, off_slot;
 	uint32_t slot_bytes;    // Q region (also the V staging of the finished tile) + face region
 	uint32_t q_bytes;       // Q region: max(smax * QB, box_cells * VB) rounded up to 1024
+	int pf_dist;            // L2 prefetch distance (see PipeGeom)
 };
 constexpr int kGradGroupThreads = 128, kGradGroups = 4;
 constexpr int kGradThreadsTotal = kGradGroups * kGradGroupThreads + kPipeProducerThreads;
@@ -454,7 +528,7 @@ __global__ void __launch_bounds__(kGradThreadsTotal, 1)
 
 	if (threadIdx.x == 0) {
 		for (int s = 0; s < NS; s++) {
-			mbar_init(full + s, 1 + kPipeProducerThreads);
+			mbar_init(full + s, 1 + kPipeProducerThreads - 32);
 			mbar_init(empty + s, 1);
 		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -463,73 +537,78 @@ __global__ void __launch_bounds__(kGradThreadsTotal, 1)
 	if ((int)blockIdx.x >= n_tiles) return;
 
 	if (threadIdx.x >= NG * GT) {
-		// ============================ producers ==================================================================
+		// ============================ producers (roles as in k_stage_pipe) ========================================
 		const int ptid = threadIdx.x - NG * GT, pwarp = ptid >> 5;
 		int* ids_all = reinterpret_cast<int*>(sm + pg.off_ids);
+		TileMeta* meta_all = reinterpret_cast<TileMeta*>(sm + pg.off_meta);
+		const int hpitch = (pg.hmax + 3) & ~3;
 		const unsigned char* qsrc = reinterpret_cast<const unsigned char*>(q);
-		struct Need {
-			int c0, halo_off, nh, f_off, nf;
-		};
-		auto need_of = [&](int tile) {
-			const TileDesc d = tv.tiles[tile0 + tile];
-			return Need{d.c0, d.halo_off, d.nh, d.f_off, d.nfo + d.ninc};
-		};
-		int t = blockIdx.x;
-		Need td = need_of(t);
-		int idr[kPipeMaxHaloRegs];
-#pragma unroll
-		for (int k = 0; k < kPipeMaxHaloRegs; k++) idr[k] = (pwarp == 0 && (lane + 32 * k) < td.nh) ? tv.halo_cell[td.halo_off + lane + 32 * k] : 0;
-		Need tdn = td;
-		if (t + G < n_tiles) tdn = need_of(t + G);
-		for (int i = 0;; i++, t += G) {
-			const int slot = i % NS;
-			const uint32_t use = (uint32_t)(i / NS);
-			int* ids = ids_all + slot * pg.hmax;
-			if (pwarp == 0) {
-#pragma unroll
-				for (int k = 0; k < kPipeMaxHaloRegs; k++)
-					if (lane + 32 * k < td.nh) ids[lane + 32 * k] = idr[k];
+		const int my_tiles = (n_tiles - (int)blockIdx.x + G - 1) / G;
+		const TileDesc* my_desc = tv.tiles + tile0 + blockIdx.x;
+		if (pwarp == 0) {
+			for (int j = 0; j < kMetaAhead; j++) {
+				if (j < my_tiles) meta_publish(meta_of(my_desc + (size_t)j * G), meta_all + j % kMetaRing, ids_all + (j % kMetaRing) * hpitch, tv.halo_cell, lane);
+				asm volatile("cp.async.commit_group;" ::: "memory");
 			}
-			named_bar(1 + NG, kPipeProducerThreads);
-			const bool has_next = t + G < n_tiles;
-			Need tdnn = tdn;
-			if (has_next) {
-				if (pwarp == 0) {
-#pragma unroll
-					for (int k = 0; k < kPipeMaxHaloRegs; k++) idr[k] = (lane + 32 * k) < tdn.nh ? tv.halo_cell[tdn.halo_off + lane + 32 * k] : 0;
-				}
-				if (t + 2 * G < n_tiles) tdnn = need_of(t + 2 * G);
-			}
-			mbar_wait(empty + slot, (use & 1u) ^ 1u);
-			unsigned char* Qs = sm + pg.off_slot + (size_t)slot * pg.slot_bytes;
-			unsigned char* Fs = Qs + pg.q_bytes;
-			if (ptid == 0) {
+			TileMeta mA{}, mB{};
+			if (kMetaAhead < my_tiles) mA = meta_of(my_desc + (size_t)kMetaAhead * G);
+			if (kMetaAhead + 1 < my_tiles) mB = meta_of(my_desc + (size_t)(kMetaAhead + 1) * G);
+			const int PD = pg.pf_dist;
+			for (int i = 0; i < my_tiles; i++) {
+				const int slot = i % NS;
+				const uint32_t use = (uint32_t)(i / NS);
+				asm volatile("cp.async.wait_group %0;" ::"n"(kMetaAhead - 1) : "memory");
+				__syncwarp();
+				named_bar(1 + NG, kPipeProducerThreads);
+				const TileMeta* td = meta_all + i % kMetaRing;
+				const int c0 = td->c0, f_off = td->f_off, nf = td->nf;
+				if (i + kMetaAhead < my_tiles) meta_publish(mA, meta_all + (i + kMetaAhead) % kMetaRing, ids_all + ((i + kMetaAhead) % kMetaRing) * hpitch, tv.halo_cell, lane);
+				asm volatile("cp.async.commit_group;" ::: "memory");
+				mA = mB;
+				if (i + kMetaAhead + 2 < my_tiles) mB = meta_of(my_desc + (size_t)(i + kMetaAhead + 2) * G);
+				mbar_wait(empty + slot, (use & 1u) ^ 1u);
+				unsigned char* Qs = sm + pg.off_slot + (size_t)slot * pg.slot_bytes;
+				const uint32_t fs = smem_u32(Qs + pg.q_bytes);
 				// the tile's slice of the face tables starts on a 16-byte boundary (the plan pads f_off to a multiple of 4) and is
 				// copied in whole 16-byte units (the tables are padded behind the last tile)
-				const uint32_t nf4 = (uint32_t)(td.nf + 3) & ~3u;
-				mbar_arrive_expect_tx(full + slot, (uint32_t)pg.box_cells * QB + nf4 * (uint32_t)((D + 1) * sizeof(R) + 4));
-				tma_load_2d(smem_u32(Qs), &map_q, 0, td.c0, full + slot);
+				const uint32_t nf4 = (uint32_t)(nf + 3) & ~3u;
+				if (lane == 0) {
+					mbar_arrive_expect_tx(full + slot, (uint32_t)pg.box_cells * QB + nf4 * (uint32_t)((D + 1) * sizeof(R) + 4));
+					tma_load_2d(smem_u32(Qs), &map_q, 0, c0, full + slot);
+				}
 				if (nf4) {
-#pragma unroll
-					for (int k = 0; k < D; k++) bulk_load(smem_u32(Fs) + (uint32_t)k * frow, tv.fS + (size_t)k * tv.T + td.f_off, nf4 * (uint32_t)sizeof(R), full + slot);
-					bulk_load(smem_u32(Fs) + (uint32_t)D * frow, tv.fw + td.f_off, nf4 * (uint32_t)sizeof(R), full + slot);
-					bulk_load(smem_u32(Fs) + (uint32_t)(D + 1) * frow, tv.f_idx + td.f_off, nf4 * 4u, full + slot);
+					if (lane >= 1 && lane < 1 + D) bulk_load(fs + (uint32_t)(lane - 1) * frow, tv.fS + (size_t)(lane - 1) * tv.T + f_off, nf4 * (uint32_t)sizeof(R), full + slot);
+					if (lane == 1 + D) bulk_load(fs + (uint32_t)D * frow, tv.fw + f_off, nf4 * (uint32_t)sizeof(R), full + slot);
+					if (lane == 2 + D) bulk_load(fs + (uint32_t)(D + 1) * frow, tv.f_idx + f_off, nf4 * 4u, full + slot);
+				}
+				if (PD > 0 && lane >= 8 && lane < 16 && i + PD < my_tiles) {
+					const TileMeta pm = meta_of(my_desc + (size_t)(i + PD) * G);
+					const int ac0 = pm.c0, af = pm.f_off;
+					const uint32_t pf4 = (uint32_t)(pm.nf + 3) & ~3u;
+					if (lane == 8) bulk_prefetch_l2(qsrc + (size_t)ac0 * QB, (uint32_t)pg.box_cells * QB);
+					if (pf4) {
+						if (lane == 9) bulk_prefetch_l2(tv.f_idx + af, pf4 * 4u);
+						if (lane >= 10 && lane < 10 + D) bulk_prefetch_l2(tv.fS + (size_t)(lane - 10) * tv.T + af, pf4 * (uint32_t)sizeof(R));
+						if (lane == 10 + D) bulk_prefetch_l2(tv.fw + af, pf4 * (uint32_t)sizeof(R));
+					}
 				}
 			}
-			const uint32_t q0 = smem_u32(Qs);
-			const int nq = td.nh * CQ;
-#pragma unroll 4
-			for (int it = ptid; it < nq; it += kPipeProducerThreads) {
-				const int cell = it / CQ, ch = it % CQ;
-				const size_t x = (size_t)ids[cell];
-				cp_async16(q0 + swz((uint32_t)(pg.box_cells + cell) * QB + (uint32_t)ch * 16u, swz_mask(QB)), qsrc + x * QB + ch * 16);
+			asm volatile("cp.async.wait_all;" ::: "memory");
+		} else {
+			constexpr int NG_ = kPipeProducerThreads - 32;
+			const int gtid = ptid - 32;
+			for (int i = 0; i < my_tiles; i++) {
+				const int slot = i % NS;
+				const uint32_t use = (uint32_t)(i / NS);
+				named_bar(1 + NG, kPipeProducerThreads);
+				const int nh = meta_all[i % kMetaRing].nh;
+				const int* ids = ids_all + (i % kMetaRing) * hpitch;
+				mbar_wait(empty + slot, (use & 1u) ^ 1u);
+				copy_halo_records<QB, NG_>(smem_u32(sm + pg.off_slot + (size_t)slot * pg.slot_bytes), qsrc, ids, nh, pg.box_cells, gtid);
+				cp_async_mbar_arrive_noinc(full + slot);
 			}
-			cp_async_mbar_arrive_noinc(full + slot);
-			if (!has_next) break;
-			td = tdn;
-			tdn = tdnn;
+			asm volatile("cp.async.wait_all;" ::: "memory");
 		}
-		asm volatile("cp.async.wait_all;" ::: "memory");
 		return;
 	}
 

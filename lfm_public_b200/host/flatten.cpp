@@ -321,6 +321,11 @@ void FlatMesh::buildAll() {
 			wallPatchIds_.push_back(b);
 			wallPatchNames_.push_back(p.name);
 		}
+		// `type farfield` (cfd_v0.cpp:986-988, 1136-1215) picks the inlet or the outlet state per face from the sign of
+		// Udirection . S with Udirection = (cos, sin)(m_dAoA): the reference never assigns m_dAoA (api/cfdv0_solver.h:141 is its only
+		// other mention), so its farfield ghosts depend on an uninitialised value.  There is no defined behaviour to reproduce:
+		// refuse the case instead of running it with ghosts that were never set.
+		if (p.type == "farfield") fail("patch '" + p.name + "' has type farfield: not served (the reference's farfield state reads the unset m_dAoA)");
 		if (p.type == "patch") {
 			if (p.name == "inlet" || p.name == "Inlet" || p.name == "Inflow" || p.name == "inflow") patchKind[(size_t)b] = LFMGPU_BC_INLET;
 			if (p.name == "outlet" || p.name == "Outlet" || p.name == "Outflow" || p.name == "outflow") patchKind[(size_t)b] = LFMGPU_BC_OUTLET;

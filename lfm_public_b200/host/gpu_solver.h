@@ -459,6 +459,11 @@ private:
 		}
 		// physical boundary ghosts (cfd_v0.cpp:382-431, roles :973-1005)
 		std::vector<int32_t> bc_cell((size_t)n_bc), bc_kind((size_t)n_bc, LFMGPU_BC_NONE), bc_patch((size_t)n_bc), bc_face((size_t)n_bc, 0);
+		// farfield patches: the reference's ghost state depends on m_dAoA, which it never assigns (cfd_v0.cpp:1141): not served
+		if (!B.m_nFarfieldBCList.empty()) {
+			fprintf(stderr, "lfmgpu: boundary patch of type farfield: not served by the GPU solver (the reference reads the unset m_dAoA there)\n");
+			MPI_Abort(MPI_COMM_WORLD, 706);
+		}
 		auto role = [&](int p) {
 			for (int x : B.m_nWallBCList)
 				if (x == p) return (int)LFMGPU_BC_WALL;

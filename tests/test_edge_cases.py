@@ -39,3 +39,20 @@ def test_edge_case_matches_reference(name, tmp_path):
     assert np.isfinite(ref["rho"]).all() and len(ref["rho"]) == c.desc.n_cells
     for k in ("rho", "U", "E", "p"):
         assert np.array_equal(mine[k], ref[k]), f"{name} {k}"
+
+
+def test_farfield_patch_is_refused(tmp_path):
+    """`type farfield` (cfd_v0.cpp:1136-1215): the reference's ghost state there depends on m_dAoA, which it never assigns, so the
+    GPU path's host side refuses the case loudly instead of advancing it with ghosts nobody set."""
+    import re
+    from lfm_public_b200 import host_api
+    from lfm_public_b200.tools import casegen, meshgen
+    d = str(tmp_path / "ff")
+    casegen.write_case(d, meshgen.hex_box(4, 3, 1, lengths=(4, 3, 0.1), two_d=True), two_d=True, solver=0, dimension=2, deltaT=1e-3, endTime=1e-2)
+    bfile = os.path.join(d, "constant", "polyMesh", "boundary")
+    s = open(bfile).read()
+    s2, n = re.subn(r"(outlet\s*\{\s*type\s+)patch", r"\1farfield", s)
+    assert n == 1
+    open(bfile, "w").write(s2)
+    with pytest.raises(Exception, match="farfield"):
+        host_api.Case.open(d).finish()
