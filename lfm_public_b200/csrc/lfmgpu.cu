@@ -165,8 +165,8 @@ struct lfmgpu_ctx {
 	bool pipe_ok = false;              // tensor maps and ring geometry are in place
 	int pipe_enable = 3;               // LFMGPU_PIPE: bit 0 stage kernel, bit 1 gradient kernel; 0: the tile kernels of round 1 serve everything
 	int pipe_slots_cap = 4;            // LFMGPU_PIPE_SLOTS
-	int pipe_pf_dist = 0;              // L2 prefetch distance of the persistent kernels in tiles per CTA (LFMGPU_PIPE_PF, 0: off)
-	int pipe_grad_slots_cap = 8;       // LFMGPU_PIPE_GSLOTS
+	int pipe_pf_dist = 3;              // L2 prefetch distance of the persistent kernels in tiles per CTA (LFMGPU_PIPE_PF, 0: off)
+	int pipe_grad_slots_cap = 9;       // LFMGPU_PIPE_GSLOTS
 	int pipe_spare_sms = 8;            // SMs left to the halo stream's kernels on a rank with neighbours (LFMGPU_PIPE_SPARE)
 	int n_sms = 0;
 	PipeGeom pipe{};
@@ -728,6 +728,7 @@ int pipe_setup(lfmgpu_ctx* h) {
 	PipeGeom g{};
 	g.box_cells = TC;
 	g.pf_dist = h->pipe_pf_dist;
+	g.dbg = getenv("LFMGPU_PIPE_DBG") ? atoi(getenv("LFMGPU_PIPE_DBG")) : 0;
 	g.hmax = hmax;
 	g.smax = TC + hmax;
 	g.fmax = (fmax + 3) / 4 * 4;
@@ -736,9 +737,9 @@ int pipe_setup(lfmgpu_ctx* h) {
 	for (int ns = std::min(4, h->pipe_slots_cap); ns >= 2; ns--) {
 		g.n_slots = ns;
 		g.off_bar = 0;
-		g.off_meta = 128;   // barriers (16 bytes per slot) in front
-		g.off_ids = g.off_meta + kMetaRing * (uint32_t)sizeof(TileMeta);
-		g.off_fl = round_up(g.off_ids + (uint32_t)kMetaRing * ((hmax + 3) / 4 * 4) * 4u, 128);
+		g.off_meta = 128;   // slot barriers (16 bytes per slot) in front, then the producers' id-ring barriers and the id rings
+		g.off_ids = g.off_meta + 2 * kProducerWarps * 8;
+		g.off_fl = round_up(g.off_ids + (uint32_t)(2 * kProducerWarps) * ((hmax + 3) / 4 * 4) * 4u, 128);
 		g.off_slot = round_up(g.off_fl + 2u * (uint32_t)h->NQ * g.fmax * (uint32_t)h->prec, 1024);
 		const size_t total = (size_t)g.off_slot + (size_t)ns * g.slot_bytes + 1024;   // + slack to align the base to 1024
 		if (total <= (size_t)dev_smem) {
@@ -753,18 +754,20 @@ int pipe_setup(lfmgpu_ctx* h) {
 	if (TC <= kGradGroupThreads) {
 		GradGeom gg{};
 		gg.box_cells = TC;
-		gg.pf_dist = h->pipe_pf_dist;
+		gg.pf_dist = getenv("LFMGPU_PIPE_GPF") ? atoi(getenv("LFMGPU_PIPE_GPF")) : 0;   // (the gradient kernel's fills are short: prefetching them measured slower)
+		gg.dbg = g.dbg;
 		gg.hmax = hmax;
 		gg.smax = TC + hmax;
 		gg.fmax = g.fmax;
-		gg.q_bytes = round_up(std::max((uint32_t)gg.smax * QB, (uint32_t)TC * VB), 1024);
-		gg.slot_bytes = gg.q_bytes + round_up((uint32_t)gg.fmax * (uint32_t)((D + 1) * h->prec + 4), 1024);
-		for (int ns = std::max(kGradGroups, std::min(8, h->pipe_grad_slots_cap)); ns >= kGradGroups; ns--) {
+		gg.q_bytes = round_up(std::max((uint32_t)gg.smax * QB, (uint32_t)TC * VB), 128);
+		gg.slot_bytes = round_up(gg.q_bytes + (uint32_t)gg.fmax * (uint32_t)((D + 1) * h->prec + 4), 1024);   // only the Q region needs the swizzle's alignment
+		for (int ns = std::max(kGradGroups, std::min(9, h->pipe_grad_slots_cap)); ns >= kGradGroups; ns--) {
+			if ((2 * ns) % kGradGroups) continue;   // see stage_pipe.cuh: the depth must keep a slot's use k - 2 inside the waiting group
 			gg.n_slots = ns;
 			gg.off_bar = 0;
 			gg.off_meta = 128;
-			gg.off_ids = gg.off_meta + kMetaRing * (uint32_t)sizeof(TileMeta);
-			gg.off_slot = round_up(gg.off_ids + (uint32_t)kMetaRing * ((hmax + 3) / 4 * 4) * 4u, 1024);
+			gg.off_ids = gg.off_meta + 2 * kProducerWarps * 8;
+			gg.off_slot = round_up(gg.off_ids + (uint32_t)(2 * kProducerWarps) * ((hmax + 3) / 4 * 4) * 4u, 1024);
 			const size_t total = (size_t)gg.off_slot + (size_t)ns * gg.slot_bytes + 1024;
 			if (total <= (size_t)dev_smem) {
 				h->gpipe = gg;

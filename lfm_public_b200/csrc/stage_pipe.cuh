@@ -155,37 +155,36 @@ template <int B, int NTHR> __device__ __forceinline__ void copy_halo_records(uin
 	}
 }
 
-// ---- the descriptor warp's metadata ring --------------------------------------------------------------------------------
-// Warp 0 of the producers runs kMetaAhead tiles ahead of the fills: the descriptor of tile i + kMetaAhead (read from global
-// memory two more iterations earlier, so that no load is waited for) goes into a ring in shared memory and the tile's halo
-// cell ids follow it with 16-byte cp.async copies (the plan pads every halo list to a 16-byte boundary), one commit group
-// per tile; `cp.async.wait_group kMetaAhead - 1` at the top of iteration i then guarantees tile i's ids.  The lookahead is
-// what lets the fill rate exceed one tile per global-memory round trip (the gradient kernel's tiles take less than that).
-constexpr int kMetaAhead = 3, kMetaRing = kMetaAhead + 2;
+// ---- producer warps ---------------------------------------------------------------------------------------------------
+// Each of the four producer warps is a complete producer for the tiles of "its" ring slots (tile i of the CTA uses slot i % NS
+// and belongs to warp (i % NS) % 4, so the uses of one slot are filled in order by one warp -- a second warp could reach the
+// slot two phases early, which a parity wait cannot tell from "released"): a serial loop per tile costs about two thousand cycles of dependent latencies (barrier tests, shared-memory
+// round trips, descriptor fetch), which one warp alone cannot hide when a tile's arithmetic is shorter than that (the
+// gradient kernel); four independent loops can.  Per tile a warp
+//   * has the tile's descriptor fields in registers (read from global memory two of its own iterations earlier) and the tile's
+//     halo cell ids in its private two-deep ring in shared memory (a TMA bulk copy issued one iteration earlier, completion
+//     on the ring's own mbarrier: the plan pads every halo list to a 16-byte boundary);
+//   * waits for the ring slot to be released, then issues the TMA loads of the own cells and the 16-byte cp.async copies of
+//     the halo records, whose completion arrives on the slot's `full` mbarrier.
+constexpr int kProducerWarps = 4;
 struct TileMeta {
-	int c0, nh, halo_off, f_off, nf, pad[3];   // 32 bytes
+	int c0, nh, halo_off, f_off, nf;
 };
 __device__ __forceinline__ TileMeta meta_of(const TileDesc* d) {
 	const int4 a = *reinterpret_cast<const int4*>(d);              // c0, nt, halo_off, nh
 	const int4 b = *reinterpret_cast<const int4*>(&d->f_off);      // f_off, nfo, ninc, hb
-	TileMeta mt;
-	mt.c0 = a.x;
-	mt.nh = a.w;
-	mt.halo_off = a.z;
-	mt.f_off = b.x;
-	mt.nf = b.y + b.z;
-	return mt;
+	return TileMeta{a.x, a.w, a.z, b.x, b.y + b.z};
 }
-// publishes the metadata of one tile: descriptor fields by lane 0, halo ids by asynchronous copies of the whole warp
-__device__ __forceinline__ void meta_publish(const TileMeta& mt, TileMeta* ring_meta, int* ring_ids, const int* __restrict__ halo_cell, int lane) {
-	if (lane == 0) {
-		ring_meta->c0 = mt.c0;
-		ring_meta->nh = mt.nh;
-		ring_meta->f_off = mt.f_off;
-		ring_meta->nf = mt.nf;
+// lane 0: start the bulk copy of a tile's halo ids into an id ring slot (nothing to copy: a plain arrival completes the phase)
+__device__ __forceinline__ void ids_fetch(const TileMeta& mt, int* ring_ids, uint64_t* bar, const int* __restrict__ halo_cell) {
+	const uint32_t bytes = ((uint32_t)mt.nh + 3u) / 4u * 16u;
+	if (bytes) {
+		mbar_arrive_expect_tx(bar, bytes);
+		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(ring_ids)), "l"(halo_cell + mt.halo_off), "r"(bytes), "r"(smem_u32(bar))
+		             : "memory");
+	} else {
+		mbar_arrive(bar);
 	}
-	const uint32_t dst = smem_u32(ring_ids);
-	for (int k = lane * 4; k < mt.nh; k += 128) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)k * 4u), "l"(halo_cell + mt.halo_off + k));
 }
 
 // what the host passes about the ring (all byte offsets from the 1024-aligned start of dynamic shared memory)
@@ -196,14 +195,16 @@ struct PipeGeom {
 	int fmax;               // faces per tile (stride of the flux rows)
 	int hmax;               // largest halo
 	uint32_t off_bar;       // full[n_slots], empty[n_slots]
-	uint32_t off_ids;       // [kMetaRing][hmax4] int halo ids, preceded by [kMetaRing] TileMeta (off_meta)
-	uint32_t off_meta;
+	uint32_t off_ids;       // [kProducerWarps][2][hmax4] int: the producer warps' halo id rings
+	uint32_t off_meta;      // [kProducerWarps][2] mbarriers of the id rings
 	uint32_t off_fl;        // [2][NQ][fmax] R face fluxes
 	uint32_t off_slot;      // first ring slot
 	uint32_t slot_bytes;    // Q region + V region (each a multiple of 1024)
 	uint32_t q_bytes;       // Q region
 	int pf_dist;            // L2 prefetch distance in tiles of this CTA (0: none): own-cell records and face-table slices of the tile
 	                        // pf_dist fills ahead are requested into the L2, so that a fill costs an L2 round trip, not a DRAM one
+	int dbg;                // timing experiments only (wrong results): bit 0 no halo copies, bit 1 no own-cell loads, bit 2 consumers skip
+	                        // the arithmetic (wait for the slot, release it): LFMGPU_PIPE_DBG
 };
 
 constexpr int kPipeGroupThreads = 256;                      // one consumer group (two warpgroups)
@@ -290,9 +291,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 
 	if (threadIdx.x == 0) {
 		for (int s = 0; s < NS; s++) {
-			mbar_init(full + s, 1 + kPipeProducerThreads - 32);   // the expect_tx arrival + one cp.async arrival per gather thread
-			mbar_init(empty + s, 1);                              // one elected consumer thread
+			mbar_init(full + s, 1 + 32);   // the expect_tx arrival + one cp.async arrival per lane of the tile's producer warp
+			mbar_init(empty + s, 1);       // one elected consumer thread
 		}
+		for (int k = 0; k < 2 * kProducerWarps; k++) mbar_init(reinterpret_cast<uint64_t*>(sm + pg.off_meta) + k, 1);   // the producers' id rings
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
@@ -305,79 +307,73 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 		//   warps 1-3  the 16-byte cp.async copies of the halo records.
 		asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kPipeProducerRegs));
 		if ((int)blockIdx.x >= n_tiles) return;
-		const int ptid = threadIdx.x - 2 * GT, pwarp = ptid >> 5;
-		int* ids_all = reinterpret_cast<int*>(sm + pg.off_ids);
-		TileMeta* meta_all = reinterpret_cast<TileMeta*>(sm + pg.off_meta);
+		const int pwarp = (threadIdx.x - 2 * GT) >> 5;
 		const int hpitch = (pg.hmax + 3) & ~3;
+		int* idring = reinterpret_cast<int*>(sm + pg.off_ids) + pwarp * 2 * hpitch;
+		uint64_t* idbar = reinterpret_cast<uint64_t*>(sm + pg.off_meta) + pwarp * 2;
 		const unsigned char* qsrc = reinterpret_cast<const unsigned char*>(q);
 		const unsigned char* vsrc = reinterpret_cast<const unsigned char*>(m.vis);
 		const int my_tiles = (n_tiles - (int)blockIdx.x + G - 1) / G;
 		const TileDesc* my_desc = tv.tiles + tile0 + blockIdx.x;   // tile i of this CTA: my_desc[i * G]
-		if (pwarp == 0) {
-			// prologue: the metadata of the first kMetaAhead tiles; descriptors of the next two in registers
-			for (int j = 0; j < kMetaAhead; j++) {
-				if (j < my_tiles) meta_publish(meta_of(my_desc + (size_t)j * G), meta_all + j % kMetaRing, ids_all + (j % kMetaRing) * hpitch, tv.halo_cell, lane);
-				asm volatile("cp.async.commit_group;" ::: "memory");
-			}
-			TileMeta mA{}, mB{};
-			if (kMetaAhead < my_tiles) mA = meta_of(my_desc + (size_t)kMetaAhead * G);
-			if (kMetaAhead + 1 < my_tiles) mB = meta_of(my_desc + (size_t)(kMetaAhead + 1) * G);
-			const int PD = pg.pf_dist;
-			for (int i = 0; i < my_tiles; i++) {
-				const int slot = i % NS;
-				const uint32_t use = (uint32_t)(i / NS);
-				asm volatile("cp.async.wait_group %0;" ::"n"(kMetaAhead - 1) : "memory");   // this lane's share of tile i's ids has landed
-				__syncwarp();
-				named_bar(3, kPipeProducerThreads);   // tile i's metadata is published to the gather warps
-				const int c0 = meta_all[i % kMetaRing].c0;
-				// metadata of tile i + kMetaAhead (its descriptor was read two iterations ago), descriptor of tile i + kMetaAhead + 2
-				if (i + kMetaAhead < my_tiles) meta_publish(mA, meta_all + (i + kMetaAhead) % kMetaRing, ids_all + ((i + kMetaAhead) % kMetaRing) * hpitch, tv.halo_cell, lane);
-				asm volatile("cp.async.commit_group;" ::: "memory");
-				mA = mB;
-				if (i + kMetaAhead + 2 < my_tiles) mB = meta_of(my_desc + (size_t)(i + kMetaAhead + 2) * G);
-				mbar_wait(empty + slot, (use & 1u) ^ 1u);   // the consumers have released this slot (passes at once on its first use)
-				if (lane == 0) {
-					unsigned char* Qs = sm + pg.off_slot + (size_t)slot * pg.slot_bytes;
+		auto next_mine = [&](int i) {   // the next tile of this CTA (after i) whose slot this warp serves; >= my_tiles: none
+			do i++;
+			while (i < my_tiles && (i % NS) % kProducerWarps != pwarp);
+			return i;
+		};
+		int i = next_mine(-1);
+		if (i >= my_tiles) return;
+		int i1 = next_mine(i), i2 = next_mine(i1);
+		TileMeta cur = meta_of(my_desc + (size_t)i * G), nxt = cur;
+		if (lane == 0) ids_fetch(cur, idring, idbar, tv.halo_cell);
+		if (i1 < my_tiles) nxt = meta_of(my_desc + (size_t)i1 * G);
+		const int PD = pg.pf_dist;
+		for (int j = 0; i < my_tiles; i = i1, i1 = i2, i2 = next_mine(i2), j++) {
+			const int slot = i % NS;
+			const uint32_t use = (uint32_t)(i / NS);
+			const bool has_next = i1 < my_tiles;
+			// the next tile's halo ids start travelling, the descriptor of the tile after it is requested
+			if (has_next && lane == 0) ids_fetch(nxt, idring + ((j + 1) & 1) * hpitch, idbar + ((j + 1) & 1), tv.halo_cell);
+			TileMeta nn = nxt;
+			if (i2 < my_tiles) nn = meta_of(my_desc + (size_t)i2 * G);
+			mbar_wait(idbar + (j & 1), (uint32_t)(j >> 1) & 1u);      // this tile's halo ids are in the ring
+			mbar_wait(empty + slot, (use & 1u) ^ 1u);                  // the consumers have released the slot (passes at once on its first use)
+			const uint32_t q0 = smem_u32(sm + pg.off_slot + (size_t)slot * pg.slot_bytes);
+			if (lane == 0) {
+				if (pg.dbg & 2) {
+					mbar_arrive(full + slot);
+				} else {
 					mbar_arrive_expect_tx(full + slot, (uint32_t)pg.box_cells * (QB + VB));
-					tma_load_2d(smem_u32(Qs), &map_q, 0, c0, full + slot);
-					tma_load_2d(smem_u32(Qs + pg.q_bytes), &map_v, 0, c0, full + slot);
-				}
-				// L2 prefetch of the tile PD fills ahead: its own-cell records (two contiguous pieces) and its slice of each face table
-				if (PD > 0 && lane < 16 && i + PD < my_tiles) {
-					const TileMeta pm = meta_of(my_desc + (size_t)(i + PD) * G);
-					const int ac0 = pm.c0, af = pm.f_off;
-					const uint32_t nf4 = (uint32_t)(pm.nf + 3) & ~3u;
-					if (lane == 0) bulk_prefetch_l2(qsrc + (size_t)ac0 * QB, (uint32_t)pg.box_cells * QB);
-					if (lane == 1) bulk_prefetch_l2(vsrc + (size_t)ac0 * VB, (uint32_t)pg.box_cells * VB);
-					if (nf4) {
-						if (lane == 2) bulk_prefetch_l2(tv.f_idx + af, nf4 * 4u);
-						if (lane >= 3 && lane < 3 + D) bulk_prefetch_l2(tv.fS + (size_t)(lane - 3) * tv.T + af, nf4 * (uint32_t)sizeof(R));
-						if (lane >= 3 + D && lane < 3 + 2 * D) bulk_prefetch_l2(tv.fK + (size_t)(lane - 3 - D) * tv.T + af, nf4 * (uint32_t)sizeof(R));
-						if (lane == 3 + 2 * D) bulk_prefetch_l2(tv.fw + af, nf4 * (uint32_t)sizeof(R));
-						if (lane == 4 + 2 * D) bulk_prefetch_l2(tv.fdm + af, nf4 * (uint32_t)sizeof(R));
-						if (lane == 5 + 2 * D) bulk_prefetch_l2(tv.fdi + af, nf4 * (uint32_t)sizeof(R));
-						if (SCHEME == 0 && lane == 6 + 2 * D) bulk_prefetch_l2(tv.fSmag + af, nf4 * (uint32_t)sizeof(R));
-					}
+					tma_load_2d(q0, &map_q, 0, cur.c0, full + slot);
+					tma_load_2d(q0 + pg.q_bytes, &map_v, 0, cur.c0, full + slot);
 				}
 			}
-			asm volatile("cp.async.wait_all;" ::: "memory");
-		} else {
-			constexpr int NG_ = kPipeProducerThreads - 32;   // gather threads
-			const int gtid = ptid - 32;
-			for (int i = 0; i < my_tiles; i++) {
-				const int slot = i % NS;
-				const uint32_t use = (uint32_t)(i / NS);
-				named_bar(3, kPipeProducerThreads);
-				const int nh = meta_all[i % kMetaRing].nh;
-				const int* ids = ids_all + (i % kMetaRing) * hpitch;
-				mbar_wait(empty + slot, (use & 1u) ^ 1u);
-				const uint32_t q0 = smem_u32(sm + pg.off_slot + (size_t)slot * pg.slot_bytes);
-				copy_halo_records<QB, NG_>(q0, qsrc, ids, nh, pg.box_cells, gtid);
-				copy_halo_records<VB, NG_>(q0 + pg.q_bytes, vsrc, ids, nh, pg.box_cells, gtid);
-				cp_async_mbar_arrive_noinc(full + slot);
+			if (!(pg.dbg & 1)) {
+				const int* ids = idring + (j & 1) * hpitch;
+				copy_halo_records<QB, 32>(q0, qsrc, ids, cur.nh, pg.box_cells, lane);
+				copy_halo_records<VB, 32>(q0 + pg.q_bytes, vsrc, ids, cur.nh, pg.box_cells, lane);
 			}
-			asm volatile("cp.async.wait_all;" ::: "memory");
+			cp_async_mbar_arrive_noinc(full + slot);
+			// L2 prefetch of the tile PD fills ahead: its own-cell records (two contiguous pieces) and its slice of each face table
+			if (PD > 0 && lane < 16 && i + PD < my_tiles) {
+				const TileMeta pm = meta_of(my_desc + (size_t)(i + PD) * G);
+				const int ac0 = pm.c0, af = pm.f_off;
+				const uint32_t nf4 = (uint32_t)(pm.nf + 3) & ~3u;
+				if (lane == 0) bulk_prefetch_l2(qsrc + (size_t)ac0 * QB, (uint32_t)pg.box_cells * QB);
+				if (lane == 1) bulk_prefetch_l2(vsrc + (size_t)ac0 * VB, (uint32_t)pg.box_cells * VB);
+				if (nf4) {
+					if (lane == 2) bulk_prefetch_l2(tv.f_idx + af, nf4 * 4u);
+					if (lane >= 3 && lane < 3 + D) bulk_prefetch_l2(tv.fS + (size_t)(lane - 3) * tv.T + af, nf4 * (uint32_t)sizeof(R));
+					if (lane >= 3 + D && lane < 3 + 2 * D) bulk_prefetch_l2(tv.fK + (size_t)(lane - 3 - D) * tv.T + af, nf4 * (uint32_t)sizeof(R));
+					if (lane == 3 + 2 * D) bulk_prefetch_l2(tv.fw + af, nf4 * (uint32_t)sizeof(R));
+					if (lane == 4 + 2 * D) bulk_prefetch_l2(tv.fdm + af, nf4 * (uint32_t)sizeof(R));
+					if (lane == 5 + 2 * D) bulk_prefetch_l2(tv.fdi + af, nf4 * (uint32_t)sizeof(R));
+					if (SCHEME == 0 && lane == 6 + 2 * D) bulk_prefetch_l2(tv.fSmag + af, nf4 * (uint32_t)sizeof(R));
+				}
+			}
+			cur = nxt;
+			nxt = nn;
 		}
+		asm volatile("cp.async.wait_all;" ::: "memory");
 		return;
 	}
 
@@ -411,6 +407,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 		// filled for THIS use, nothing else), then for this fill.
 		if (use) mbar_wait(empty + slot, (use - 1u) & 1u);
 		mbar_wait(full + slot, use & 1u);
+		if (pg.dbg & 4) {   // timing experiment: the fill pipeline alone
+			named_bar(bar_id, GT);
+			if (tid == 0) mbar_arrive(empty + slot);
+			if (!has_next) break;
+			td = tdn;
+			continue;
+		}
 
 		// ---- B: every face of the tile once ----------------------------------------------------------------
 		for (int lf = tid; lf < nf; lf += GT) {
@@ -494,7 +497,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 // calc_VIS (cfd_v0.cpp:1744-1860) as a persistent, TMA-fed kernel: same producer / ring as k_stage_pipe, with
 //   * per slot: the Q records of tile + halo (TMA box + 16-byte cp.async, swizzled) and the tile's slice of the tile-ordered
 //     face tables S[D], w, idx (contiguous per tile: D + 2 linear bulk copies, cp.async.bulk.shared::cta.global);
-//   * four consumer groups of 128 threads on alternate tiles: one thread per cell walks the cell's faces in ascending face
+//   * three consumer groups of 128 threads on alternate tiles: one thread per cell walks the cell's faces in ascending face
 //     id (the reference's summation order), forms dudx / dTdx / sigmaU / tr and writes the cell's V record into the slot's
 //     (by then dead) Q region, from where ONE bulk store takes the tile's V records to HBM.
 // ---------------------------------------------------------------------------------------------------------------------
@@ -504,8 +507,12 @@ struct GradGeom {
 	uint32_t slot_bytes;    // Q region (also the V staging of the finished tile) + face region
 	uint32_t q_bytes;       // Q region: max(smax * QB, box_cells * VB) rounded up to 1024
 	int pf_dist;            // L2 prefetch distance (see PipeGeom)
+	int dbg;                // timing experiments (see PipeGeom)
 };
-constexpr int kGradGroupThreads = 128, kGradGroups = 4;
+// Ring depth and group count are tied: a group reaches use k of a slot knowing only that ITS OWN earlier tiles were
+// released; the parity wait for the release of use k - 1 is unambiguous only if use k - 2 (tile i - 2 NS) was one of them,
+// i.e. 2 NS must be a multiple of the number of groups (k_stage_pipe: two groups, any depth; here three groups, depth 3 or 6).
+constexpr int kGradGroupThreads = 128, kGradGroups = 3;
 constexpr int kGradThreadsTotal = kGradGroups * kGradGroupThreads + kPipeProducerThreads;
 
 __device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -528,9 +535,10 @@ __global__ void __launch_bounds__(kGradThreadsTotal, 1)
 
 	if (threadIdx.x == 0) {
 		for (int s = 0; s < NS; s++) {
-			mbar_init(full + s, 1 + kPipeProducerThreads - 32);
+			mbar_init(full + s, 1 + 32);
 			mbar_init(empty + s, 1);
 		}
+		for (int k = 0; k < 2 * kProducerWarps; k++) mbar_init(reinterpret_cast<uint64_t*>(sm + pg.off_meta) + k, 1);   // the producers' id rings
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
@@ -538,77 +546,66 @@ __global__ void __launch_bounds__(kGradThreadsTotal, 1)
 
 	if (threadIdx.x >= NG * GT) {
 		// ============================ producers (roles as in k_stage_pipe) ========================================
-		const int ptid = threadIdx.x - NG * GT, pwarp = ptid >> 5;
-		int* ids_all = reinterpret_cast<int*>(sm + pg.off_ids);
-		TileMeta* meta_all = reinterpret_cast<TileMeta*>(sm + pg.off_meta);
+		const int pwarp = (threadIdx.x - NG * GT) >> 5;
 		const int hpitch = (pg.hmax + 3) & ~3;
+		int* idring = reinterpret_cast<int*>(sm + pg.off_ids) + pwarp * 2 * hpitch;
+		uint64_t* idbar = reinterpret_cast<uint64_t*>(sm + pg.off_meta) + pwarp * 2;
 		const unsigned char* qsrc = reinterpret_cast<const unsigned char*>(q);
 		const int my_tiles = (n_tiles - (int)blockIdx.x + G - 1) / G;
 		const TileDesc* my_desc = tv.tiles + tile0 + blockIdx.x;
-		if (pwarp == 0) {
-			for (int j = 0; j < kMetaAhead; j++) {
-				if (j < my_tiles) meta_publish(meta_of(my_desc + (size_t)j * G), meta_all + j % kMetaRing, ids_all + (j % kMetaRing) * hpitch, tv.halo_cell, lane);
-				asm volatile("cp.async.commit_group;" ::: "memory");
+		auto next_mine = [&](int i) {   // the next tile of this CTA (after i) whose slot this warp serves; >= my_tiles: none
+			do i++;
+			while (i < my_tiles && (i % NS) % kProducerWarps != pwarp);
+			return i;
+		};
+		int i = next_mine(-1);
+		if (i >= my_tiles) return;
+		int i1 = next_mine(i), i2 = next_mine(i1);
+		TileMeta cur = meta_of(my_desc + (size_t)i * G), nxt = cur;
+		if (lane == 0) ids_fetch(cur, idring, idbar, tv.halo_cell);
+		if (i1 < my_tiles) nxt = meta_of(my_desc + (size_t)i1 * G);
+		const int PD = pg.pf_dist;
+		for (int j = 0; i < my_tiles; i = i1, i1 = i2, i2 = next_mine(i2), j++) {
+			const int slot = i % NS;
+			const uint32_t use = (uint32_t)(i / NS);
+			const bool has_next = i1 < my_tiles;
+			if (has_next && lane == 0) ids_fetch(nxt, idring + ((j + 1) & 1) * hpitch, idbar + ((j + 1) & 1), tv.halo_cell);
+			TileMeta nn = nxt;
+			if (i2 < my_tiles) nn = meta_of(my_desc + (size_t)i2 * G);
+			mbar_wait(idbar + (j & 1), (uint32_t)(j >> 1) & 1u);
+			mbar_wait(empty + slot, (use & 1u) ^ 1u);
+			const uint32_t q0 = smem_u32(sm + pg.off_slot + (size_t)slot * pg.slot_bytes);
+			const uint32_t fs = q0 + pg.q_bytes;
+			// the tile's slice of the face tables starts on a 16-byte boundary (the plan pads f_off to a multiple of 4) and is
+			// copied in whole 16-byte units (the tables are padded behind the last tile)
+			const uint32_t nf4 = (uint32_t)(cur.nf + 3) & ~3u;
+			if (lane == 0) {
+				mbar_arrive_expect_tx(full + slot, ((pg.dbg & 2) ? 0u : (uint32_t)pg.box_cells * QB) + nf4 * (uint32_t)((D + 1) * sizeof(R) + 4));
+				if (!(pg.dbg & 2)) tma_load_2d(q0, &map_q, 0, cur.c0, full + slot);
 			}
-			TileMeta mA{}, mB{};
-			if (kMetaAhead < my_tiles) mA = meta_of(my_desc + (size_t)kMetaAhead * G);
-			if (kMetaAhead + 1 < my_tiles) mB = meta_of(my_desc + (size_t)(kMetaAhead + 1) * G);
-			const int PD = pg.pf_dist;
-			for (int i = 0; i < my_tiles; i++) {
-				const int slot = i % NS;
-				const uint32_t use = (uint32_t)(i / NS);
-				asm volatile("cp.async.wait_group %0;" ::"n"(kMetaAhead - 1) : "memory");
-				__syncwarp();
-				named_bar(1 + NG, kPipeProducerThreads);
-				const TileMeta* td = meta_all + i % kMetaRing;
-				const int c0 = td->c0, f_off = td->f_off, nf = td->nf;
-				if (i + kMetaAhead < my_tiles) meta_publish(mA, meta_all + (i + kMetaAhead) % kMetaRing, ids_all + ((i + kMetaAhead) % kMetaRing) * hpitch, tv.halo_cell, lane);
-				asm volatile("cp.async.commit_group;" ::: "memory");
-				mA = mB;
-				if (i + kMetaAhead + 2 < my_tiles) mB = meta_of(my_desc + (size_t)(i + kMetaAhead + 2) * G);
-				mbar_wait(empty + slot, (use & 1u) ^ 1u);
-				unsigned char* Qs = sm + pg.off_slot + (size_t)slot * pg.slot_bytes;
-				const uint32_t fs = smem_u32(Qs + pg.q_bytes);
-				// the tile's slice of the face tables starts on a 16-byte boundary (the plan pads f_off to a multiple of 4) and is
-				// copied in whole 16-byte units (the tables are padded behind the last tile)
-				const uint32_t nf4 = (uint32_t)(nf + 3) & ~3u;
-				if (lane == 0) {
-					mbar_arrive_expect_tx(full + slot, (uint32_t)pg.box_cells * QB + nf4 * (uint32_t)((D + 1) * sizeof(R) + 4));
-					tma_load_2d(smem_u32(Qs), &map_q, 0, c0, full + slot);
-				}
-				if (nf4) {
-					if (lane >= 1 && lane < 1 + D) bulk_load(fs + (uint32_t)(lane - 1) * frow, tv.fS + (size_t)(lane - 1) * tv.T + f_off, nf4 * (uint32_t)sizeof(R), full + slot);
-					if (lane == 1 + D) bulk_load(fs + (uint32_t)D * frow, tv.fw + f_off, nf4 * (uint32_t)sizeof(R), full + slot);
-					if (lane == 2 + D) bulk_load(fs + (uint32_t)(D + 1) * frow, tv.f_idx + f_off, nf4 * 4u, full + slot);
-				}
-				if (PD > 0 && lane >= 8 && lane < 16 && i + PD < my_tiles) {
-					const TileMeta pm = meta_of(my_desc + (size_t)(i + PD) * G);
-					const int ac0 = pm.c0, af = pm.f_off;
-					const uint32_t pf4 = (uint32_t)(pm.nf + 3) & ~3u;
-					if (lane == 8) bulk_prefetch_l2(qsrc + (size_t)ac0 * QB, (uint32_t)pg.box_cells * QB);
-					if (pf4) {
-						if (lane == 9) bulk_prefetch_l2(tv.f_idx + af, pf4 * 4u);
-						if (lane >= 10 && lane < 10 + D) bulk_prefetch_l2(tv.fS + (size_t)(lane - 10) * tv.T + af, pf4 * (uint32_t)sizeof(R));
-						if (lane == 10 + D) bulk_prefetch_l2(tv.fw + af, pf4 * (uint32_t)sizeof(R));
-					}
+			__syncwarp();   // the expect_tx precedes the bulk copies of the other lanes
+			if (nf4) {
+				if (lane >= 1 && lane < 1 + D) bulk_load(fs + (uint32_t)(lane - 1) * frow, tv.fS + (size_t)(lane - 1) * tv.T + cur.f_off, nf4 * (uint32_t)sizeof(R), full + slot);
+				if (lane == 1 + D) bulk_load(fs + (uint32_t)D * frow, tv.fw + cur.f_off, nf4 * (uint32_t)sizeof(R), full + slot);
+				if (lane == 2 + D) bulk_load(fs + (uint32_t)(D + 1) * frow, tv.f_idx + cur.f_off, nf4 * 4u, full + slot);
+			}
+			if (!(pg.dbg & 1)) copy_halo_records<QB, 32>(q0, qsrc, idring + (j & 1) * hpitch, cur.nh, pg.box_cells, lane);
+			cp_async_mbar_arrive_noinc(full + slot);
+			if (PD > 0 && lane >= 8 && lane < 16 && i + PD < my_tiles) {
+				const TileMeta pm = meta_of(my_desc + (size_t)(i + PD) * G);
+				const int ac0 = pm.c0, af = pm.f_off;
+				const uint32_t pf4 = (uint32_t)(pm.nf + 3) & ~3u;
+				if (lane == 8) bulk_prefetch_l2(qsrc + (size_t)ac0 * QB, (uint32_t)pg.box_cells * QB);
+				if (pf4) {
+					if (lane == 9) bulk_prefetch_l2(tv.f_idx + af, pf4 * 4u);
+					if (lane >= 10 && lane < 10 + D) bulk_prefetch_l2(tv.fS + (size_t)(lane - 10) * tv.T + af, pf4 * (uint32_t)sizeof(R));
+					if (lane == 10 + D) bulk_prefetch_l2(tv.fw + af, pf4 * (uint32_t)sizeof(R));
 				}
 			}
-			asm volatile("cp.async.wait_all;" ::: "memory");
-		} else {
-			constexpr int NG_ = kPipeProducerThreads - 32;
-			const int gtid = ptid - 32;
-			for (int i = 0; i < my_tiles; i++) {
-				const int slot = i % NS;
-				const uint32_t use = (uint32_t)(i / NS);
-				named_bar(1 + NG, kPipeProducerThreads);
-				const int nh = meta_all[i % kMetaRing].nh;
-				const int* ids = ids_all + (i % kMetaRing) * hpitch;
-				mbar_wait(empty + slot, (use & 1u) ^ 1u);
-				copy_halo_records<QB, NG_>(smem_u32(sm + pg.off_slot + (size_t)slot * pg.slot_bytes), qsrc, ids, nh, pg.box_cells, gtid);
-				cp_async_mbar_arrive_noinc(full + slot);
-			}
-			asm volatile("cp.async.wait_all;" ::: "memory");
+			cur = nxt;
+			nxt = nn;
 		}
+		asm volatile("cp.async.wait_all;" ::: "memory");
 		return;
 	}
 
@@ -617,11 +614,27 @@ __global__ void __launch_bounds__(kGradThreadsTotal, 1)
 	const int bar_id = 1 + g;
 	int t = blockIdx.x + g * G;
 	if (t >= n_tiles) return;
+	// what the gather needs from global memory travels one tile ahead: this tile's gather lists and cell volume were requested
+	// while the previous tile was computed, the next tile's descriptor is requested now
+	auto cell_inputs = [&](const TileDesc& d, int* e, R& vinv) {
+		const bool act = tid < d.nt;
+		const int c = d.c0 + (act ? tid : 0);
+#pragma unroll
+		for (int s = 0; s < kMaxSlots; s++) e[s] = (act && s < m.F) ? (int)tv.csr_local[(size_t)s * m.n_cells + c] : 0;
+		vinv = act ? m.vol_inv[c] : R(0);
+	};
+	TileDesc td = tv.tiles[tile0 + t];
+	TileDesc tdn = td;
+	if (t + NG * G < n_tiles) tdn = tv.tiles[tile0 + t + NG * G];
+	int e[kMaxSlots];
+	R vinv;
+	cell_inputs(td, e, vinv);
 	for (int i = g;; i += NG, t += NG * G) {
 		const int slot = i % NS;
 		const uint32_t use = (uint32_t)(i / NS);
 		const bool has_next = t + NG * G < n_tiles;
-		const TileDesc td = tv.tiles[tile0 + t];
+		TileDesc tdnn = tdn;
+		if (t + 2 * NG * G < n_tiles) tdnn = tv.tiles[tile0 + t + 2 * NG * G];
 		unsigned char* Qs = sm + pg.off_slot + (size_t)slot * pg.slot_bytes;
 		const unsigned char* Fs = Qs + pg.q_bytes;
 		const R* fg = reinterpret_cast<const R*>(Fs);                                         // [D+1][fmax]: S, w
@@ -631,14 +644,15 @@ __global__ void __launch_bounds__(kGradThreadsTotal, 1)
 		// one thread per cell (the host launches this kernel for tiles of at most GT cells)
 		const int lc = tid;
 		const bool active = lc < td.nt;
-		const int c = td.c0 + (active ? lc : 0);
-		// what the gather needs from global memory, requested before the wait
-		int e[kMaxSlots];
-		R vinv = R(0);
-#pragma unroll
-		for (int s = 0; s < kMaxSlots; s++) e[s] = (active && s < m.F) ? (int)tv.csr_local[(size_t)s * m.n_cells + c] : 0;
-		if (active) vinv = m.vol_inv[c];
 		mbar_wait(full + slot, use & 1u);
+		if (pg.dbg & 4) {   // timing experiment: the fill pipeline alone
+			named_bar(bar_id, GT);
+			if (tid == 0) mbar_arrive(empty + slot);
+			if (!has_next) break;
+			td = tdn;
+			tdn = tdnn;
+			continue;
+		}
 		R rec[RC::VW];
 		if (active) {
 			RecSide<R, D> own;
@@ -703,6 +717,7 @@ __global__ void __launch_bounds__(kGradThreadsTotal, 1)
 			}
 			if (D == 3) rec[RC::TR] = dudx_trace_neg<R, D>(&dudx[0][0]);
 		}
+		if (has_next) cell_inputs(tdn, e, vinv);   // the next tile's gather lists and volumes travel from here on
 		named_bar(bar_id, GT);   // every thread of the group has read what it needs of the Q region: it becomes the V staging
 		if (active) {
 #pragma unroll
@@ -717,6 +732,8 @@ __global__ void __launch_bounds__(kGradThreadsTotal, 1)
 			mbar_arrive(empty + slot);
 		}
 		if (!has_next) break;
+		td = tdn;
+		tdn = tdnn;
 	}
 	if (tid == 0) bulk_wait0();
 }
