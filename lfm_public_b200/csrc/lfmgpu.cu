@@ -175,6 +175,7 @@ struct lfmgpu_ctx {
 	GradGeom gpipe{};
 	size_t gpipe_smem = 0;
 	CUtensorMap map_q[2], map_v;       // record arrays as 2D tensors [ncs][QW | VW], box = one tile of own cells, swizzled
+	CUtensorMap gmap_q[2], gmap_v;     // the same tensors with a box of one record: the maps of the halo gathers (tile::gather4)
 	int smem_pad_kb = 0;               // extra shared memory requested per stage CTA (occupancy experiments)
 	// introspection
 	uint64_t launches = 0;
@@ -719,7 +720,7 @@ int pipe_setup(lfmgpu_ctx* h) {
 	}
 	const int TC = h->tile_cells;
 	if (TC > 256 || TC % 2 || hmax > kPipeMaxHalo) return 0;
-	hmax = std::max(hmax, 4);
+	hmax = (std::max(hmax, 4) + 3) / 4 * 4;   // halo cells are gathered four at a time
 	const int D = h->D, QW = Rec<3>::QW, VW = D == 3 ? Rec<3>::VW : Rec<2>::VW;
 	const uint32_t QB = (uint32_t)(QW * h->prec), VB = (uint32_t)(VW * h->prec);
 	int dev_smem = 0;
@@ -782,8 +783,10 @@ int pipe_setup(lfmgpu_ctx* h) {
 		        h->pipe_ok ? "on" : "off", h->pipe.n_slots, h->pipe.slot_bytes, h->pipe_smem, h->grad_pipe_ok ? "on" : "off", h->gpipe.n_slots, h->gpipe.slot_bytes, h->gpipe_smem, hmax, g.fmax);
 	if (!h->pipe_ok) return 0;
 	for (int b = 0; b < 2; b++) TRY(make_record_map(&h->map_q[b], h->q[b], h->prec, QW, h->ncs, TC));
+	for (int b = 0; b < 2; b++) TRY(make_record_map(&h->gmap_q[b], h->q[b], h->prec, QW, h->ncs, 1));
 	const void* vis = h->prec == 8 ? (const void*)h->md.vis : (const void*)h->mf.vis;
 	TRY(make_record_map(&h->map_v, (void*)vis, h->prec, VW, h->ncs, TC));
+	TRY(make_record_map(&h->gmap_v, (void*)vis, h->prec, VW, h->ncs, 1));
 	return 0;
 }
 
@@ -793,7 +796,7 @@ template <class R, int D> int grad_pipe(lfmgpu_ctx* h, int t0, int t1) {
 	const int sms = std::max(1, h->n_sms - (h->n_nbr ? h->pipe_spare_sms : 0));
 	const int grid = std::min(t1 - t0, sms);
 	LAUNCH(h, "tile_grad", h->s_main,
-	       (kern<<<grid, kGradThreadsTotal, h->gpipe_smem, h->s_main>>>(h->mesh<R>(), tile_view<R>(h, h->gpipe.smax, h->gpipe.fmax), h->map_q[h->cur], h->gpipe, (const R*)h->q[h->cur], t0, t1 - t0)));
+	       (kern<<<grid, kGradThreadsTotal, h->gpipe_smem, h->s_main>>>(h->mesh<R>(), tile_view<R>(h, h->gpipe.smax, h->gpipe.fmax), h->map_q[h->cur], h->gmap_q[h->cur], h->gpipe, (const R*)h->q[h->cur], t0, t1 - t0)));
 	CHECK_LAUNCH();
 	return 0;
 }
@@ -806,7 +809,7 @@ template <class R, int D, int SCHEME> int stage_pipe(lfmgpu_ctx* h, int t0, int 
 	const int sms = std::max(1, h->n_sms - (h->n_nbr ? h->pipe_spare_sms : 0));
 	const int grid = std::min(t1 - t0, sms);
 	LAUNCH(h, "tile_stage", h->s_main,
-	       (kern<<<grid, kPipeThreads, h->pipe_smem, h->s_main>>>(h->mesh<R>(), tile_view<R>(h, h->pipe.smax, h->pipe.fmax), h->map_q[h->cur], h->map_v, h->pipe, (const R*)h->q[h->cur],
+	       (kern<<<grid, kPipeThreads, h->pipe_smem, h->s_main>>>(h->mesh<R>(), tile_view<R>(h, h->pipe.smax, h->pipe.fmax), h->map_q[h->cur], h->map_v, h->gmap_q[h->cur], h->gmap_v, h->pipe, (const R*)h->q[h->cur],
 	                                                              (R*)h->q[1 - h->cur], t0, t1 - t0, dt, Ak, Bk, first, res)));
 	CHECK_LAUNCH();
 	return 0;

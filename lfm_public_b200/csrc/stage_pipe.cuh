@@ -62,6 +62,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
 	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst_smem), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
 	             : "memory");
 }
+// TMA gather (sm_100 tile::gather4): FOUR rows of the 2D tensor, named by their indices, land in four consecutive row slots
+// of shared memory (swizzled by address like a box); the tensor map's box is one row.  Probed on B200 with
+// scripts/probe/gather4_probe.cu: a box of one row is required (a box of four rows is an illegal instruction), one
+// instruction delivers 4 x row bytes.
+__device__ __forceinline__ void tma_gather4(uint32_t dst_smem, const CUtensorMap* map, const int4& rows, uint64_t* bar) {
+	asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst_smem), "l"(map), "r"(0), "r"(rows.x),
+	             "r"(rows.y), "r"(rows.z), "r"(rows.w), "r"(smem_u32(bar))
+	             : "memory");
+}
 // TMA: contiguous shared memory -> global memory (sizes and addresses multiples of 16 bytes)
 __device__ __forceinline__ void bulk_store(void* dst_global, uint32_t src_smem, uint32_t bytes) {
 	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_global), "r"(src_smem), "r"(bytes) : "memory");
@@ -277,7 +286,8 @@ __device__ __forceinline__ void gather_update_rec(const DevMesh<R>& m, const Til
 
 template <class R, int D, int SCHEME>
 __global__ void __launch_bounds__(kPipeThreads, 1)
-    k_stage_pipe(DevMesh<R> m, TileView<R> tv, const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_v, PipeGeom pg, const R* __restrict__ q, R* __restrict__ qn, int tile0,
+    k_stage_pipe(DevMesh<R> m, TileView<R> tv, const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap gmap_q,
+                 const __grid_constant__ CUtensorMap gmap_v, PipeGeom pg, const R* __restrict__ q, R* __restrict__ qn, int tile0,
                  int n_tiles, R dt, R Ak, R Bk, int first, int res) {
 	using RC = Rec<D>;
 	constexpr int NQ = D + 2, QB = RC::QW * (int)sizeof(R), VB = RC::VW * (int)sizeof(R), CQ = QB / 16, CV = VB / 16;
@@ -291,8 +301,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 
 	if (threadIdx.x == 0) {
 		for (int s = 0; s < NS; s++) {
-			mbar_init(full + s, 1 + 32);   // the expect_tx arrival + one cp.async arrival per lane of the tile's producer warp
-			mbar_init(empty + s, 1);       // one elected consumer thread
+			mbar_init(full + s, 1);    // the expect_tx arrival of the tile's producer warp; everything else is counted in bytes
+			mbar_init(empty + s, 1);   // one elected consumer thread
 		}
 		for (int k = 0; k < 2 * kProducerWarps; k++) mbar_init(reinterpret_cast<uint64_t*>(sm + pg.off_meta) + k, 1);   // the producers' id rings
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -338,21 +348,25 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 			mbar_wait(idbar + (j & 1), (uint32_t)(j >> 1) & 1u);      // this tile's halo ids are in the ring
 			mbar_wait(empty + slot, (use & 1u) ^ 1u);                  // the consumers have released the slot (passes at once on its first use)
 			const uint32_t q0 = smem_u32(sm + pg.off_slot + (size_t)slot * pg.slot_bytes);
+			// the halo: groups of four cells per TMA gather (the plan pads every halo list to a multiple of four with cell 0)
+			const int ngrp = (pg.dbg & 1) ? 0 : (cur.nh + 3) >> 2;
 			if (lane == 0) {
-				if (pg.dbg & 2) {
-					mbar_arrive(full + slot);
-				} else {
-					mbar_arrive_expect_tx(full + slot, (uint32_t)pg.box_cells * (QB + VB));
+				const uint32_t own = (pg.dbg & 2) ? 0u : (uint32_t)pg.box_cells * (QB + VB);
+				mbar_arrive_expect_tx(full + slot, own + (uint32_t)ngrp * 4u * (QB + VB));
+				if (own) {
 					tma_load_2d(q0, &map_q, 0, cur.c0, full + slot);
 					tma_load_2d(q0 + pg.q_bytes, &map_v, 0, cur.c0, full + slot);
 				}
 			}
-			if (!(pg.dbg & 1)) {
+			__syncwarp();   // the expect_tx is registered before any lane's copy can complete
+			{
 				const int* ids = idring + (j & 1) * hpitch;
-				copy_halo_records<QB, 32>(q0, qsrc, ids, cur.nh, pg.box_cells, lane);
-				copy_halo_records<VB, 32>(q0 + pg.q_bytes, vsrc, ids, cur.nh, pg.box_cells, lane);
+				for (int gq = lane; gq < ngrp; gq += 32) {
+					const int4 rows = *reinterpret_cast<const int4*>(ids + 4 * gq);
+					tma_gather4(q0 + (uint32_t)(pg.box_cells + 4 * gq) * QB, &gmap_q, rows, full + slot);
+					tma_gather4(q0 + pg.q_bytes + (uint32_t)(pg.box_cells + 4 * gq) * VB, &gmap_v, rows, full + slot);
+				}
 			}
-			cp_async_mbar_arrive_noinc(full + slot);
 			// L2 prefetch of the tile PD fills ahead: its own-cell records (two contiguous pieces) and its slice of each face table
 			if (PD > 0 && lane < 16 && i + PD < my_tiles) {
 				const TileMeta pm = meta_of(my_desc + (size_t)(i + PD) * G);
@@ -521,7 +535,8 @@ __device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, ui
 
 template <class R, int D>
 __global__ void __launch_bounds__(kGradThreadsTotal, 1)
-    k_grad_pipe(DevMesh<R> m, TileView<R> tv, const __grid_constant__ CUtensorMap map_q, GradGeom pg, const R* __restrict__ q, int tile0, int n_tiles) {
+    k_grad_pipe(DevMesh<R> m, TileView<R> tv, const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap gmap_q, GradGeom pg, const R* __restrict__ q, int tile0,
+                int n_tiles) {
 	using RC = Rec<D>;
 	constexpr int QB = RC::QW * (int)sizeof(R), VB = RC::VW * (int)sizeof(R), CQ = QB / 16, CVC = VB / 16;
 	constexpr int GT = kGradGroupThreads, NG = kGradGroups;
@@ -535,7 +550,7 @@ __global__ void __launch_bounds__(kGradThreadsTotal, 1)
 
 	if (threadIdx.x == 0) {
 		for (int s = 0; s < NS; s++) {
-			mbar_init(full + s, 1 + 32);
+			mbar_init(full + s, 1);
 			mbar_init(empty + s, 1);
 		}
 		for (int k = 0; k < 2 * kProducerWarps; k++) mbar_init(reinterpret_cast<uint64_t*>(sm + pg.off_meta) + k, 1);   // the producers' id rings
@@ -579,8 +594,9 @@ __global__ void __launch_bounds__(kGradThreadsTotal, 1)
 			// the tile's slice of the face tables starts on a 16-byte boundary (the plan pads f_off to a multiple of 4) and is
 			// copied in whole 16-byte units (the tables are padded behind the last tile)
 			const uint32_t nf4 = (uint32_t)(cur.nf + 3) & ~3u;
+			const int ngrp = (pg.dbg & 1) ? 0 : (cur.nh + 3) >> 2;
 			if (lane == 0) {
-				mbar_arrive_expect_tx(full + slot, ((pg.dbg & 2) ? 0u : (uint32_t)pg.box_cells * QB) + nf4 * (uint32_t)((D + 1) * sizeof(R) + 4));
+				mbar_arrive_expect_tx(full + slot, ((pg.dbg & 2) ? 0u : (uint32_t)pg.box_cells * QB) + nf4 * (uint32_t)((D + 1) * sizeof(R) + 4) + (uint32_t)ngrp * 4u * QB);
 				if (!(pg.dbg & 2)) tma_load_2d(q0, &map_q, 0, cur.c0, full + slot);
 			}
 			__syncwarp();   // the expect_tx precedes the bulk copies of the other lanes
@@ -589,8 +605,10 @@ __global__ void __launch_bounds__(kGradThreadsTotal, 1)
 				if (lane == 1 + D) bulk_load(fs + (uint32_t)D * frow, tv.fw + cur.f_off, nf4 * (uint32_t)sizeof(R), full + slot);
 				if (lane == 2 + D) bulk_load(fs + (uint32_t)(D + 1) * frow, tv.f_idx + cur.f_off, nf4 * 4u, full + slot);
 			}
-			if (!(pg.dbg & 1)) copy_halo_records<QB, 32>(q0, qsrc, idring + (j & 1) * hpitch, cur.nh, pg.box_cells, lane);
-			cp_async_mbar_arrive_noinc(full + slot);
+			{
+				const int* ids = idring + (j & 1) * hpitch;
+				for (int gq = lane; gq < ngrp; gq += 32) tma_gather4(q0 + (uint32_t)(pg.box_cells + 4 * gq) * QB, &gmap_q, *reinterpret_cast<const int4*>(ids + 4 * gq), full + slot);
+			}
 			if (PD > 0 && lane >= 8 && lane < 16 && i + PD < my_tiles) {
 				const TileMeta pm = meta_of(my_desc + (size_t)(i + PD) * G);
 				const int ac0 = pm.c0, af = pm.f_off;
