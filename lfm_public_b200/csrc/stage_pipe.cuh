@@ -226,63 +226,75 @@ constexpr int kPipeMaxHalo = 256;                           // largest halo the 
 constexpr int kPipeProducerRegs = 32, kPipeConsumerRegs = 112;
 static_assert(kPipeProducerThreads * kPipeProducerRegs + 2 * kPipeGroupThreads * kPipeConsumerRegs <= kPipeThreads * 96, "setmaxnreg.inc would wait for registers the CTA does not own");
 
-// Phase C for components [I0, I1) of tile cell lc on the record layout (gather_update of tile_kernels.cuh): the cell's
-// conservatives are read from, and the new ones written back to, its Q record in the ring slot.
-template <class R, int D, int I0, int I1>
-__device__ __forceinline__ void gather_update_rec(const DevMesh<R>& m, const TileView<R>& tv, const TileDesc& td, unsigned char* Qs, const R* fl, int fmax, int lc, bool active, int bar_id, R dt, R Ak,
-                                                  R Bk, int first, int res) {
-	constexpr int NQ = D + 2, QB = Rec<D>::QW * (int)sizeof(R), EPC = Chunk16<R>::N;
-	const int c = td.c0 + (active ? lc : 0);
+// Phase C for components [I0, I1) of tile cell lc on the record layout (gather_update of tile_kernels.cuh): dq = A_k dq +
+// sum_faces(+-dt rhs / V) + sponge, q_new = q + B_k dq (prepare_for_RKstep's scaling, the scatter of cfd_v0.cpp:2792-2804 as
+// an ordered gather, sponge 2810-2814, update 2819-2822).  The cell's conservatives are read from its Q record in the ring
+// slot; the new ones are returned in qnew[I0 .. I1).  `x -= y` is evaluated as `x += (-y)`: bit-identical, branch-free.
+// gather_inputs issues the global loads; the caller puts the group barrier that closes phase B between the two (the halves
+// of a warp run different instantiations: a barrier inside them would be reached divergently), so the loads travel during
+// the wait.
+// NC components starting at the run-time component cb (both lanes of a cell run the same code; only addresses depend on cb)
+template <class R, int D, int NC> struct CellIn {   // what phase C reads from global memory for one cell
 	int e[kMaxSlots];
-	R dq[NQ], vinv = R(0), sg = R(0);
+	R dq[NC], vinv, sg;
+};
+template <class R, int D, int NC> __device__ __forceinline__ void gather_inputs(const DevMesh<R>& m, const TileView<R>& tv, int c, int cb, bool active, int first, CellIn<R, D, NC>& in) {
 #pragma unroll
-	for (int s = 0; s < kMaxSlots; s++) e[s] = 0;
+	for (int s = 0; s < kMaxSlots; s++) in.e[s] = 0;
 #pragma unroll
-	for (int i = 0; i < NQ; i++) dq[i] = R(0);
+	for (int i = 0; i < NC; i++) in.dq[i] = R(0);
+	in.vinv = in.sg = R(0);
 	if (active) {
 #pragma unroll
 		for (int s = 0; s < kMaxSlots; s++)
-			if (s < m.F) e[s] = (int)tv.csr_local[(size_t)s * m.n_cells + c];
+			if (s < m.F) in.e[s] = (int)tv.csr_local[(size_t)s * m.n_cells + c];
 		if (!first) {
 #pragma unroll
-			for (int i = I0; i < I1; i++) dq[i] = m.dq[(size_t)i * m.n_cells + c];
+			for (int i = 0; i < NC; i++) in.dq[i] = m.dq[(size_t)(cb + i) * m.n_cells + c];
 		}
-		vinv = m.vol_inv[c];
-		sg = m.sigma[c];
+		in.vinv = m.vol_inv[c];
+		in.sg = m.sigma[c];
 	}
-	if (bar_id >= 0) named_bar(bar_id, kPipeGroupThreads);   // every face flux of the tile is in fl (the loads above travel meanwhile)
-	if (!active) return;
-	R RES[NQ];
+}
+template <class R, int D, int NC>
+__device__ __forceinline__ void gather_update_rec(const DevMesh<R>& m, CellIn<R, D, NC>& in, int c, int cb, const unsigned char* Qs, const R* fl, int fmax, int lc, R dt, R Ak, R Bk, int res, R* qnew) {
+	constexpr int NQ = D + 2, QB = Rec<D>::QW * (int)sizeof(R);
+	R RES[NC];
 #pragma unroll
-	for (int i = I0; i < I1; i++) {
-		dq[i] *= Ak;
+	for (int i = 0; i < NC; i++) {
+		in.dq[i] *= Ak;
 		RES[i] = R(0);
 	}
+	const R* flc = fl + (size_t)cb * fmax;
 #pragma unroll
 	for (int s = 0; s < kMaxSlots; s++) {
-		if (e[s] == 0) break;
-		const bool own = e[s] > 0;
-		const int lfc = (own ? e[s] : -e[s]) - 1;
+		if (in.e[s] == 0) break;
+		const bool own = in.e[s] > 0;
+		const int lfc = (own ? in.e[s] : -in.e[s]) - 1;
 #pragma unroll
-		for (int i = I0; i < I1; i++) {
-			const R v = fl[i * fmax + lfc];
+		for (int i = 0; i < NC; i++) {
+			const R v = flc[i * fmax + lfc];
 			const R rr = own ? v : -v;
 			if (res) RES[i] += rr;
-			dq[i] += dt * rr * vinv;
+			in.dq[i] += dt * rr * in.vinv;
 		}
 	}
 	const uint32_t p = swz((uint32_t)lc * QB, swz_mask(QB));
 #pragma unroll
-	for (int i = I0; i < I1; i++) {
-		R* slot_q = reinterpret_cast<R*>(Qs + (p ^ (uint32_t)((i / EPC) << 4))) + (i % EPC);
-		const R cqi = *slot_q;
-		const R target = i == 0 ? m.k.rhoInf : (i == NQ - 1 ? m.k.rhoEInf : m.k.rhoUInf[i > 0 && i < NQ - 1 ? i - 1 : 0]);
-		dq[i] += dt * sg * (target - cqi);
-		m.dq[(size_t)i * m.n_cells + c] = dq[i];
-		*slot_q = cqi + Bk * dq[i];      // only this cell's own threads touch its record after phase B
-		if (res) m.RES[(size_t)i * m.n_cells + c] = RES[i];
+	for (int i = 0; i < NC; i++) {
+		const int k = cb + i;   // component
+		const R cqi = *reinterpret_cast<const R*>(Qs + (p ^ (uint32_t)(((k * (int)sizeof(R)) >> 4) << 4)) + ((k * (int)sizeof(R)) & 15));
+		const R target = k == 0 ? m.k.rhoInf : (k == NQ - 1 ? m.k.rhoEInf : m.k.rhoUInf[(k > 0 && k < NQ - 1) ? k - 1 : 0]);
+		in.dq[i] += dt * in.sg * (target - cqi);
+		m.dq[(size_t)k * m.n_cells + c] = in.dq[i];
+		qnew[i] = cqi + Bk * in.dq[i];
+		if (res) m.RES[(size_t)k * m.n_cells + c] = RES[i];
 	}
 }
+
+// exchange of a value between the two lanes of a cell (lanes l and l ^ 16)
+__device__ __forceinline__ double pair_swap(double v) { return __shfl_xor_sync(0xffffffffu, v, 16); }
+__device__ __forceinline__ float pair_swap(float v) { return __shfl_xor_sync(0xffffffffu, v, 16); }
 
 template <class R, int D, int SCHEME>
 __global__ void __launch_bounds__(kPipeThreads, 1)
@@ -401,19 +413,27 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 	const int fmax = pg.fmax;
 	int t = blockIdx.x + g * G;
 	if (t >= n_tiles) return;
-	TileDesc td = tv.tiles[tile0 + t];
+	// of a tile descriptor the consumers need four values
+	struct Tile {
+		int c0, nt, f_off, nf;
+	};
+	auto tile_of = [&](int tile) {
+		const TileMeta mt = meta_of(tv.tiles + tile0 + tile);
+		return Tile{mt.c0, tv.tiles[tile0 + tile].nt, mt.f_off, mt.nf};
+	};
+	Tile td = tile_of(t);
 	FaceIn<R, D> cur;
-	if (tid < td.nfo + td.ninc) fetch_face<R, D, SCHEME>(tv, (size_t)td.f_off + tid, cur);
+	if (tid < td.nf) fetch_face<R, D, SCHEME>(tv, (size_t)td.f_off + tid, cur);
 	for (int i = g;; i += 2, t += 2 * G) {
 		const int slot = i % NS;
 		const uint32_t use = (uint32_t)(i / NS);
 		const bool has_next = t + 2 * G < n_tiles;
-		TileDesc tdn = td;
-		if (has_next) tdn = tv.tiles[tile0 + t + 2 * G];   // in flight during this tile
+		Tile tdn = td;
+		if (has_next) tdn = tile_of(t + 2 * G);   // in flight during this tile
 		unsigned char* Qs = sm + pg.off_slot + (size_t)slot * pg.slot_bytes;
 		const unsigned char* Vs = Qs + pg.q_bytes;
 		unsigned char* outb = Qs + pg.q_bytes;   // the V region is dead once phase B is over: it stages the finished Q records (un-swizzled)
-		const int nf = td.nfo + td.ninc;
+		const int nf = td.nf;
 		// The two groups take alternate tiles, so this group can reach a slot while its previous user (a tile of the OTHER group)
 		// still waits for its data: one phase behind, which the parity of `full` alone cannot tell from "already filled again".
 		// The slot's previous fill was issued before this group's last tile was, so the slot is never further behind than that:
@@ -455,44 +475,59 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 			if (lf + GT < nf) cur = nxt;
 		}
 
-		// ---- C: ordered gather, sponge, RK update (components split between the halves of the group when the tile leaves
-		// half of it idle; the ordered sums are per component, so the split changes no result) -------------------
-		const bool split = 2 * td.nt <= GT;
-		const int rounds = split ? 1 : (td.nt + GT - 1) / GT;
-		for (int r = 0; r < rounds; r++) {
-			constexpr int H = (NQ + 1) / 2;
-			const int part = split ? (tid >= GT / 2 ? 1 : 0) : 2;
-			const int lc = split ? tid - (part ? GT / 2 : 0) : tid + r * GT;
-			const bool active = lc < td.nt;
-			// the barrier that closes phase B sits inside (a named barrier: defined for any call site); later rounds need none
-			const int bid = r == 0 ? bar_id : -1;
-			if (part == 0)
-				gather_update_rec<R, D, 0, H>(m, tv, td, Qs, fl, fmax, lc, active, bid, dt, Ak, Bk, first, res);
-			else if (part == 1)
-				gather_update_rec<R, D, H, NQ>(m, tv, td, Qs, fl, fmax, lc, active, bid, dt, Ak, Bk, first, res);
-			else
-				gather_update_rec<R, D, 0, NQ>(m, tv, td, Qs, fl, fmax, lc, active, bid, dt, Ak, Bk, first, res);
-		}
-		// the first face of this group's next tile travels during the epilogue and the wait for its slot
-		if (has_next && tid < tdn.nfo + tdn.ninc) fetch_face<R, D, SCHEME>(tv, (size_t)tdn.f_off + tid, cur);
-		named_bar(bar_id, GT);   // all new conservatives are in the slot
-
-		// ---- derived values of the new state, the finished Q records -> staging (un-swizzled) -> one bulk store ----
-		for (int lc = tid; lc < td.nt; lc += GT) {
-			RecSide<R, D> s;
-			s.load_q(Qs, lc);
-			CellState<R, D> cs;
-			R rec[RC::QW];
+		// ---- C: ordered gather, sponge, RK update, derived values.  A cell belongs to a PAIR of lanes of one warp (l and l ^ 16):
+		// the low lane takes components [0, H), the high lane [NQ - H, NQ) (the ordered sums are per component, so the split
+		// changes no result; with an odd NQ the middle component is formed by both, identically) -- the SAME code for both, only
+		// addresses depend on the half, so the warp does not diverge.  The lanes swap their new conservatives through the warp
+		// and each writes its half of the finished record to the staging area (un-swizzled): low lane the chunks that hold
+		// conservatives only, high lane -- which also forms the derived values -- the rest.  No barrier between the update and
+		// the staging: the pair is one warp.
+		{
+			constexpr int H = (NQ + 1) / 2, EPC = Chunk16<R>::N;
+			const int wl = tid & 31, part = wl >> 4, cb = part * (NQ - H);
+			for (int base = 0; base < td.nt; base += GT / 2) {
+				const int lc = base + (tid >> 5) * 16 + (wl & 15);
+				const bool active = lc < td.nt;
+				const int c = td.c0 + (active ? lc : 0);
+				CellIn<R, D, H> in;
+				gather_inputs<R, D, H>(m, tv, c, cb, active, first, in);
+				if (base == 0) named_bar(bar_id, GT);   // every face flux of the tile is in fl (the loads above travel meanwhile)
+				R mine[H];
 #pragma unroll
-			for (int k = 0; k < NQ; k++) rec[k] = cs.q[k] = s.q(k);
-			derive_state<R, D, SCHEME>(m.k, cs);
-			rec[RC::RHO_INV] = cs.rho_inv;
-			rec[RC::RPSI] = cs.Rpsi;
-			rec[RC::AUX] = cs.aux;
-			if (RC::AUX + 1 < RC::QW) rec[RC::QW - 1] = R(0);
+				for (int k = 0; k < H; k++) mine[k] = R(0);
+				if (active) gather_update_rec<R, D, H>(m, in, c, cb, Qs, fl, fmax, lc, dt, Ak, Bk, res, mine);
+				// the record: component k is mine[k - cb] where this lane formed it, the partner's otherwise
+				R rec[RC::QW];
 #pragma unroll
-			for (int j = 0; j < CQ; j++) *reinterpret_cast<typename Chunk16<R>::T*>(outb + (size_t)lc * QB + j * 16) = Chunk16<R>::pack(rec + j * Chunk16<R>::N);
+				for (int k = 0; k < RC::QW; k++) rec[k] = R(0);
+#pragma unroll
+				for (int k = 0; k < H; k++) {
+					const R other = pair_swap(mine[k]);
+					// low lane: mine -> component k, other -> component NQ - H + k; high lane: the reverse
+					rec[k] = part == 0 ? mine[k] : other;
+					if (NQ - H + k >= H) rec[NQ - H + k] = part == 0 ? other : mine[k];
+				}
+				if (active) {
+					constexpr int C0 = (NQ / EPC);   // chunks [0, C0) hold conservatives only: the low lane's share
+					if (part == 0) {
+#pragma unroll
+						for (int j = 0; j < C0; j++) *reinterpret_cast<typename Chunk16<R>::T*>(outb + (size_t)lc * QB + j * 16) = Chunk16<R>::pack(rec + j * EPC);
+					} else {
+						CellState<R, D> cs;
+#pragma unroll
+						for (int k = 0; k < NQ; k++) cs.q[k] = rec[k];
+						derive_state<R, D, SCHEME>(m.k, cs);
+						rec[RC::RHO_INV] = cs.rho_inv;
+						rec[RC::RPSI] = cs.Rpsi;
+						rec[RC::AUX] = cs.aux;
+#pragma unroll
+						for (int j = C0; j < CQ; j++) *reinterpret_cast<typename Chunk16<R>::T*>(outb + (size_t)lc * QB + j * 16) = Chunk16<R>::pack(rec + j * EPC);
+					}
+				}
+			}
 		}
+		// the first face of this group's next tile travels during the store and the wait for its slot
+		if (has_next && tid < tdn.nf) fetch_face<R, D, SCHEME>(tv, (size_t)tdn.f_off + tid, cur);
 		fence_proxy_async();   // the staging writes above become visible to the TMA engine
 		named_bar(bar_id, GT);
 		if (tid == 0) {
