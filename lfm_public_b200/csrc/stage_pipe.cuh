@@ -146,24 +146,6 @@ template <class R, int D> struct RecSide {
 	__device__ __forceinline__ R tauMC(int, int) const { return R(0); }   // laminar closure only
 };
 
-// Producer side of a halo: copies the B-byte records of the cells ids[0 .. nh) into slots first_slot.. of a swizzled region
-// with 16-byte cp.async.  Consecutive threads take consecutive 16-byte chunks (B/16 threads per record: whole sectors per
-// request); a thread keeps its chunk index for the whole loop and walks the halo list with a fixed cell stride, so that an
-// element costs one id load, one 64-bit multiply-add and the swizzle.
-template <int B, int NTHR> __device__ __forceinline__ void copy_halo_records(uint32_t region_smem, const unsigned char* src, const int* ids, int nh, int first_slot, int tid) {
-	constexpr int C = B / 16, CELLS_PER_PASS = NTHR / C;
-	static_assert(NTHR % C == 0, "the chunk index of a thread must not change between passes");
-	const int ch = tid % C;
-	const unsigned char* s0 = src + ch * 16;
-	const uint32_t d0 = (uint32_t)ch * 16u;
-#pragma unroll 4
-	for (int cell = tid / C; cell < nh; cell += CELLS_PER_PASS) {
-		const size_t x = (size_t)ids[cell];
-		const uint32_t off = (uint32_t)(first_slot + cell) * B + d0;
-		cp_async16(region_smem + swz(off, swz_mask(B)), s0 + x * B);
-	}
-}
-
 // ---- producer warps ---------------------------------------------------------------------------------------------------
 // Each of the four producer warps is a complete producer for the tiles of "its" ring slots (tile i of the CTA uses slot i % NS
 // and belongs to warp (i % NS) % 4, so the uses of one slot are filled in order by one warp -- a second warp could reach the
@@ -268,15 +250,20 @@ __device__ __forceinline__ void gather_update_rec(const DevMesh<R>& m, CellIn<R,
 	const R* flc = fl + (size_t)cb * fmax;
 #pragma unroll
 	for (int s = 0; s < kMaxSlots; s++) {
-		if (in.e[s] == 0) break;
-		const bool own = in.e[s] > 0;
-		const int lfc = (own ? in.e[s] : -in.e[s]) - 1;
+		// (a cell's list is dense: entries behind the first 0 are 0 too.  No early exit, so that the loads of all slots can be
+		// issued together; an empty slot contributes nothing -- not even a +0 that could turn a -0 sum into +0)
+		const bool used = in.e[s] != 0, own = in.e[s] > 0;
+		const int lfc = used ? (own ? in.e[s] : -in.e[s]) - 1 : 0;
+		R v[NC];
 #pragma unroll
-		for (int i = 0; i < NC; i++) {
-			const R v = flc[i * fmax + lfc];
-			const R rr = own ? v : -v;
-			if (res) RES[i] += rr;
-			in.dq[i] += dt * rr * in.vinv;
+		for (int i = 0; i < NC; i++) v[i] = flc[i * fmax + lfc];
+		if (used) {
+#pragma unroll
+			for (int i = 0; i < NC; i++) {
+				const R rr = own ? v[i] : -v[i];
+				if (res) RES[i] += rr;
+				in.dq[i] += dt * rr * in.vinv;
+			}
 		}
 	}
 	const uint32_t p = swz((uint32_t)lc * QB, swz_mask(QB));
@@ -302,7 +289,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
                  const __grid_constant__ CUtensorMap gmap_v, PipeGeom pg, const R* __restrict__ q, R* __restrict__ qn, int tile0,
                  int n_tiles, R dt, R Ak, R Bk, int first, int res) {
 	using RC = Rec<D>;
-	constexpr int NQ = D + 2, QB = RC::QW * (int)sizeof(R), VB = RC::VW * (int)sizeof(R), CQ = QB / 16, CV = VB / 16;
+	constexpr int NQ = D + 2, QB = RC::QW * (int)sizeof(R), VB = RC::VW * (int)sizeof(R), CQ = QB / 16;
 	constexpr int GT = kPipeGroupThreads;
 	extern __shared__ unsigned char smem_dyn[];
 	unsigned char* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -451,8 +438,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 
 		// ---- B: every face of the tile once ----------------------------------------------------------------
 		for (int lf = tid; lf < nf; lf += GT) {
-			FaceIn<R, D> nxt;
-			if (lf + GT < nf) fetch_face<R, D, SCHEME>(tv, (size_t)td.f_off + lf + GT, nxt);
+			// the first face of a tile was fetched a tile ago; the face tables of this tile were prefetched into the L2 by the producers
+			// (a register prefetch of the next round's face measured the same and cost 19 registers and the kernel's only spills)
+			if (lf != tid) fetch_face<R, D, SCHEME>(tv, (size_t)td.f_off + lf, cur);
 			const int lo = (int)(cur.idx & 0xffffu), ln = (int)((cur.idx >> 16) & 0x7fffu);
 			const bool ghost = (cur.idx >> 31) != 0;
 			R dv[D];
@@ -472,7 +460,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 			face_flux<R, D, SCHEME>(m.k, c, n, cur.g, ghost, dv, rhs);
 #pragma unroll
 			for (int k = 0; k < NQ; k++) fl[k * fmax + lf] = rhs[k];
-			if (lf + GT < nf) cur = nxt;
 		}
 
 		// ---- C: ordered gather, sponge, RK update, derived values.  A cell belongs to a PAIR of lanes of one warp (l and l ^ 16):
@@ -573,7 +560,7 @@ __global__ void __launch_bounds__(kGradThreadsTotal, 1)
     k_grad_pipe(DevMesh<R> m, TileView<R> tv, const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap gmap_q, GradGeom pg, const R* __restrict__ q, int tile0,
                 int n_tiles) {
 	using RC = Rec<D>;
-	constexpr int QB = RC::QW * (int)sizeof(R), VB = RC::VW * (int)sizeof(R), CQ = QB / 16, CVC = VB / 16;
+	constexpr int QB = RC::QW * (int)sizeof(R), VB = RC::VW * (int)sizeof(R), CVC = VB / 16;
 	constexpr int GT = kGradGroupThreads, NG = kGradGroups;
 	extern __shared__ unsigned char smem_dyn[];
 	unsigned char* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -723,7 +710,7 @@ __global__ void __launch_bounds__(kGradThreadsTotal, 1)
 			}
 #pragma unroll
 			for (int s = 0; s < kMaxSlots; s++) {
-				if (e[s] == 0) break;
+				if (e[s] != 0) {   // (dense list; no early exit: the loads of all six faces can travel together)
 				const bool is_own = e[s] > 0;
 				const int lf = (is_own ? e[s] : -e[s]) - 1;
 				const uint32_t idx = fi[lf];
@@ -750,6 +737,7 @@ __global__ void __launch_bounds__(kGradThreadsTotal, 1)
 #pragma unroll
 					for (int b = 0; b < D; b++) dudx[a][b] += face_U[a] * sov[b];
 					dTdx[a] += face_T * sov[a];
+				}
 				}
 			}
 			// the tau / sigmaU block of calc_VIS (U = rhoU / rho: a true division, cfd_v0.cpp:1806-1857)
