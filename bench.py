@@ -319,6 +319,29 @@ def quick_measure(n, precision, scheme, tile, brick_order, steps, device=0):
         case.close()
 
 
+def bind_to_gpu_cores(local_rank, world):
+    """Pins this rank to its own share of the cores NVML lists as close to its GPU (pinned host buffers are allocated after
+    this, so they land on that NUMA node): eight ranks sharing every core of the host was one suspect of the round-1 e2e
+    collapse at N = 8.  Returns what was done (goes into the e2e record)."""
+    if world == 1:
+        return "unchanged (one rank: the CPU baseline that follows uses every core)"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hdl = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(hdl, (os.cpu_count() + 63) // 64)
+        cores = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return "nvml affinity empty: unchanged"
+        per = max(1, len(allowed) // max(1, world))
+        mine = allowed[(local_rank * per) % len(allowed):][:per] or allowed
+        os.sched_setaffinity(0, mine)
+        return f"cores {mine[0]}-{mine[-1]} of the {len(allowed)} NVML lists for GPU {local_rank}"
+    except Exception as e:
+        return f"unchanged ({type(e).__name__})"
+
+
 def nccl_parity_check(args, dist, rank, world, local_rank, n=24, steps=3):
     """Outside the timed region, N > 1 only: a small block case (n^3 cells per rank, the bench workload's layout and
     dictionaries) advanced `steps` time steps (a) on this rank's GPU with the halo exchange over NCCL and (b) by the CPU
@@ -377,6 +400,7 @@ def run_gpu_arm(args):
     if gpu_api.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
     blocks = BLOCKS[world]
+    affinity = bind_to_gpu_cores(local_rank, world)
     parity_nccl = None
     if world > 1 and not args.no_parity:
         ok, digest = nccl_parity_check(args, dist, rank, world, local_rank)
@@ -473,6 +497,19 @@ def run_gpu_arm(args):
     g.event_record(3)
     barrier()
     ms_e2e = max_over_ranks(g.event_elapsed_ms(2, 3)) / Ke
+    # the same loop without the time step: what the host <-> device path alone allows at this rank count (the ceiling of e2e)
+    g.pipe_in_start(pin_in[0].ptr, pin_in[0].nbytes)
+    for it in range(1 + Ke):
+        if it == 1:
+            barrier()
+            g.event_record(4)
+        g.pipe_in_commit()
+        g.pipe_in_start(pin_in[(it + 1) % 2].ptr, pin_in[(it + 1) % 2].nbytes)
+        g.pipe_out_start()
+        g.pipe_out_fetch(pin_out[it % 2].ptr, pin_out[it % 2].nbytes)
+    g.event_record(5)
+    barrier()
+    ms_copy = max_over_ranks(g.event_elapsed_ms(4, 5)) / Ke
     e2e_ok = bool(np.isfinite(pin_out[0].array).all() and np.isfinite(pin_out[1].array).all() and pin_out[Ke % 2].array.std() > 0)
     for p_ in pin_in + pin_out:
         p_.free()
@@ -503,15 +540,21 @@ def run_gpu_arm(args):
         ms, nl = ktimes[dom]
         per_launch_cells = n_cells * (max(1, min(K, 3)) * 5) / nl      # cells one launch covers
         achieved = alg[dom] * per_launch_cells / (ms / nl * 1e-3) / 1e9
-        traffic = None
-        try:                                                          # measured DRAM bytes per launch of the committed ncu capture
+        traffic, traffic_note = None, None
+        try:
+            # measured DRAM bytes per launch from the committed ncu capture -- valid only for the very binary that was profiled:
+            # the capture is stamped with the SHA-256 of liblfmgpu.so (scripts/ncu_traffic.py) and dropped when the library differs
+            import hashlib
             tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[dom]["f64" if s == 8 else "f32"]
-            if tr["n"] == args.n:
+            so = hashlib.sha256(open(os.path.join(ROOT, "lfm_public_b200", "liblfmgpu.so"), "rb").read()).hexdigest()
+            if tr["n"] == args.n and tr.get("numbering") == args.numbering and tr.get("lib_sha256") == so:
                 traffic = tr["bytes_per_launch"]
+            else:
+                traffic_note = "the committed ncu capture is of another binary or workload: not reported"
         except Exception:
             pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_cell": alg[dom],
+                    "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src, "alg_bytes_per_cell": alg[dom],
                     "avg_launch_ms": ms / nl, "kernel_ms_per_step": {k: v[0] / max(1, min(K, 3)) for k, v in ktimes.items()},
                     "stage_frac": (Gb + Fb) * n_cells * 5 / (ms_step * 1e-3) / 1e9 / peak}
 
@@ -555,6 +598,8 @@ def run_gpu_arm(args):
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": int(NQ * n_cells * s) * world,
                 "d2h_bytes_per_step": int(NQ * n_cells * s) * world, "ms_per_step": ms_e2e, "finite": e2e_ok,
+                "copy_only_ms_per_step": ms_copy, "copy_only_ceiling": total_cells * 5 / (ms_copy * 1e-3),
+                "frac_of_copy_ceiling": ms_copy / ms_e2e, "cpu_affinity": affinity,
                 "mode": "pipelined batches: H2D of batch k+1 and D2H of batch k-1 overlap the step of batch k (pinned host buffers)"},
         "gpu_launches": int(launches), "clocks": clk, "finite": finite, "setup_s": t_setup,
         "tiles": tile_info, "use_tiles": args.use_tiles, "extra": extras,

@@ -164,9 +164,9 @@ struct lfmgpu_ctx {
 	// persistent TMA-fed stage kernel (stage_pipe.cuh)
 	bool pipe_ok = false;              // tensor maps and ring geometry are in place
 	int pipe_enable = 3;               // LFMGPU_PIPE: bit 0 stage kernel, bit 1 gradient kernel; 0: the tile kernels of round 1 serve everything
-	int pipe_slots_cap = 4;            // LFMGPU_PIPE_SLOTS
+	int pipe_slots_cap = 6;            // LFMGPU_PIPE_SLOTS
 	int pipe_pf_dist = 3;              // L2 prefetch distance of the persistent kernels in tiles per CTA (LFMGPU_PIPE_PF, 0: off)
-	int pipe_grad_slots_cap = 9;       // LFMGPU_PIPE_GSLOTS
+	int pipe_grad_slots_cap = 12;      // LFMGPU_PIPE_GSLOTS
 	int pipe_spare_sms = 8;            // SMs left to the halo stream's kernels on a rank with neighbours (LFMGPU_PIPE_SPARE)
 	int n_sms = 0;
 	PipeGeom pipe{};
@@ -177,6 +177,16 @@ struct lfmgpu_ctx {
 	CUtensorMap map_q[2], map_v;       // record arrays as 2D tensors [ncs][QW | VW], box = one tile of own cells, swizzled
 	CUtensorMap gmap_q[2], gmap_v;     // the same tensors with a box of one record: the maps of the halo gathers (tile::gather4)
 	int smem_pad_kb = 0;               // extra shared memory requested per stage CTA (occupancy experiments)
+	// CUDA graph of two consecutive time steps of a rank without neighbours (lfmgpu_step): ten RK stages return the double
+	// buffer to its starting parity, so the same executable graph serves every following pair of steps with the same arguments
+	int use_graph = 1;                 // LFMGPU_GRAPH=0: every kernel is launched from the host
+	cudaGraphExec_t graph_exec = nullptr;
+	uint64_t graph_kernels = 0;        // kernel launches inside the graph (added to `launches` at every replay)
+	struct GraphKey {
+		int scheme, want_res, minmod, les, cur, dq_zero_after;
+		double dt;
+		bool operator==(const GraphKey& o) const { return scheme == o.scheme && want_res == o.want_res && minmod == o.minmod && les == o.les && cur == o.cur && dt == o.dt; }
+	} graph_key{};
 	// introspection
 	uint64_t launches = 0;
 	bool timing = false;
@@ -706,6 +716,16 @@ int make_record_map(CUtensorMap* out, void* base, int prec, int width, size_t ro
 
 inline uint32_t round_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
+// dynamic shared memory of the persistent kernels of this rank's precision and dimension, on the handle's device
+template <class R, int D> int pipe_attrs(lfmgpu_ctx* h) {
+	if (h->pipe_ok) {
+		CU(cudaFuncSetAttribute(k_stage_pipe<R, D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->pipe_smem));
+		CU(cudaFuncSetAttribute(k_stage_pipe<R, D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->pipe_smem));
+	}
+	if (h->grad_pipe_ok) CU(cudaFuncSetAttribute(k_grad_pipe<R, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->gpipe_smem));
+	return 0;
+}
+
 // Called once the tile plan exists: decides whether the persistent kernel can serve this rank (every submesh cut with the
 // same tile size <= 256 -- the height of the TMA box -- halos of at most 256 cells, at least two ring slots in shared memory)
 int pipe_setup(lfmgpu_ctx* h) {
@@ -735,10 +755,10 @@ int pipe_setup(lfmgpu_ctx* h) {
 	g.fmax = (fmax + 3) / 4 * 4;
 	g.q_bytes = round_up((uint32_t)g.smax * QB, 1024);
 	g.slot_bytes = g.q_bytes + round_up((uint32_t)g.smax * VB, 1024);
-	for (int ns = std::min(4, h->pipe_slots_cap); ns >= 2; ns--) {
+	for (int ns = std::min(6, h->pipe_slots_cap); ns >= 2; ns--) {
 		g.n_slots = ns;
 		g.off_bar = 0;
-		g.off_meta = 128;   // slot barriers (16 bytes per slot) in front, then the producers' id-ring barriers and the id rings
+		g.off_meta = 256;   // slot barriers (16 bytes per slot, at most 16 slots) in front, then the producers' id-ring barriers and the id rings
 		g.off_ids = g.off_meta + 2 * kProducerWarps * 8;
 		g.off_fl = round_up(g.off_ids + (uint32_t)(2 * kProducerWarps) * ((hmax + 3) / 4 * 4) * 4u, 128);
 		g.off_slot = round_up(g.off_fl + 2u * (uint32_t)h->NQ * g.fmax * (uint32_t)h->prec, 1024);
@@ -762,11 +782,11 @@ int pipe_setup(lfmgpu_ctx* h) {
 		gg.fmax = g.fmax;
 		gg.q_bytes = round_up(std::max((uint32_t)gg.smax * QB, (uint32_t)TC * VB), 128);
 		gg.slot_bytes = round_up(gg.q_bytes + (uint32_t)gg.fmax * (uint32_t)((D + 1) * h->prec + 4), 1024);   // only the Q region needs the swizzle's alignment
-		for (int ns = std::max(kGradGroups, std::min(9, h->pipe_grad_slots_cap)); ns >= kGradGroups; ns--) {
+		for (int ns = std::max(kGradGroups, std::min(12, h->pipe_grad_slots_cap)); ns >= kGradGroups; ns--) {
 			if ((2 * ns) % kGradGroups) continue;   // see stage_pipe.cuh: the depth must keep a slot's use k - 2 inside the waiting group
 			gg.n_slots = ns;
 			gg.off_bar = 0;
-			gg.off_meta = 128;
+			gg.off_meta = 256;   // (a ring of 9 slots needs 144 bytes of slot barriers: 128 was one slot short and let them overlap the id-ring barriers)
 			gg.off_ids = gg.off_meta + 2 * kProducerWarps * 8;
 			gg.off_slot = round_up(gg.off_ids + (uint32_t)(2 * kProducerWarps) * ((hmax + 3) / 4 * 4) * 4u, 1024);
 			const size_t total = (size_t)gg.off_slot + (size_t)ns * gg.slot_bytes + 1024;
@@ -787,12 +807,13 @@ int pipe_setup(lfmgpu_ctx* h) {
 	const void* vis = h->prec == 8 ? (const void*)h->md.vis : (const void*)h->mf.vis;
 	TRY(make_record_map(&h->map_v, (void*)vis, h->prec, VW, h->ncs, TC));
 	TRY(make_record_map(&h->gmap_v, (void*)vis, h->prec, VW, h->ncs, 1));
+	TRY(h->prec == 8 ? (D == 3 ? pipe_attrs<double, 3>(h) : pipe_attrs<double, 2>(h)) : (D == 3 ? pipe_attrs<float, 3>(h) : pipe_attrs<float, 2>(h)));
 	return 0;
 }
 
 template <class R, int D> int grad_pipe(lfmgpu_ctx* h, int t0, int t1) {
 	auto kern = k_grad_pipe<R, D>;
-	CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->gpipe_smem));
+	// (the kernel's shared-memory limit was raised in pipe_setup, not here: a launch may be under stream capture)
 	const int sms = std::max(1, h->n_sms - (h->n_nbr ? h->pipe_spare_sms : 0));
 	const int grid = std::min(t1 - t0, sms);
 	LAUNCH(h, "tile_grad", h->s_main,
@@ -803,7 +824,7 @@ template <class R, int D> int grad_pipe(lfmgpu_ctx* h, int t0, int t1) {
 
 template <class R, int D, int SCHEME> int stage_pipe(lfmgpu_ctx* h, int t0, int t1, R dt, R Ak, R Bk, int first, int res) {
 	auto kern = k_stage_pipe<R, D, SCHEME>;
-	CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->pipe_smem));
+
 	// a rank with neighbours keeps a few SMs free: the halo stream's pack / NCCL / unpack kernels must be able to start while
 	// the interior submesh's persistent CTAs hold every register of the SMs they run on
 	const int sms = std::max(1, h->n_sms - (h->n_nbr ? h->pipe_spare_sms : 0));
@@ -1345,6 +1366,49 @@ int stage_all(lfmgpu_ctx** hs, int n, int scheme, int rk, double dt, int want_re
 	return 0;
 }
 
+int steps_all(lfmgpu_ctx** hs, int n, int scheme, double dt, int n_steps, int first, int want_res);
+
+// lfmgpu_step on a rank without neighbours: pairs of time steps are replayed from a CUDA graph (a small mesh is launch-bound:
+// a 2D case of half a million cells spends 150 us per stage in five launches).  The graph is captured from the very code
+// path that launches eagerly; the host-side bookkeeping that capture advances (buffer parity, flags) is the state after the
+// two steps, and ten stages leave the parity where it was, so replaying needs no bookkeeping at all.
+int steps_graphed(lfmgpu_ctx* h, int scheme, double dt, int n_steps, int want_res) {
+	lfmgpu_ctx* hs[1] = {h};
+	const bool eligible = h->use_graph && h->n_nbr == 0 && !h->timing && h->c.rk_order % 2 == 1 && n_steps >= 4;
+	if (!eligible) return steps_all(hs, 1, scheme, dt, n_steps, 0, want_res);
+	// the first step runs eagerly: one-off work (derived values after an upload, lazy allocations) stays out of the graph
+	TRY(steps_all(hs, 1, scheme, dt, 1, 0, want_res));
+	n_steps--;
+	const lfmgpu_ctx::GraphKey key{scheme, want_res, h->minmod_opt, h->les_opt, h->cur, 0, dt};
+	if (!h->graph_exec || !(h->graph_key == key)) {
+		if (h->graph_exec) {
+			cudaGraphExecDestroy(h->graph_exec);
+			h->graph_exec = nullptr;
+		}
+		const uint64_t l0 = h->launches;
+		cudaGraph_t graph = nullptr;
+		CU(cudaStreamBeginCapture(h->s_main, cudaStreamCaptureModeThreadLocal));
+		const int rc = steps_all(hs, 1, scheme, dt, 2, 0, want_res);
+		const cudaError_t ce = cudaStreamEndCapture(h->s_main, &graph);
+		if (rc || ce != cudaSuccess || !graph) {
+			if (graph) cudaGraphDestroy(graph);
+			return rc ? rc : fail("CUDA graph capture of two time steps failed: %s", cudaGetErrorString(ce));
+		}
+		const cudaError_t ci = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+		cudaGraphDestroy(graph);
+		if (ci != cudaSuccess) return fail("cudaGraphInstantiate: %s", cudaGetErrorString(ci));
+		h->graph_kernels = h->launches - l0;
+		h->launches = l0;   // nothing has run yet: the launches are counted when the graph is
+		h->graph_key = key;
+	}
+	for (; n_steps >= 2; n_steps -= 2) {
+		CU(cudaGraphLaunch(h->graph_exec, h->s_main));
+		h->launches += h->graph_kernels;
+	}
+	if (n_steps) TRY(steps_all(hs, 1, scheme, dt, n_steps, 0, want_res));
+	return 0;
+}
+
 int steps_all(lfmgpu_ctx** hs, int n, int scheme, double dt, int n_steps, int first, int want_res) {
 	if (first) {
 		// pre-loop warm-up (mesh_solver.cpp:409-428)
@@ -1455,6 +1519,7 @@ int lfmgpu_create(const lfmgpu_desc* ds, int device, lfmgpu_t* out) {
 	if (const char* e = getenv("LFMGPU_FIXED_STRIDES")) h->fixed_strides = atoi(e);
 	if (const char* e = getenv("LFMGPU_TILE_SMEM")) h->tile_smem_budget = std::max(16, atoi(e)) * 1024;
 	if (const char* e = getenv("LFMGPU_SMEM_PAD")) h->smem_pad_kb = std::max(0, atoi(e));
+	if (const char* e = getenv("LFMGPU_GRAPH")) h->use_graph = atoi(e);
 	if (const char* e = getenv("LFMGPU_PIPE")) h->pipe_enable = atoi(e);   // bit 0: stage kernel, bit 1: gradient kernel
 	if (const char* e = getenv("LFMGPU_PIPE_SLOTS")) h->pipe_slots_cap = std::max(2, atoi(e));
 	if (const char* e = getenv("LFMGPU_PIPE_SPARE")) h->pipe_spare_sms = std::max(0, atoi(e));
@@ -1607,6 +1672,7 @@ int lfmgpu_destroy(lfmgpu_t h) {
 	cudaSetDevice(h->device);
 	cudaDeviceSynchronize();
 	if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+	if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
 	for (auto& t : h->timed) {
 		cudaEventDestroy(t.a);
 		cudaEventDestroy(t.b);
@@ -1747,8 +1813,7 @@ int lfmgpu_step(lfmgpu_t h, int scheme, double dt, int n_steps, int minmod, int 
 	if (scheme != LFMGPU_SCHEME_M1 && scheme != LFMGPU_SCHEME_M2 && scheme != LFMGPU_SCHEME_M2AUSM) return fail("scheme %d is not served by the GPU path", scheme);
 	if (h->transport == 1 && h->n_ranks > 1) return fail("lfmgpu_step: in-process ranks must be driven together (lfmgpu_step_multi)");
 	if (h->n_nbr && h->transport == 0) return fail("lfmgpu_step: rank has neighbours but no halo transport was initialised");
-	lfmgpu_ctx* hs[1] = {h};
-	return steps_all(hs, 1, scheme, dt, n_steps, 0, want_res);
+	return steps_graphed(h, scheme, dt, n_steps, want_res);
 }
 
 int lfmgpu_step_multi(const lfmgpu_t* hs, int n_ranks, int scheme, double dt, int n_steps, int first, int want_res) {

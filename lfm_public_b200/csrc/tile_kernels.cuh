@@ -173,7 +173,7 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // ---------------------------------------------------------------------------------------------------
 // SMAX / FMAX > 0: compile-time shared-memory strides (row offsets become immediates of the LDS/STS instructions
 // instead of one address computation per access); 0: the strides of the launch (tv.smax / tv.fmax).
-constexpr int kFixedSmax = 320, kFixedFmax = 480;
+constexpr int kFixedSmax = 304, kFixedFmax = 480;   // (304 staged cells: six ring slots of the persistent gradient kernel still fit)
 
 template <class R, int D, int NT, int SMAX = 0, int FMAX = 0, int LES = 0>
 __global__ void __launch_bounds__(NT) k_tile_grad(DevMesh<R> m, TileView<R> tv, const R* __restrict__ q, int tile0) {

@@ -23,15 +23,18 @@ def _run(args, timeout=900):
 
 @pytest.mark.skipif(not common.have_ref(), reason="reference binary not built")
 def test_reference_arm_line():
-    d = _run(["--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-n", "16"])
+    d = _run(["--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-n", "16", "--ref-arm-n", "24"])
     assert d["impl"] == "reference" and BASE_KEYS <= set(d) and d["value"] > 0
+    # the line names the mesh the CPU arm really advanced (24^3 here), not the GPU arm's
+    assert "24^3" in d["config"]["workload"] and d["config"]["total_cells"] == 24 ** 3 and "24^3" in d["cpu_baseline"]["sample"]
+    assert d["cpu_baseline"]["smaller_sample"]["value"] > 0
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["config"]["workload"]
 
 
 @pytest.mark.gpu
 def test_cuda_arm_line():
-    d = _run(["--n", "32", "--steps", "2", "--warmup", "3", "--ref-n", "16", "--ref-steps", "2"])
+    d = _run(["--n", "32", "--steps", "2", "--warmup", "3", "--ref-n", "16", "--ref-steps", "2", "--extras-n", "32"])
     assert BASE_KEYS | {"roofline", "clocks"} <= set(d)
     assert d["n_gpus"] == 1 and d["dtype"] == "f64" and d["value"] > 0 and d["finite"] and d["gpu_launches"] > 0
     r = d["roofline"]
@@ -39,3 +42,6 @@ def test_cuda_arm_line():
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] == e["d2h_bytes_per_step"] == 5 * 32 ** 3 * 8 and e["finite"]
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] > 0
+    x = d["extra"]
+    assert "error" not in x, x
+    assert x["f32"]["value"] > 0 and all(x["numbering"][k]["value"] > 0 for k in ("morton", "bricks", "lex"))

@@ -233,3 +233,32 @@ def test_medium_mesh_all_paths(tmp_path):
             gpu_api.step_multi([g], scheme, 2e-3, 3, first=True)
             assert np.array_equal(g.download(defs.FIELD_Q), ref), f"scheme {scheme} tiles {use_tiles}"
             g.close()
+
+
+@pytest.mark.parametrize("name", ["quad2d_m1", "ogrid3d_m2", "tri2d_m2"])
+def test_graph_replay_bit_exact(name, tmp_path, monkeypatch):
+    """lfmgpu_step on a rank without neighbours replays pairs of time steps from a CUDA graph (LFMGPU_GRAPH, default on): nine
+    steps in one call (one eager + four replayed pairs) must leave exactly the fields of the oracle and of the eager launches,
+    and a second call with another dt must re-capture rather than replay the stale graph."""
+    n_steps = 9
+    fields = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("LFMGPU_GRAPH", mode)
+        o, cases, oracles, gpus = _setup(name, tmp_path / mode, 1)
+        assert len(gpus) == 1
+        g, orc = gpus[0], oracles[0]
+        g.warmup()
+        l0 = g.launch_count
+        g.step(o["solver"], o["deltaT"], n_steps)
+        launches = g.launch_count - l0
+        g.step(o["solver"], 0.5 * o["deltaT"], 4)
+        g.sync()
+        if mode == "1":
+            oracle_lib.run(oracles, o["solver"], o["deltaT"], n_steps, first=True)
+            oracle_lib.run(oracles, o["solver"], 0.5 * o["deltaT"], 4, first=False)
+            for field in (defs.FIELD_Q, defs.FIELD_DQ, defs.FIELD_DUDX, defs.FIELD_QGHOST):
+                assert np.array_equal(g.download(field), orc.download(field)), f"{name}: graph replay differs from the oracle in field {field}"
+        fields[mode] = (g.download(defs.FIELD_Q), launches)
+        _close(gpus)
+    assert np.array_equal(fields["1"][0], fields["0"][0])
+    assert fields["1"][1] == fields["0"][1] > 0          # replayed kernels are counted like launched ones

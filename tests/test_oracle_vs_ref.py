@@ -13,6 +13,7 @@ import pytest
 import common
 import oracle_lib
 from common import CASES, N_STEPS
+from lfm_public_b200 import host_api
 
 needs_ref = pytest.mark.skipif(not common.have_ref(), reason="oracle/_ref/lfm_solve_ref not built (needs /root/reference)")
 
@@ -96,3 +97,28 @@ def test_cfl_matches_reference_printout(tmp_path):
         mine.append(orc.cfl(o["deltaT"]))
     assert len(cfls) == N_STEPS
     assert np.allclose(mine, cfls, rtol=2e-10, atol=0)
+
+
+@pytest.mark.parametrize("name", ["cylinder_vortex", "cylinder_vortex_unstructured"])
+def test_oracle_on_the_reference_example_cases(name, tmp_path):
+    """The CPU restatement against the reference executable on the reference's own example cases (BASELINE.json configs 1, 2):
+    same SHA-256 of rho, U, E, p after three steps as the fixtures scripts/make_example_fixtures.py took from
+    oracle/_ref/lfm_solve_ref.  Runs where the case archive exists (tmp_cases/<name>.txz: not committed, see the script)."""
+    import hashlib
+    import json
+    import tarfile
+    fpath = os.path.join(common.GOLDEN_DIR, "examples.json")
+    arc = os.path.join(common.ROOT, "tmp_cases", name + ".txz")
+    if not os.path.exists(fpath) or not os.path.exists(arc):
+        pytest.skip("example fixture or case archive absent")
+    fx = json.load(open(fpath)).get(name)
+    if fx is None:
+        pytest.skip("no fixture for this case")
+    with tarfile.open(arc, "r:xz") as t:
+        t.extractall(tmp_path)
+    case = host_api.Case.open(str(tmp_path / name)).finish()
+    orc = oracle_lib.Oracle(case)
+    oracle_lib.run([orc], fx["solver"], fx["deltaT"], fx["n_steps"], first=True)
+    mine = common.primitives_from_q(case.to_mesh_order(orc.download(0)), case.desc.c.gamma_m1)
+    for k, want in fx["sha256"].items():
+        assert hashlib.sha256(np.ascontiguousarray(mine[k], dtype=np.float64).tobytes()).hexdigest() == want, (name, k)
