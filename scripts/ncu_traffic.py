@@ -16,12 +16,14 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def traffic(rep):
+def traffic(rep, kernel=None):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     r = list(csv.reader(io.StringIO(raw)))
     h, units = r[0], r[1]
     tot, dur = [], []
     for row in r[2:]:
+        if kernel and kernel not in row[h.index("Kernel Name")]:
+            continue   # one capture may hold both kernels
         b = 0.0
         for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             v, u = float(row[h.index(k)]), units[h.index(k)]
@@ -38,7 +40,7 @@ def main():
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     out = json.load(open(path)) if os.path.exists(path) else {}
     for name, rep in (("tile_stage", stage), ("tile_grad", grad)):
-        b, d, u = traffic(rep)
+        b, d, u = traffic(rep, {"tile_stage": "k_stage_pipe", "tile_grad": "k_grad_pipe"}[name] if stage == grad else None)
         out.setdefault(name, {})[prec] = {"n": n, "numbering": numbering, "bytes_per_launch": b, "ncu_duration": d, "ncu_duration_unit": u,
                                           "lib_sha256": so, "capture": os.path.basename(rep)}
     json.dump(out, open(path, "w"), indent=1, sort_keys=True)
