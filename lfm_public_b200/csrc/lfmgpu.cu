@@ -750,6 +750,9 @@ int pipe_setup(lfmgpu_ctx* h) {
 	g.box_cells = TC;
 	g.pf_dist = h->pipe_pf_dist;
 	g.dbg = getenv("LFMGPU_PIPE_DBG") ? atoi(getenv("LFMGPU_PIPE_DBG")) : 0;
+	g.coop = getenv("LFMGPU_PIPE_COOP") ? atoi(getenv("LFMGPU_PIPE_COOP")) : 1;
+	g.wstore = getenv("LFMGPU_PIPE_WSTORE") ? atoi(getenv("LFMGPU_PIPE_WSTORE")) : 1;
+	g.pf_cell = getenv("LFMGPU_PIPE_PFC") ? atoi(getenv("LFMGPU_PIPE_PFC")) : 1;
 	g.hmax = hmax;
 	g.smax = TC + hmax;
 	g.fmax = (fmax + 3) / 4 * 4;

@@ -77,6 +77,8 @@ __device__ __forceinline__ void bulk_store(void* dst_global, uint32_t src_smem, 
 }
 // TMA: ask the L2 to fetch a contiguous piece of global memory (address and size multiples of 16 bytes); nothing waits for it
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) { asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes)); }
+// one cache line into the L2, per lane (LSU instruction: no uniform-datapath serialisation, nothing waits for it)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -196,6 +198,10 @@ struct PipeGeom {
 	                        // pf_dist fills ahead are requested into the L2, so that a fill costs an L2 round trip, not a DRAM one
 	int dbg;                // timing experiments only (wrong results): bit 0 no halo copies, bit 1 no own-cell loads, bit 2 consumers skip
 	                        // the arithmetic (wait for the slot, release it): LFMGPU_PIPE_DBG
+	int coop;               // 1: the four producer warps share every fill (a quarter of the halo gathers each); 0: one warp per ring slot
+	int wstore;             // 1: every consumer warp stores the records of its own cells and releases the slot for itself (no group barrier
+	                        // behind phase C; the flux rows are guarded by an mbarrier instead); 0: one store per tile behind a group barrier
+	int pf_cell;            // 1: the L2 prefetch also covers what phase C reads per cell (gather lists, accumulators, volumes, sponge)
 };
 
 constexpr int kPipeGroupThreads = 256;                      // one consumer group (two warpgroups)
@@ -238,6 +244,8 @@ template <class R, int D, int NC> __device__ __forceinline__ void gather_inputs(
 		in.sg = m.sigma[c];
 	}
 }
+__device__ __forceinline__ double flip_sign(double v, bool neg) { return __hiloint2double(__double2hiint(v) ^ (neg ? (int)0x80000000u : 0), __double2loint(v)); }
+__device__ __forceinline__ float flip_sign(float v, bool neg) { return __int_as_float(__float_as_int(v) ^ (neg ? (int)0x80000000u : 0)); }
 template <class R, int D, int NC>
 __device__ __forceinline__ void gather_update_rec(const DevMesh<R>& m, CellIn<R, D, NC>& in, int c, int cb, const unsigned char* Qs, const R* fl, int fmax, int lc, R dt, R Ak, R Bk, int res, R* qnew) {
 	constexpr int NQ = D + 2, QB = Rec<D>::QW * (int)sizeof(R);
@@ -260,7 +268,7 @@ __device__ __forceinline__ void gather_update_rec(const DevMesh<R>& m, CellIn<R,
 		if (used) {
 #pragma unroll
 			for (int i = 0; i < NC; i++) {
-				const R rr = own ? v[i] : -v[i];
+				const R rr = flip_sign(v[i], !own);   // own ? v : -v as one integer XOR on the sign bit (a DADD and two selects otherwise)
 				if (res) RES[i] += rr;
 				in.dq[i] += dt * rr * in.vinv;
 			}
@@ -300,9 +308,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 
 	if (threadIdx.x == 0) {
 		for (int s = 0; s < NS; s++) {
-			mbar_init(full + s, 1);    // the expect_tx arrival of the tile's producer warp; everything else is counted in bytes
-			mbar_init(empty + s, 1);   // one elected consumer thread
+			mbar_init(full + s, pg.coop ? kProducerWarps : 1);   // the expect_tx arrival of each producer warp that fills the slot; everything else is counted in bytes
+			mbar_init(empty + s, pg.wstore ? GT / 32 : 1);   // one elected consumer thread (wstore: one lane of every warp of the group)
 		}
+		for (int k = 0; k < 2; k++) mbar_init(full + 2 * pg.n_slots + k, GT / 32);   // flfree[group]: every warp of the group is done with the flux rows
 		for (int k = 0; k < 2 * kProducerWarps; k++) mbar_init(reinterpret_cast<uint64_t*>(sm + pg.off_meta) + k, 1);   // the producers' id rings
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
@@ -324,6 +333,96 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 		const unsigned char* vsrc = reinterpret_cast<const unsigned char*>(m.vis);
 		const int my_tiles = (n_tiles - (int)blockIdx.x + G - 1) / G;
 		const TileDesc* my_desc = tv.tiles + tile0 + blockIdx.x;   // tile i of this CTA: my_desc[i * G]
+		// L2 prefetch of a tile some fills ahead: its own-cell records (two contiguous pieces), its slice of each face table and
+		// (pf_cell) the per-cell inputs of phase C, which no copy stages: gather lists, RK accumulators, volumes, sponge
+		auto prefetch_tile = [&](const TileDesc* d) {
+			const TileMeta pm = meta_of(d);
+			const int ac0 = pm.c0, af = pm.f_off;
+			const uint32_t nf4 = (uint32_t)(pm.nf + 3) & ~3u;
+			if (lane == 0) bulk_prefetch_l2(qsrc + (size_t)ac0 * QB, (uint32_t)pg.box_cells * QB);
+			if (lane == 1) bulk_prefetch_l2(vsrc + (size_t)ac0 * VB, (uint32_t)pg.box_cells * VB);
+			if (nf4) {
+				if (lane == 2) bulk_prefetch_l2(tv.f_idx + af, nf4 * 4u);
+				if (lane >= 3 && lane < 3 + D) bulk_prefetch_l2(tv.fS + (size_t)(lane - 3) * tv.T + af, nf4 * (uint32_t)sizeof(R));
+				if (lane >= 3 + D && lane < 3 + 2 * D) bulk_prefetch_l2(tv.fK + (size_t)(lane - 3 - D) * tv.T + af, nf4 * (uint32_t)sizeof(R));
+				if (lane == 3 + 2 * D) bulk_prefetch_l2(tv.fw + af, nf4 * (uint32_t)sizeof(R));
+				if (lane == 4 + 2 * D) bulk_prefetch_l2(tv.fdm + af, nf4 * (uint32_t)sizeof(R));
+				if (lane == 5 + 2 * D) bulk_prefetch_l2(tv.fdi + af, nf4 * (uint32_t)sizeof(R));
+				if (SCHEME == 0 && lane == 6 + 2 * D) bulk_prefetch_l2(tv.fSmag + af, nf4 * (uint32_t)sizeof(R));
+			}
+			if (pg.pf_cell) {
+				// one 128-byte line per lane and round; the first line of a row may start before the tile, the last one is clamped to
+				// the last cell of the rank (a prefetch names an element that exists)
+				constexpr int CPL = 128 / (int)sizeof(R);                       // cells per line, R rows
+				const int nl = pg.box_cells / CPL + 1, nl16 = pg.box_cells / 64 + 1;   // lines per row (at most one round of the warp: box <= 256 cells)
+				const int cr = min(ac0 + lane * CPL, m.n_cells - 1), c16 = min(ac0 + lane * 64, m.n_cells - 1);
+				if (lane < nl) {
+					prefetch_l2(m.vol_inv + cr);
+					prefetch_l2(m.sigma + cr);
+					if (!first) {
+#pragma unroll
+						for (int k = 0; k < NQ; k++) prefetch_l2(m.dq + (size_t)k * m.n_cells + cr);
+					}
+				}
+				if (lane < nl16) {
+#pragma unroll
+					for (int sl = 0; sl < kMaxSlots; sl++)
+						if (sl < m.F) prefetch_l2(tv.csr_local + (size_t)sl * m.n_cells + c16);
+				}
+			}
+		};
+		const int PD = pg.pf_dist;
+		if (pg.coop) {
+			// Every producer warp walks every tile of the CTA and issues a quarter of its fill.  A TMA gather names its rows in uniform
+			// registers, so a warp issues the gathers of its lanes one after the other (about 15 instructions each): one warp alone
+			// needs longer for the ~90 gathers of a fill than the consumers need for a tile (profiles/r2_final_ncu256_stage_stalls.txt:
+			// the consumers waited for `full` in 13 % of their samples while the pipeline as a whole had throughput to spare).
+			// Each warp announces its own share of the bytes (`full` counts four arrivals), so no copy can complete before its
+			// expect_tx; each keeps its own copy of the halo ids (a few hundred bytes per tile) instead of sharing a ring that would
+			// need one more barrier.  No warp can run a phase ahead of a slot: every fill needs every warp.
+			TileMeta cur = meta_of(my_desc), nxt = cur;
+			if (lane == 0) ids_fetch(cur, idring, idbar, tv.halo_cell);
+			if (1 < my_tiles) nxt = meta_of(my_desc + G);
+			int slot = 0;
+			uint32_t use = 0;
+			for (int i = 0; i < my_tiles; i++) {
+				if (i + 1 < my_tiles && lane == 0) ids_fetch(nxt, idring + ((i + 1) & 1) * hpitch, idbar + ((i + 1) & 1), tv.halo_cell);
+				TileMeta nn = nxt;
+				if (i + 2 < my_tiles) nn = meta_of(my_desc + (size_t)(i + 2) * G);
+				mbar_wait(idbar + (i & 1), (uint32_t)(i >> 1) & 1u);
+				mbar_wait(empty + slot, (use & 1u) ^ 1u);
+				const uint32_t q0 = smem_u32(sm + pg.off_slot + (size_t)slot * pg.slot_bytes);
+				const int ngrp = (pg.dbg & 1) ? 0 : (cur.nh + 3) >> 2;
+				const int mine = ngrp > pwarp ? (ngrp - pwarp + kProducerWarps - 1) / kProducerWarps : 0;   // groups pwarp, pwarp + 4, ...
+				if (lane == 0) {
+					const uint32_t own = (pwarp != 0 || (pg.dbg & 2)) ? 0u : (uint32_t)pg.box_cells * (QB + VB);
+					mbar_arrive_expect_tx(full + slot, own + (uint32_t)mine * 4u * (QB + VB));
+					if (own) {
+						tma_load_2d(q0, &map_q, 0, cur.c0, full + slot);
+						tma_load_2d(q0 + pg.q_bytes, &map_v, 0, cur.c0, full + slot);
+					}
+				}
+				__syncwarp();   // the expect_tx is registered before any lane's copy can complete
+				{
+					const int* ids = idring + (i & 1) * hpitch;
+					for (int k = lane; k < mine; k += 32) {
+						const int gq = pwarp + kProducerWarps * k;
+						const int4 rows = *reinterpret_cast<const int4*>(ids + 4 * gq);
+						tma_gather4(q0 + (uint32_t)(pg.box_cells + 4 * gq) * QB, &gmap_q, rows, full + slot);
+						tma_gather4(q0 + pg.q_bytes + (uint32_t)(pg.box_cells + 4 * gq) * VB, &gmap_v, rows, full + slot);
+					}
+				}
+				if (PD > 0 && (i & (kProducerWarps - 1)) == pwarp && i + PD < my_tiles) prefetch_tile(my_desc + (size_t)(i + PD) * G);
+				__syncwarp();   // every lane has read this tile's ids before lane 0 lets the next bulk copy overwrite the ring
+				cur = nxt;
+				nxt = nn;
+				if (++slot == NS) {
+					slot = 0;
+					use++;
+				}
+			}
+			return;
+		}
 		auto next_mine = [&](int i) {   // the next tile of this CTA (after i) whose slot this warp serves; >= my_tiles: none
 			do i++;
 			while (i < my_tiles && (i % NS) % kProducerWarps != pwarp);
@@ -335,7 +434,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 		TileMeta cur = meta_of(my_desc + (size_t)i * G), nxt = cur;
 		if (lane == 0) ids_fetch(cur, idring, idbar, tv.halo_cell);
 		if (i1 < my_tiles) nxt = meta_of(my_desc + (size_t)i1 * G);
-		const int PD = pg.pf_dist;
 		for (int j = 0; i < my_tiles; i = i1, i1 = i2, i2 = next_mine(i2), j++) {
 			const int slot = i % NS;
 			const uint32_t use = (uint32_t)(i / NS);
@@ -366,23 +464,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 					tma_gather4(q0 + pg.q_bytes + (uint32_t)(pg.box_cells + 4 * gq) * VB, &gmap_v, rows, full + slot);
 				}
 			}
-			// L2 prefetch of the tile PD fills ahead: its own-cell records (two contiguous pieces) and its slice of each face table
-			if (PD > 0 && lane < 16 && i + PD < my_tiles) {
-				const TileMeta pm = meta_of(my_desc + (size_t)(i + PD) * G);
-				const int ac0 = pm.c0, af = pm.f_off;
-				const uint32_t nf4 = (uint32_t)(pm.nf + 3) & ~3u;
-				if (lane == 0) bulk_prefetch_l2(qsrc + (size_t)ac0 * QB, (uint32_t)pg.box_cells * QB);
-				if (lane == 1) bulk_prefetch_l2(vsrc + (size_t)ac0 * VB, (uint32_t)pg.box_cells * VB);
-				if (nf4) {
-					if (lane == 2) bulk_prefetch_l2(tv.f_idx + af, nf4 * 4u);
-					if (lane >= 3 && lane < 3 + D) bulk_prefetch_l2(tv.fS + (size_t)(lane - 3) * tv.T + af, nf4 * (uint32_t)sizeof(R));
-					if (lane >= 3 + D && lane < 3 + 2 * D) bulk_prefetch_l2(tv.fK + (size_t)(lane - 3 - D) * tv.T + af, nf4 * (uint32_t)sizeof(R));
-					if (lane == 3 + 2 * D) bulk_prefetch_l2(tv.fw + af, nf4 * (uint32_t)sizeof(R));
-					if (lane == 4 + 2 * D) bulk_prefetch_l2(tv.fdm + af, nf4 * (uint32_t)sizeof(R));
-					if (lane == 5 + 2 * D) bulk_prefetch_l2(tv.fdi + af, nf4 * (uint32_t)sizeof(R));
-					if (SCHEME == 0 && lane == 6 + 2 * D) bulk_prefetch_l2(tv.fSmag + af, nf4 * (uint32_t)sizeof(R));
-				}
-			}
+			if (PD > 0 && i + PD < my_tiles) prefetch_tile(my_desc + (size_t)(i + PD) * G);
+			__syncwarp();
 			cur = nxt;
 			nxt = nn;
 		}
@@ -411,9 +494,20 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 	Tile td = tile_of(t);
 	FaceIn<R, D> cur;
 	if (tid < td.nf) fetch_face<R, D, SCHEME>(tv, (size_t)td.f_off + tid, cur);
-	for (int i = g;; i += 2, t += 2 * G) {
-		const int slot = i % NS;
-		const uint32_t use = (uint32_t)(i / NS);
+	// this group's tiles are i = g, g + 2, ... of the CTA: slot i % NS, use i / NS, kept as running values (a division per tile
+	// sat in front of the wait for the slot)
+	int slot = g % NS;
+	uint32_t use = (uint32_t)(g / NS);
+	uint64_t* flfree = full + 2 * NS + g;   // (wstore) completes once per tile of this group
+	uint32_t nth = 0;                       // tiles this group has finished
+	auto next_use = [&]() {
+		slot += 2;
+		if (slot >= NS) {
+			slot -= NS;
+			use++;
+		}
+	};
+	for (;; t += 2 * G, next_use()) {
 		const bool has_next = t + 2 * G < n_tiles;
 		Tile tdn = td;
 		if (has_next) tdn = tile_of(t + 2 * G);   // in flight during this tile
@@ -430,7 +524,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 		mbar_wait(full + slot, use & 1u);
 		if (pg.dbg & 4) {   // timing experiment: the fill pipeline alone
 			named_bar(bar_id, GT);
-			if (tid == 0) mbar_arrive(empty + slot);
+			if (pg.wstore ? (tid & 31) == 0 : tid == 0) mbar_arrive(empty + slot);
 			if (!has_next) break;
 			td = tdn;
 			continue;
@@ -458,9 +552,12 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 			n.load_v(Vs, ln);
 			R rhs[NQ];
 			face_flux<R, D, SCHEME>(m.k, c, n, cur.g, ghost, dv, rhs);
+			// (wstore) the flux rows still belong to the previous tile of this group until every warp has gathered from them
+			if (pg.wstore && lf == tid && nth) mbar_wait(flfree, (nth - 1u) & 1u);
 #pragma unroll
 			for (int k = 0; k < NQ; k++) fl[k * fmax + lf] = rhs[k];
 		}
+		// (a warp without a face in this tile writes nothing: it has nothing to wait for; phases are counted by nth)
 
 		// ---- C: ordered gather, sponge, RK update, derived values.  A cell belongs to a PAIR of lanes of one warp (l and l ^ 16):
 		// the low lane takes components [0, H), the high lane [NQ - H, NQ) (the ordered sums are per component, so the split
@@ -516,17 +613,35 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 		// the first face of this group's next tile travels during the store and the wait for its slot
 		if (has_next && tid < tdn.nf) fetch_face<R, D, SCHEME>(tv, (size_t)tdn.f_off + tid, cur);
 		fence_proxy_async();   // the staging writes above become visible to the TMA engine
-		named_bar(bar_id, GT);
-		if (tid == 0) {
-			bulk_store(reinterpret_cast<unsigned char*>(qn) + (size_t)td.c0 * QB, smem_u32(outb), (uint32_t)td.nt * QB);
-			bulk_commit();
-			bulk_wait_read0();           // the store has read its source: the slot may be refilled
-			mbar_arrive(empty + slot);   // every thread of the group is past its last access to the slot
+		if (pg.wstore) {
+			// every warp hands over the records of its own cells (16 per pass, contiguous in the staging area and in HBM) and
+			// releases the slot and the flux rows for itself: nobody waits for the slowest warp of the group here
+			__syncwarp();
+			if ((tid & 31) == 0) {
+				for (int base = (tid >> 5) * 16; base < td.nt; base += GT / 2) {
+					const int n = min(16, td.nt - base);
+					bulk_store(reinterpret_cast<unsigned char*>(qn) + (size_t)(td.c0 + base) * QB, smem_u32(outb) + (uint32_t)base * QB, (uint32_t)n * QB);
+				}
+				bulk_commit();
+				bulk_wait_read0();
+				mbar_arrive(empty + slot);
+				mbar_arrive(flfree);
+			}
+			__syncwarp();
+			nth++;
+		} else {
+			named_bar(bar_id, GT);
+			if (tid == 0) {
+				bulk_store(reinterpret_cast<unsigned char*>(qn) + (size_t)td.c0 * QB, smem_u32(outb), (uint32_t)td.nt * QB);
+				bulk_commit();
+				bulk_wait_read0();           // the store has read its source: the slot may be refilled
+				mbar_arrive(empty + slot);   // every thread of the group is past its last access to the slot
+			}
 		}
 		if (!has_next) break;
 		td = tdn;
 	}
-	if (tid == 0) bulk_wait0();   // the last store has left shared memory and is performed before the CTA exits
+	if (pg.wstore ? (tid & 31) == 0 : tid == 0) bulk_wait0();   // the last store has left shared memory and is performed before the CTA exits
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -59,7 +59,7 @@ def test_plan_of_degenerate_meshes(tmp_path):
 def test_plan_of_the_bench_numbering():
     """Brick-numbered hexahedra (the bench workload, here 128^3 = 2.1 M cells): every invariant holds, the tiles stay inside the
     compile-time strides of the kernels, and the plan is the one the B200 runs reported (tile count, shared memory and
-    incoming/own face ratio printed by tools/tune.py in profiles/r2_plan_bricks_128_gpu.log)."""
+    incoming/own face ratio printed by tools/tune.py in profiles/r2_final_tune128_bricks.log)."""
     import json
 
     import bench
@@ -67,7 +67,7 @@ def test_plan_of_the_bench_numbering():
     case.finish()
     st = gpu_api.plan_check(case)
     assert st["tileable"] and st["max_staged"] <= 320 and st["max_faces"] <= 480
-    log = open(os.path.join(common.ROOT, "profiles", "r2_plan_bricks_128_gpu.log")).read().splitlines()
+    log = open(os.path.join(common.ROOT, "profiles", "r2_final_tune128_bricks.log")).read().splitlines()
     on_gpu = [json.loads(l)["tiles"] for l in log if l.startswith("{")][-1]
     assert st["n_tiles"] == on_gpu["n_tiles"] and st["smem_bytes"] == on_gpu["smem_bytes"] and st["tile_cells"] == on_gpu["tile_cells"]
     assert st["halo_face_ratio"] == on_gpu["halo_face_ratio"]
