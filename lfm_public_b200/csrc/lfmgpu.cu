@@ -167,6 +167,7 @@ struct lfmgpu_ctx {
 	int pipe_slots_cap = 6;            // LFMGPU_PIPE_SLOTS
 	int pipe_pf_dist = 3;              // L2 prefetch distance of the persistent kernels in tiles per CTA (LFMGPU_PIPE_PF, 0: off)
 	int pipe_grad_slots_cap = 12;      // LFMGPU_PIPE_GSLOTS
+	int grad_groups = 4;               // consumer groups of the gradient kernel, 3 or 4 (LFMGPU_PIPE_GGROUPS)
 	int pipe_spare_sms = 8;            // SMs left to the halo stream's kernels on a rank with neighbours (LFMGPU_PIPE_SPARE)
 	int n_sms = 0;
 	PipeGeom pipe{};
@@ -722,7 +723,10 @@ template <class R, int D> int pipe_attrs(lfmgpu_ctx* h) {
 		CU(cudaFuncSetAttribute(k_stage_pipe<R, D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->pipe_smem));
 		CU(cudaFuncSetAttribute(k_stage_pipe<R, D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->pipe_smem));
 	}
-	if (h->grad_pipe_ok) CU(cudaFuncSetAttribute(k_grad_pipe<R, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->gpipe_smem));
+	if (h->grad_pipe_ok) {
+		CU(cudaFuncSetAttribute(k_grad_pipe<R, D, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->gpipe_smem));
+		CU(cudaFuncSetAttribute(k_grad_pipe<R, D, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->gpipe_smem));
+	}
 	return 0;
 }
 
@@ -752,6 +756,7 @@ int pipe_setup(lfmgpu_ctx* h) {
 	g.dbg = getenv("LFMGPU_PIPE_DBG") ? atoi(getenv("LFMGPU_PIPE_DBG")) : 0;
 	g.coop = getenv("LFMGPU_PIPE_COOP") ? atoi(getenv("LFMGPU_PIPE_COOP")) : 1;
 	g.wstore = getenv("LFMGPU_PIPE_WSTORE") ? atoi(getenv("LFMGPU_PIPE_WSTORE")) : 1;
+	g.pf_face = getenv("LFMGPU_PIPE_PFF") ? atoi(getenv("LFMGPU_PIPE_PFF")) : 0;
 	g.pf_cell = getenv("LFMGPU_PIPE_PFC") ? atoi(getenv("LFMGPU_PIPE_PFC")) : 1;
 	g.hmax = hmax;
 	g.smax = TC + hmax;
@@ -780,13 +785,15 @@ int pipe_setup(lfmgpu_ctx* h) {
 		gg.box_cells = TC;
 		gg.pf_dist = getenv("LFMGPU_PIPE_GPF") ? atoi(getenv("LFMGPU_PIPE_GPF")) : 0;   // (the gradient kernel's fills are short: prefetching them measured slower)
 		gg.dbg = g.dbg;
+		gg.wstore = getenv("LFMGPU_PIPE_GWSTORE") ? atoi(getenv("LFMGPU_PIPE_GWSTORE")) : 1;
 		gg.hmax = hmax;
 		gg.smax = TC + hmax;
 		gg.fmax = g.fmax;
 		gg.q_bytes = round_up(std::max((uint32_t)gg.smax * QB, (uint32_t)TC * VB), 128);
 		gg.slot_bytes = round_up(gg.q_bytes + (uint32_t)gg.fmax * (uint32_t)((D + 1) * h->prec + 4), 1024);   // only the Q region needs the swizzle's alignment
-		for (int ns = std::max(kGradGroups, std::min(12, h->pipe_grad_slots_cap)); ns >= kGradGroups; ns--) {
-			if ((2 * ns) % kGradGroups) continue;   // see stage_pipe.cuh: the depth must keep a slot's use k - 2 inside the waiting group
+		const int NG = h->grad_groups;
+		for (int ns = std::max(NG, std::min(12, h->pipe_grad_slots_cap)); ns >= NG; ns--) {
+			if ((2 * ns) % NG) continue;   // see stage_pipe.cuh: the depth must keep a slot's use k - 2 inside the waiting group
 			gg.n_slots = ns;
 			gg.off_bar = 0;
 			gg.off_meta = 256;   // (a ring of 9 slots needs 144 bytes of slot barriers: 128 was one slot short and let them overlap the id-ring barriers)
@@ -815,12 +822,12 @@ int pipe_setup(lfmgpu_ctx* h) {
 }
 
 template <class R, int D> int grad_pipe(lfmgpu_ctx* h, int t0, int t1) {
-	auto kern = k_grad_pipe<R, D>;
+	auto kern = h->grad_groups == 4 ? k_grad_pipe<R, D, 4> : k_grad_pipe<R, D, 3>;
 	// (the kernel's shared-memory limit was raised in pipe_setup, not here: a launch may be under stream capture)
 	const int sms = std::max(1, h->n_sms - (h->n_nbr ? h->pipe_spare_sms : 0));
 	const int grid = std::min(t1 - t0, sms);
 	LAUNCH(h, "tile_grad", h->s_main,
-	       (kern<<<grid, kGradThreadsTotal, h->gpipe_smem, h->s_main>>>(h->mesh<R>(), tile_view<R>(h, h->gpipe.smax, h->gpipe.fmax), h->map_q[h->cur], h->gmap_q[h->cur], h->gpipe, (const R*)h->q[h->cur], t0, t1 - t0)));
+	       (kern<<<grid, grad_threads_total(h->grad_groups), h->gpipe_smem, h->s_main>>>(h->mesh<R>(), tile_view<R>(h, h->gpipe.smax, h->gpipe.fmax), h->map_q[h->cur], h->gmap_q[h->cur], h->gpipe, (const R*)h->q[h->cur], t0, t1 - t0)));
 	CHECK_LAUNCH();
 	return 0;
 }
@@ -1528,6 +1535,7 @@ int lfmgpu_create(const lfmgpu_desc* ds, int device, lfmgpu_t* out) {
 	if (const char* e = getenv("LFMGPU_PIPE_SPARE")) h->pipe_spare_sms = std::max(0, atoi(e));
 	if (const char* e = getenv("LFMGPU_PIPE_PF")) h->pipe_pf_dist = std::max(0, atoi(e));
 	if (const char* e = getenv("LFMGPU_PIPE_GSLOTS")) h->pipe_grad_slots_cap = atoi(e);
+	if (const char* e = getenv("LFMGPU_PIPE_GGROUPS")) h->grad_groups = atoi(e) == 3 ? 3 : 4;
 	if (!rc) rc = tile_plan_build(h, ds);
 	if (!rc) rc = pipe_setup(h);
 	if (!(h->pipe_enable & 2)) h->grad_pipe_ok = false;

@@ -79,6 +79,7 @@ __device__ __forceinline__ void bulk_store(void* dst_global, uint32_t src_smem, 
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) { asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes)); }
 // one cache line into the L2, per lane (LSU instruction: no uniform-datapath serialisation, nothing waits for it)
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -201,6 +202,8 @@ struct PipeGeom {
 	int coop;               // 1: the four producer warps share every fill (a quarter of the halo gathers each); 0: one warp per ring slot
 	int wstore;             // 1: every consumer warp stores the records of its own cells and releases the slot for itself (no group barrier
 	                        // behind phase C; the flux rows are guarded by an mbarrier instead); 0: one store per tile behind a group barrier
+	int pf_face;            // 1: the consumers ask for the face constants of their second round (L2 hits after the producers' prefetch) into
+	                        // the L1 before they start the first: the round then starts on L1 hits instead of an L2 round trip
 	int pf_cell;            // 1: the L2 prefetch also covers what phase C reads per cell (gather lists, accumulators, volumes, sponge)
 };
 
@@ -531,6 +534,19 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 		}
 
 		// ---- B: every face of the tile once ----------------------------------------------------------------
+		if (pg.pf_face && tid + GT < nf) {
+			const size_t j = (size_t)td.f_off + tid + GT;
+			prefetch_l1(tv.f_idx + j);
+#pragma unroll
+			for (int k = 0; k < D; k++) {
+				prefetch_l1(tv.fS + k * tv.T + j);
+				prefetch_l1(tv.fK + k * tv.T + j);
+			}
+			prefetch_l1(tv.fw + j);
+			prefetch_l1(tv.fdm + j);
+			prefetch_l1(tv.fdi + j);
+			if (SCHEME == 0) prefetch_l1(tv.fSmag + j);
+		}
 		for (int lf = tid; lf < nf; lf += GT) {
 			// the first face of a tile was fetched a tile ago; the face tables of this tile were prefetched into the L2 by the producers
 			// (a register prefetch of the next round's face measured the same and cost 19 registers and the kernel's only spills)
@@ -659,24 +675,30 @@ struct GradGeom {
 	uint32_t q_bytes;       // Q region: max(smax * QB, box_cells * VB) rounded up to 1024
 	int pf_dist;            // L2 prefetch distance (see PipeGeom)
 	int dbg;                // timing experiments (see PipeGeom)
+	int wstore;             // per-warp stores and releases (see PipeGeom)
 };
 // Ring depth and group count are tied: a group reaches use k of a slot knowing only that ITS OWN earlier tiles were
 // released; the parity wait for the release of use k - 1 is unambiguous only if use k - 2 (tile i - 2 NS) was one of them,
-// i.e. 2 NS must be a multiple of the number of groups (k_stage_pipe: two groups, any depth; here three groups, depth 3 or 6).
-constexpr int kGradGroupThreads = 128, kGradGroups = 3;
-constexpr int kGradThreadsTotal = kGradGroups * kGradGroupThreads + kPipeProducerThreads;
+// i.e. 2 NS must be a multiple of the number of groups (k_stage_pipe: two groups, any depth; here three groups: depth 3, 6, 9;
+// four groups: an even depth).
+// Group count NG: 3 (512 threads: every thread may use 128 registers, no setmaxnreg) or 4 (640 threads on the stage kernel's register
+// budget: 96 at launch, the producers give back all but 32, the consumers grow to 112 -- a third more warps for a kernel whose
+// consumers wait on their own dependent latencies).
+constexpr int kGradGroupThreads = 128;
+__host__ __device__ constexpr int grad_threads_total(int ng) { return ng * kGradGroupThreads + kPipeProducerThreads; }
 
 __device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-template <class R, int D>
-__global__ void __launch_bounds__(kGradThreadsTotal, 1)
+template <class R, int D, int NG>
+__global__ void __launch_bounds__(grad_threads_total(NG), 1)
     k_grad_pipe(DevMesh<R> m, TileView<R> tv, const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap gmap_q, GradGeom pg, const R* __restrict__ q, int tile0,
                 int n_tiles) {
 	using RC = Rec<D>;
 	constexpr int QB = RC::QW * (int)sizeof(R), VB = RC::VW * (int)sizeof(R), CVC = VB / 16;
-	constexpr int GT = kGradGroupThreads, NG = kGradGroups;
+	constexpr int GT = kGradGroupThreads;
+	static_assert(NG == 3 || (NG == 4 && kPipeProducerThreads * kPipeProducerRegs + NG * GT * kPipeConsumerRegs <= grad_threads_total(NG) * 96), "register budget of the four-group variant");
 	extern __shared__ unsigned char smem_dyn[];
 	unsigned char* sm = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
 	uint64_t* full = reinterpret_cast<uint64_t*>(sm + pg.off_bar);
@@ -688,16 +710,17 @@ __global__ void __launch_bounds__(kGradThreadsTotal, 1)
 	if (threadIdx.x == 0) {
 		for (int s = 0; s < NS; s++) {
 			mbar_init(full + s, 1);
-			mbar_init(empty + s, 1);
+			mbar_init(empty + s, pg.wstore ? GT / 32 : 1);
 		}
 		for (int k = 0; k < 2 * kProducerWarps; k++) mbar_init(reinterpret_cast<uint64_t*>(sm + pg.off_meta) + k, 1);   // the producers' id rings
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
-	if ((int)blockIdx.x >= n_tiles) return;
+	if ((int)blockIdx.x >= n_tiles) return;   // (the whole CTA)
 
 	if (threadIdx.x >= NG * GT) {
 		// ============================ producers (roles as in k_stage_pipe) ========================================
+		if constexpr (NG == 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kPipeProducerRegs));
 		const int pwarp = (threadIdx.x - NG * GT) >> 5;
 		const int hpitch = (pg.hmax + 3) & ~3;
 		int* idring = reinterpret_cast<int*>(sm + pg.off_ids) + pwarp * 2 * hpitch;
@@ -765,6 +788,7 @@ __global__ void __launch_bounds__(kGradThreadsTotal, 1)
 	}
 
 	// ============================ consumers ====================================================================
+	if constexpr (NG == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kPipeConsumerRegs));
 	const int g = threadIdx.x / GT, tid = threadIdx.x % GT;
 	const int bar_id = 1 + g;
 	int t = blockIdx.x + g * G;
@@ -784,9 +808,16 @@ __global__ void __launch_bounds__(kGradThreadsTotal, 1)
 	int e[kMaxSlots];
 	R vinv;
 	cell_inputs(td, e, vinv);
-	for (int i = g;; i += NG, t += NG * G) {
-		const int slot = i % NS;
-		const uint32_t use = (uint32_t)(i / NS);
+	int slot = g % NS;   // this group's tiles are i = g, g + NG, ... of the CTA: slot i % NS, use i / NS as running values (NG <= NS)
+	uint32_t use = (uint32_t)(g / NS);
+	auto next_use = [&]() {
+		slot += NG;
+		if (slot >= NS) {
+			slot -= NS;
+			use++;
+		}
+	};
+	for (;; t += NG * G, next_use()) {
 		const bool has_next = t + NG * G < n_tiles;
 		TileDesc tdnn = tdn;
 		if (t + 2 * NG * G < n_tiles) tdnn = tv.tiles[tile0 + t + 2 * NG * G];
@@ -802,7 +833,7 @@ __global__ void __launch_bounds__(kGradThreadsTotal, 1)
 		mbar_wait(full + slot, use & 1u);
 		if (pg.dbg & 4) {   // timing experiment: the fill pipeline alone
 			named_bar(bar_id, GT);
-			if (tid == 0) mbar_arrive(empty + slot);
+			if (pg.wstore ? (tid & 31) == 0 : tid == 0) mbar_arrive(empty + slot);
 			if (!has_next) break;
 			td = tdn;
 			tdn = tdnn;
@@ -880,18 +911,34 @@ __global__ void __launch_bounds__(kGradThreadsTotal, 1)
 			for (int j = 0; j < CVC; j++) *reinterpret_cast<typename Chunk16<R>::T*>(Qs + (size_t)lc * VB + j * 16) = Chunk16<R>::pack(rec + j * Chunk16<R>::N);
 		}
 		fence_proxy_async();
-		named_bar(bar_id, GT);
-		if (tid == 0) {
-			bulk_store(reinterpret_cast<unsigned char*>(m.vis) + (size_t)td.c0 * VB, smem_u32(Qs), (uint32_t)td.nt * VB);
-			bulk_commit();
-			bulk_wait_read0();   // the slot may be refilled once the store has read it
-			mbar_arrive(empty + slot);
+		if (pg.wstore) {
+			// every warp hands over the V records of its own 32 cells and releases the slot for itself (`empty` counts the warps of
+			// the group): no second group barrier, no single thread the whole group waits for
+			__syncwarp();
+			if ((tid & 31) == 0) {
+				const int base = tid, n = min(32, td.nt - base);
+				if (n > 0) {
+					bulk_store(reinterpret_cast<unsigned char*>(m.vis) + (size_t)(td.c0 + base) * VB, smem_u32(Qs) + (uint32_t)base * VB, (uint32_t)n * VB);
+					bulk_commit();
+					bulk_wait_read0();
+				}
+				mbar_arrive(empty + slot);
+			}
+			__syncwarp();
+		} else {
+			named_bar(bar_id, GT);
+			if (tid == 0) {
+				bulk_store(reinterpret_cast<unsigned char*>(m.vis) + (size_t)td.c0 * VB, smem_u32(Qs), (uint32_t)td.nt * VB);
+				bulk_commit();
+				bulk_wait_read0();   // the slot may be refilled once the store has read it
+				mbar_arrive(empty + slot);
+			}
 		}
 		if (!has_next) break;
 		td = tdn;
 		tdn = tdnn;
 	}
-	if (tid == 0) bulk_wait0();
+	if (pg.wstore ? (tid & 31) == 0 : tid == 0) bulk_wait0();
 }
 
 }  // namespace lfm
