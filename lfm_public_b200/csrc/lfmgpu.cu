@@ -165,9 +165,9 @@ struct lfmgpu_ctx {
 	bool pipe_ok = false;              // tensor maps and ring geometry are in place
 	int pipe_enable = 3;               // LFMGPU_PIPE: bit 0 stage kernel, bit 1 gradient kernel; 0: the tile kernels of round 1 serve everything
 	int pipe_slots_cap = 6;            // LFMGPU_PIPE_SLOTS
-	int pipe_pf_dist = 3;              // L2 prefetch distance of the persistent kernels in tiles per CTA (LFMGPU_PIPE_PF, 0: off)
+	int pipe_pf_dist = 2;              // L2 prefetch distance of the persistent kernels in tiles per CTA (LFMGPU_PIPE_PF, 0: off)
 	int pipe_grad_slots_cap = 12;      // LFMGPU_PIPE_GSLOTS
-	int grad_groups = 4;               // consumer groups of the gradient kernel, 3 or 4 (LFMGPU_PIPE_GGROUPS)
+	int grad_groups = 3;               // consumer groups of the gradient kernel, 3 or 4 (LFMGPU_PIPE_GGROUPS)
 	int pipe_spare_sms = 8;            // SMs left to the halo stream's kernels on a rank with neighbours (LFMGPU_PIPE_SPARE)
 	int n_sms = 0;
 	PipeGeom pipe{};
@@ -756,6 +756,8 @@ int pipe_setup(lfmgpu_ctx* h) {
 	g.dbg = getenv("LFMGPU_PIPE_DBG") ? atoi(getenv("LFMGPU_PIPE_DBG")) : 0;
 	g.coop = getenv("LFMGPU_PIPE_COOP") ? atoi(getenv("LFMGPU_PIPE_COOP")) : 1;
 	g.wstore = getenv("LFMGPU_PIPE_WSTORE") ? atoi(getenv("LFMGPU_PIPE_WSTORE")) : 1;
+	const int direct = getenv("LFMGPU_PIPE_DIRECT") ? atoi(getenv("LFMGPU_PIPE_DIRECT")) : 2;   // bit 0: stage kernel, bit 1: gradient kernel
+	g.direct = direct & 1;
 	g.pf_face = getenv("LFMGPU_PIPE_PFF") ? atoi(getenv("LFMGPU_PIPE_PFF")) : 0;
 	g.pf_cell = getenv("LFMGPU_PIPE_PFC") ? atoi(getenv("LFMGPU_PIPE_PFC")) : 1;
 	g.hmax = hmax;
@@ -785,6 +787,7 @@ int pipe_setup(lfmgpu_ctx* h) {
 		gg.box_cells = TC;
 		gg.pf_dist = getenv("LFMGPU_PIPE_GPF") ? atoi(getenv("LFMGPU_PIPE_GPF")) : 0;   // (the gradient kernel's fills are short: prefetching them measured slower)
 		gg.dbg = g.dbg;
+		gg.direct = (direct >> 1) & 1;
 		gg.wstore = getenv("LFMGPU_PIPE_GWSTORE") ? atoi(getenv("LFMGPU_PIPE_GWSTORE")) : 1;
 		gg.hmax = hmax;
 		gg.smax = TC + hmax;
@@ -1535,7 +1538,7 @@ int lfmgpu_create(const lfmgpu_desc* ds, int device, lfmgpu_t* out) {
 	if (const char* e = getenv("LFMGPU_PIPE_SPARE")) h->pipe_spare_sms = std::max(0, atoi(e));
 	if (const char* e = getenv("LFMGPU_PIPE_PF")) h->pipe_pf_dist = std::max(0, atoi(e));
 	if (const char* e = getenv("LFMGPU_PIPE_GSLOTS")) h->pipe_grad_slots_cap = atoi(e);
-	if (const char* e = getenv("LFMGPU_PIPE_GGROUPS")) h->grad_groups = atoi(e) == 3 ? 3 : 4;
+	if (const char* e = getenv("LFMGPU_PIPE_GGROUPS")) h->grad_groups = atoi(e) == 4 ? 4 : 3;
 	if (!rc) rc = tile_plan_build(h, ds);
 	if (!rc) rc = pipe_setup(h);
 	if (!(h->pipe_enable & 2)) h->grad_pipe_ok = false;

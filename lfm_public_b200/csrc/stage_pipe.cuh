@@ -202,6 +202,8 @@ struct PipeGeom {
 	int coop;               // 1: the four producer warps share every fill (a quarter of the halo gathers each); 0: one warp per ring slot
 	int wstore;             // 1: every consumer warp stores the records of its own cells and releases the slot for itself (no group barrier
 	                        // behind phase C; the flux rows are guarded by an mbarrier instead); 0: one store per tile behind a group barrier
+	int direct;             // 1: the finished records go from registers straight to HBM (two 16-byte stores per lane = whole sectors) instead of
+	                        // through a staging area and a bulk store; slots and flux rows are released per warp as with wstore
 	int pf_face;            // 1: the consumers ask for the face constants of their second round (L2 hits after the producers' prefetch) into
 	                        // the L1 before they start the first: the round then starts on L1 hits instead of an L2 round trip
 	int pf_cell;            // 1: the L2 prefetch also covers what phase C reads per cell (gather lists, accumulators, volumes, sponge)
@@ -312,7 +314,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 	if (threadIdx.x == 0) {
 		for (int s = 0; s < NS; s++) {
 			mbar_init(full + s, pg.coop ? kProducerWarps : 1);   // the expect_tx arrival of each producer warp that fills the slot; everything else is counted in bytes
-			mbar_init(empty + s, pg.wstore ? GT / 32 : 1);   // one elected consumer thread (wstore: one lane of every warp of the group)
+			mbar_init(empty + s, (pg.wstore || pg.direct) ? GT / 32 : 1);   // one elected consumer thread (wstore, direct: one lane of every warp of the group)
 		}
 		for (int k = 0; k < 2; k++) mbar_init(full + 2 * pg.n_slots + k, GT / 32);   // flfree[group]: every warp of the group is done with the flux rows
 		for (int k = 0; k < 2 * kProducerWarps; k++) mbar_init(reinterpret_cast<uint64_t*>(sm + pg.off_meta) + k, 1);   // the producers' id rings
@@ -501,7 +503,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 	// sat in front of the wait for the slot)
 	int slot = g % NS;
 	uint32_t use = (uint32_t)(g / NS);
-	uint64_t* flfree = full + 2 * NS + g;   // (wstore) completes once per tile of this group
+	const bool per_warp = pg.wstore || pg.direct;
+	uint64_t* flfree = full + 2 * NS + g;   // (per_warp) completes once per tile of this group
 	uint32_t nth = 0;                       // tiles this group has finished
 	auto next_use = [&]() {
 		slot += 2;
@@ -527,7 +530,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 		mbar_wait(full + slot, use & 1u);
 		if (pg.dbg & 4) {   // timing experiment: the fill pipeline alone
 			named_bar(bar_id, GT);
-			if (pg.wstore ? (tid & 31) == 0 : tid == 0) mbar_arrive(empty + slot);
+			if (per_warp ? (tid & 31) == 0 : tid == 0) mbar_arrive(empty + slot);
 			if (!has_next) break;
 			td = tdn;
 			continue;
@@ -569,7 +572,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 			R rhs[NQ];
 			face_flux<R, D, SCHEME>(m.k, c, n, cur.g, ghost, dv, rhs);
 			// (wstore) the flux rows still belong to the previous tile of this group until every warp has gathered from them
-			if (pg.wstore && lf == tid && nth) mbar_wait(flfree, (nth - 1u) & 1u);
+			if (per_warp && lf == tid && nth) mbar_wait(flfree, (nth - 1u) & 1u);
 #pragma unroll
 			for (int k = 0; k < NQ; k++) fl[k * fmax + lf] = rhs[k];
 		}
@@ -609,9 +612,15 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 				}
 				if (active) {
 					constexpr int C0 = (NQ / EPC);   // chunks [0, C0) hold conservatives only: the low lane's share
+					unsigned char* gout = reinterpret_cast<unsigned char*>(qn) + (size_t)c * QB;   // (direct) the cell's record in HBM
 					if (part == 0) {
 #pragma unroll
-						for (int j = 0; j < C0; j++) *reinterpret_cast<typename Chunk16<R>::T*>(outb + (size_t)lc * QB + j * 16) = Chunk16<R>::pack(rec + j * EPC);
+						for (int j = 0; j < C0; j++) {
+							if (pg.direct)
+								*reinterpret_cast<typename Chunk16<R>::T*>(gout + j * 16) = Chunk16<R>::pack(rec + j * EPC);
+							else
+								*reinterpret_cast<typename Chunk16<R>::T*>(outb + (size_t)lc * QB + j * 16) = Chunk16<R>::pack(rec + j * EPC);
+						}
 					} else {
 						CellState<R, D> cs;
 #pragma unroll
@@ -621,13 +630,30 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 						rec[RC::RPSI] = cs.Rpsi;
 						rec[RC::AUX] = cs.aux;
 #pragma unroll
-						for (int j = C0; j < CQ; j++) *reinterpret_cast<typename Chunk16<R>::T*>(outb + (size_t)lc * QB + j * 16) = Chunk16<R>::pack(rec + j * EPC);
+						for (int j = C0; j < CQ; j++) {
+							if (pg.direct)
+								*reinterpret_cast<typename Chunk16<R>::T*>(gout + j * 16) = Chunk16<R>::pack(rec + j * EPC);
+							else
+								*reinterpret_cast<typename Chunk16<R>::T*>(outb + (size_t)lc * QB + j * 16) = Chunk16<R>::pack(rec + j * EPC);
+						}
 					}
 				}
 			}
 		}
 		// the first face of this group's next tile travels during the store and the wait for its slot
 		if (has_next && tid < tdn.nf) fetch_face<R, D, SCHEME>(tv, (size_t)tdn.f_off + tid, cur);
+		if (pg.direct) {
+			// nothing is staged: a warp is done with the slot and the flux rows when its lanes are
+			__syncwarp();
+			if ((tid & 31) == 0) {
+				mbar_arrive(empty + slot);
+				mbar_arrive(flfree);
+			}
+			nth++;
+			if (!has_next) break;
+			td = tdn;
+			continue;
+		}
 		fence_proxy_async();   // the staging writes above become visible to the TMA engine
 		if (pg.wstore) {
 			// every warp hands over the records of its own cells (16 per pass, contiguous in the staging area and in HBM) and
@@ -657,7 +683,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
 		if (!has_next) break;
 		td = tdn;
 	}
-	if (pg.wstore ? (tid & 31) == 0 : tid == 0) bulk_wait0();   // the last store has left shared memory and is performed before the CTA exits
+	if (!pg.direct && (pg.wstore ? (tid & 31) == 0 : tid == 0)) bulk_wait0();   // the last store has left shared memory and is performed before the CTA exits
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -676,6 +702,9 @@ struct GradGeom {
 	int pf_dist;            // L2 prefetch distance (see PipeGeom)
 	int dbg;                // timing experiments (see PipeGeom)
 	int wstore;             // per-warp stores and releases (see PipeGeom)
+	int direct;             // 1: every thread writes its cell's V record from registers straight to HBM (eight 16-byte stores; the L2 merges the
+	                        // half sectors): no staging -- whose 128-byte-strided writes were 8-way bank conflicts, more than half of the
+	                        // kernel's shared-memory wavefronts (profiles/r2_final_ncu256_summary.txt) --, no proxy fence, no group barrier
 };
 // Ring depth and group count are tied: a group reaches use k of a slot knowing only that ITS OWN earlier tiles were
 // released; the parity wait for the release of use k - 1 is unambiguous only if use k - 2 (tile i - 2 NS) was one of them,
@@ -710,7 +739,7 @@ __global__ void __launch_bounds__(grad_threads_total(NG), 1)
 	if (threadIdx.x == 0) {
 		for (int s = 0; s < NS; s++) {
 			mbar_init(full + s, 1);
-			mbar_init(empty + s, pg.wstore ? GT / 32 : 1);
+			mbar_init(empty + s, (pg.wstore || pg.direct) ? GT / 32 : 1);
 		}
 		for (int k = 0; k < 2 * kProducerWarps; k++) mbar_init(reinterpret_cast<uint64_t*>(sm + pg.off_meta) + k, 1);   // the producers' id rings
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -833,7 +862,7 @@ __global__ void __launch_bounds__(grad_threads_total(NG), 1)
 		mbar_wait(full + slot, use & 1u);
 		if (pg.dbg & 4) {   // timing experiment: the fill pipeline alone
 			named_bar(bar_id, GT);
-			if (pg.wstore ? (tid & 31) == 0 : tid == 0) mbar_arrive(empty + slot);
+			if ((pg.wstore || pg.direct) ? (tid & 31) == 0 : tid == 0) mbar_arrive(empty + slot);
 			if (!has_next) break;
 			td = tdn;
 			tdn = tdnn;
@@ -905,6 +934,19 @@ __global__ void __launch_bounds__(grad_threads_total(NG), 1)
 			if (D == 3) rec[RC::TR] = dudx_trace_neg<R, D>(&dudx[0][0]);
 		}
 		if (has_next) cell_inputs(tdn, e, vinv);   // the next tile's gather lists and volumes travel from here on
+		if (pg.direct) {
+			if (active) {
+				unsigned char* gout = reinterpret_cast<unsigned char*>(m.vis) + (size_t)(td.c0 + lc) * VB;
+#pragma unroll
+				for (int j = 0; j < CVC; j++) *reinterpret_cast<typename Chunk16<R>::T*>(gout + j * 16) = Chunk16<R>::pack(rec + j * Chunk16<R>::N);
+			}
+			__syncwarp();   // every lane of the warp has read what it needs of the slot
+			if ((tid & 31) == 0) mbar_arrive(empty + slot);
+			if (!has_next) break;
+			td = tdn;
+			tdn = tdnn;
+			continue;
+		}
 		named_bar(bar_id, GT);   // every thread of the group has read what it needs of the Q region: it becomes the V staging
 		if (active) {
 #pragma unroll
@@ -938,7 +980,7 @@ __global__ void __launch_bounds__(grad_threads_total(NG), 1)
 		td = tdn;
 		tdn = tdnn;
 	}
-	if (pg.wstore ? (tid & 31) == 0 : tid == 0) bulk_wait0();
+	if (!pg.direct && (pg.wstore ? (tid & 31) == 0 : tid == 0)) bulk_wait0();
 }
 
 }  // namespace lfm
