@@ -756,7 +756,7 @@ int pipe_setup(lfmgpu_ctx* h) {
 	g.dbg = getenv("LFMGPU_PIPE_DBG") ? atoi(getenv("LFMGPU_PIPE_DBG")) : 0;
 	g.coop = getenv("LFMGPU_PIPE_COOP") ? atoi(getenv("LFMGPU_PIPE_COOP")) : 1;
 	g.wstore = getenv("LFMGPU_PIPE_WSTORE") ? atoi(getenv("LFMGPU_PIPE_WSTORE")) : 1;
-	const int direct = getenv("LFMGPU_PIPE_DIRECT") ? atoi(getenv("LFMGPU_PIPE_DIRECT")) : 2;   // bit 0: stage kernel, bit 1: gradient kernel
+	const int direct = getenv("LFMGPU_PIPE_DIRECT") ? atoi(getenv("LFMGPU_PIPE_DIRECT")) : 1;   // bit 0: stage kernel, bit 1: gradient kernel
 	g.direct = direct & 1;
 	g.pf_face = getenv("LFMGPU_PIPE_PFF") ? atoi(getenv("LFMGPU_PIPE_PFF")) : 0;
 	g.pf_cell = getenv("LFMGPU_PIPE_PFC") ? atoi(getenv("LFMGPU_PIPE_PFC")) : 1;
