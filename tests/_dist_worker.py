@@ -18,10 +18,14 @@ from lfm_public_b200 import host_api  # noqa: E402
 
 def main():
     out_dir, n, steps = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+    bench_layout = len(sys.argv) > 4 and sys.argv[4] == "bench"   # the multi-GPU bench's own numbering and z-periodic layout
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     blocks = bench.BLOCKS[world]
-    case, dt = bench.build_rank_case(n, blocks, rank, world, 8, 1, (4, 4, 4))
+    if bench_layout:
+        case, dt = bench.build_rank_case(n, blocks, rank, world, 8, 1, "morton", "morton", z_cyclic=True)
+    else:
+        case, dt = bench.build_rank_case(n, blocks, rank, world, 8, 1, (4, 4, 4))
     host_api.exchange_distributed(case, rank)
     a = case.arrays()
     orc = oracle_lib.Oracle(case)
