@@ -6,8 +6,10 @@
  *
  * Ranks are forked from the first process inside MPI_Init when LFM_MPI_NP=<n> is set (no mpirun);
  * point-to-point runs over AF_UNIX socket pairs with a progress engine, collectives over a shared
- * anonymous mapping.  One-sided (MPI_Win_*) and neighbourhood collectives are link-only stubs that
- * abort: the reference's haloCommType 0/1/2 (two-sided) paths are the ones supported.
+ * anonymous mapping.  One-sided communication is served for general active target synchronisation
+ * (MPI_Win_post / start / complete / wait + MPI_Get / MPI_Rget: the reference's haloCommType 3/4), emulated
+ * with messages (mpi_shim.cpp); passive target locks and neighbourhood collectives are link-only stubs
+ * that abort.
  */
 #ifndef LFM_MINI_MPI_H
 #define LFM_MINI_MPI_H

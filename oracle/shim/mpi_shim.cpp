@@ -91,6 +91,44 @@ struct Peer {
 };
 std::vector<Peer> g_peers;
 
+// ---- one-sided communication, general active target synchronisation (post / start / complete / wait) ----------------------
+// The ranks are separate processes without a common mapping of the window memory, so an exposure epoch is emulated with
+// messages on the same sockets: MPI_Win_post sends the window's contents to every origin of the group (the target may not
+// change an exposed window before MPI_Win_wait returns, so the copy taken at the post IS what a get of that epoch reads),
+// MPI_Get copies out of the copy received from its target, MPI_Win_complete tells every target that the origin is done and
+// MPI_Win_wait collects those notes.  The messages carry reserved tags and never enter the point-to-point matching: they
+// are queued per (peer, window) as they arrive, whatever the receiver is doing.
+const int32_t RMA_SNAP = 0x7f000000, RMA_DONE = 0x7e000000, RMA_KIND = 0x7f000000, RMA_WIN = 0x00ffffff;
+inline bool is_rma(int32_t tag) { return (tag & RMA_KIND) == RMA_SNAP || (tag & RMA_KIND) == RMA_DONE; }
+struct Window {
+	char* base = nullptr;
+	size_t size = 0;
+	int disp_unit = 1;
+	std::vector<int> exposed_to, accessing;                 // groups of the open exposure / access epoch
+	std::vector<std::deque<std::vector<char>>> snap;        // [peer]: window copies received, oldest first
+	std::vector<int> done;                                  // [peer]: completion notes received and not yet waited for
+};
+std::vector<Window> g_wins;
+std::vector<std::vector<int>> g_groups = {{}};             // handle 0: the world group (filled in MPI_Comm_group)
+
+void rma_deliver(int peer, const Hdr& h, std::vector<char>& data) {
+	const size_t w = (size_t)(h.tag & RMA_WIN);
+	if (w >= g_wins.size()) {   // a peer may post before this rank has returned from its own MPI_Win_create
+		g_wins.resize(w + 1);
+	}
+	Window& W = g_wins[w];
+	if (W.snap.empty()) {
+		W.snap.resize((size_t)g_size);
+		W.done.assign((size_t)g_size, 0);
+	}
+	if ((h.tag & RMA_KIND) == RMA_SNAP) {
+		W.snap[(size_t)peer].emplace_back();
+		W.snap[(size_t)peer].back().swap(data);
+	} else {
+		W.done[(size_t)peer]++;
+	}
+}
+
 [[noreturn]] void die(const char* msg) {
 	fprintf(stderr, "[mini-mpi rank %d] %s\n", g_rank, msg);
 	if (g_sh) g_sh->abort_code.store(99);
@@ -168,7 +206,7 @@ bool progress_peer(int p) {
 			P.have_hdr = true;
 			P.hdr_off = 0;
 			P.body_off = 0;
-			if (!P.recvq.empty() && P.unexpected.empty()) {
+			if (!is_rma(P.hdr.tag) && !P.recvq.empty() && P.unexpected.empty()) {
 				P.cur_req = P.recvq.front();
 				P.recvq.pop_front();
 				if ((size_t)P.hdr.nbytes != g_reqs[P.cur_req].nbytes) die("message size mismatch (posted recv vs incoming)");
@@ -199,6 +237,9 @@ bool progress_peer(int p) {
 		if (blocked) break;
 		if (P.cur_req >= 0) {
 			complete_recv(P.cur_req);
+		} else if (is_rma(P.hdr.tag)) {
+			rma_deliver(p, P.hdr, P.stash);
+			P.stash.clear();
 		} else {
 			Unexpected u;
 			u.hdr = P.hdr;
@@ -604,21 +645,122 @@ int MPI_Type_create_resized(MPI_Datatype, MPI_Aint, MPI_Aint extent, MPI_Datatyp
 int MPI_Type_commit(MPI_Datatype*) { return MPI_SUCCESS; }
 
 #define UNSUPPORTED(name) \
-	die(name " is not implemented by the mini-MPI shim (use haloCommType 0, 1 or 2)")
+	die(name " is not implemented by the mini-MPI shim")
 
-int MPI_Win_create(void*, MPI_Aint, int, MPI_Info, MPI_Comm, MPI_Win*) { UNSUPPORTED("MPI_Win_create"); }
-int MPI_Win_free(MPI_Win*) { UNSUPPORTED("MPI_Win_free"); }
-int MPI_Win_post(MPI_Group, int, MPI_Win) { UNSUPPORTED("MPI_Win_post"); }
-int MPI_Win_start(MPI_Group, int, MPI_Win) { UNSUPPORTED("MPI_Win_start"); }
-int MPI_Win_complete(MPI_Win) { UNSUPPORTED("MPI_Win_complete"); }
-int MPI_Win_wait(MPI_Win) { UNSUPPORTED("MPI_Win_wait"); }
-int MPI_Win_lock(int, int, int, MPI_Win) { UNSUPPORTED("MPI_Win_lock"); }
-int MPI_Win_lock_all(int, MPI_Win) { UNSUPPORTED("MPI_Win_lock_all"); }
-int MPI_Get(void*, int, MPI_Datatype, int, MPI_Aint, int, MPI_Datatype, MPI_Win) { UNSUPPORTED("MPI_Get"); }
-int MPI_Rget(void*, int, MPI_Datatype, int, MPI_Aint, int, MPI_Datatype, MPI_Win, MPI_Request*) { UNSUPPORTED("MPI_Rget"); }
-int MPI_Comm_group(MPI_Comm, MPI_Group*) { UNSUPPORTED("MPI_Comm_group"); }
-int MPI_Group_incl(MPI_Group, int, const int*, MPI_Group*) { UNSUPPORTED("MPI_Group_incl"); }
-int MPI_Group_free(MPI_Group*) { UNSUPPORTED("MPI_Group_free"); }
+// (blocking) internal send of a reserved-tag message; incoming traffic keeps being drained meanwhile
+static void rma_send(int peer, int32_t tag, const char* data, size_t nbytes) {
+	int r = new_req();
+	Req& rq = g_reqs[(size_t)r];
+	rq.kind = SEND;
+	rq.peer = peer;
+	rq.tag = tag;
+	rq.buf = const_cast<char*>(data);
+	rq.nbytes = nbytes;
+	post(r);
+	wait_req(r);
+	g_reqs[(size_t)r].in_use = false;
+}
+static Window& win_of(MPI_Win win) {
+	if (win < 0 || (size_t)win >= g_wins.size() || !g_wins[(size_t)win].base) die("invalid window handle");
+	return g_wins[(size_t)win];
+}
+
+int MPI_Win_create(void* base, MPI_Aint size, int disp_unit, MPI_Info, MPI_Comm, MPI_Win* win) {
+	// collective and called in the same order by every rank: the n-th window of every rank gets handle n
+	static int n_created = 0;
+	const size_t w = (size_t)n_created++;
+	if (w >= g_wins.size()) g_wins.resize(w + 1);
+	Window& W = g_wins[w];
+	W.base = (char*)base;
+	W.size = (size_t)size;
+	W.disp_unit = disp_unit;
+	if (W.snap.empty()) {
+		W.snap.resize((size_t)g_size);
+		W.done.assign((size_t)g_size, 0);
+	}
+	*win = (MPI_Win)w;
+	barrier_impl();
+	return MPI_SUCCESS;
+}
+int MPI_Win_free(MPI_Win* win) {
+	barrier_impl();
+	*win = -1;
+	return MPI_SUCCESS;
+}
+int MPI_Win_post(MPI_Group g, int, MPI_Win win) {
+	Window& W = win_of(win);
+	if (!W.exposed_to.empty()) die("MPI_Win_post on a window whose exposure epoch is still open");
+	W.exposed_to = g_groups[(size_t)g];
+	for (int r : W.exposed_to) rma_send(r, RMA_SNAP | (int32_t)win, W.base, W.size);
+	return MPI_SUCCESS;
+}
+int MPI_Win_start(MPI_Group g, int, MPI_Win win) {
+	Window& W = win_of(win);
+	if (!W.accessing.empty()) die("MPI_Win_start on a window whose access epoch is still open");
+	W.accessing = g_groups[(size_t)g];
+	return MPI_SUCCESS;
+}
+static const std::vector<char>& rma_copy_of(Window& W, int target) {
+	bool member = false;
+	for (int r : W.accessing) member |= r == target;
+	if (!member) die("MPI_Get outside an access epoch that includes the target");
+	while (W.snap[(size_t)target].empty()) {   // the target has not posted yet
+		if (!progress_all()) idle_wait();
+	}
+	return W.snap[(size_t)target].front();
+}
+int MPI_Get(void* o, int oc, MPI_Datatype ot, int rank, MPI_Aint disp, int tc, MPI_Datatype tt, MPI_Win win) {
+	Window& W = win_of(win);
+	const size_t nbytes = (size_t)oc * g_types[(size_t)ot].extent;
+	if (nbytes != (size_t)tc * g_types[(size_t)tt].extent) die("MPI_Get: origin and target sizes differ");
+	const std::vector<char>& copy = rma_copy_of(W, rank);
+	const size_t off = (size_t)disp * (size_t)W.disp_unit;   // (the reference creates its windows with disp_unit 1 on every rank)
+	if (off + nbytes > copy.size()) die("MPI_Get beyond the end of the target window");
+	memcpy(o, copy.data() + off, nbytes);
+	return MPI_SUCCESS;
+}
+int MPI_Rget(void* o, int oc, MPI_Datatype ot, int rank, MPI_Aint disp, int tc, MPI_Datatype tt, MPI_Win win, MPI_Request* req) {
+	MPI_Get(o, oc, ot, rank, disp, tc, tt, win);
+	*req = MPI_REQUEST_NULL;   // complete at once
+	return MPI_SUCCESS;
+}
+int MPI_Win_complete(MPI_Win win) {
+	Window& W = win_of(win);
+	for (int r : W.accessing) {
+		rma_copy_of(W, r);   // an epoch without a get towards r still consumes r's exposure
+		W.snap[(size_t)r].pop_front();
+		rma_send(r, RMA_DONE | (int32_t)win, nullptr, 0);
+	}
+	W.accessing.clear();
+	return MPI_SUCCESS;
+}
+int MPI_Win_wait(MPI_Win win) {
+	Window& W = win_of(win);
+	for (int r : W.exposed_to) {
+		while (W.done[(size_t)r] == 0) {
+			if (!progress_all()) idle_wait();
+		}
+		W.done[(size_t)r]--;
+	}
+	W.exposed_to.clear();
+	return MPI_SUCCESS;
+}
+int MPI_Win_lock(int, int, int, MPI_Win) { UNSUPPORTED("MPI_Win_lock (passive target synchronisation)"); }
+int MPI_Win_lock_all(int, MPI_Win) { UNSUPPORTED("MPI_Win_lock_all (passive target synchronisation)"); }
+int MPI_Comm_group(MPI_Comm, MPI_Group* g) {
+	g_groups[0].resize((size_t)g_size);
+	for (int r = 0; r < g_size; r++) g_groups[0][(size_t)r] = r;
+	*g = 0;
+	return MPI_SUCCESS;
+}
+int MPI_Group_incl(MPI_Group g, int n, const int* ranks, MPI_Group* out) {
+	std::vector<int> members;
+	for (int i = 0; i < n; i++) members.push_back(g_groups[(size_t)g][(size_t)ranks[i]]);
+	g_groups.push_back(members);
+	*out = (MPI_Group)g_groups.size() - 1;
+	return MPI_SUCCESS;
+}
+int MPI_Group_free(MPI_Group*) { return MPI_SUCCESS; }
 int MPI_Comm_split(MPI_Comm, int, int, MPI_Comm*) { UNSUPPORTED("MPI_Comm_split"); }
 int MPI_Dist_graph_create_adjacent(MPI_Comm, int, const int*, const int*, int, const int*, const int*, MPI_Info, int, MPI_Comm*) {
 	UNSUPPORTED("MPI_Dist_graph_create_adjacent");
