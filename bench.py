@@ -543,11 +543,12 @@ def run_gpu_arm(args):
         traffic, traffic_note = None, None
         try:
             # measured DRAM bytes per launch from the committed ncu capture -- valid only for the very binary that was profiled:
-            # the capture is stamped with the SHA-256 of liblfmgpu.so (scripts/ncu_traffic.py) and dropped when the library differs
-            import hashlib
+            # the capture is stamped with the SHA-256 of the library's device code (.nv_fatbin; scripts/ncu_traffic.py,
+            # tools/libstamp.py) and dropped when the kernels differ
+            from lfm_public_b200.tools.libstamp import device_code_sha256
             tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[dom]["f64" if s == 8 else "f32"]
-            so = hashlib.sha256(open(os.path.join(ROOT, "lfm_public_b200", "liblfmgpu.so"), "rb").read()).hexdigest()
-            if tr["n"] == args.n and tr.get("numbering") == args.numbering and tr.get("lib_sha256") == so:
+            so = device_code_sha256(os.path.join(ROOT, "lfm_public_b200", "liblfmgpu.so"))
+            if tr["n"] == args.n and tr.get("numbering") == args.numbering and tr.get("fatbin_sha256") == so:
                 traffic = tr["bytes_per_launch"]
             else:
                 traffic_note = "the committed ncu capture is of another binary or workload: not reported"

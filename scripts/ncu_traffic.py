@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Writes profiles/ncu_traffic.json from a full ncu capture of the dominant kernels: DRAM bytes per launch
-(dram__bytes_read.sum + dram__bytes_write.sum), stamped with the SHA-256 of the library that was profiled so that bench.py
-reports `roofline.traffic` only for that binary.
+(dram__bytes_read.sum + dram__bytes_write.sum), stamped with the SHA-256 of the device code (.nv_fatbin section) of the library
+that was profiled so that bench.py reports `roofline.traffic` only for those kernels.
 
     python scripts/ncu_traffic.py <stage.ncu-rep> <grad.ncu-rep> <n> <numbering> [f64|f32]
 """
@@ -36,13 +36,17 @@ def traffic(rep, kernel=None):
 def main():
     stage, grad, n, numbering = sys.argv[1], sys.argv[2], int(sys.argv[3]), sys.argv[4]
     prec = sys.argv[5] if len(sys.argv) > 5 else "f64"
-    so = hashlib.sha256(open(os.path.join(ROOT, "lfm_public_b200", "liblfmgpu.so"), "rb").read()).hexdigest()
+    sys.path.insert(0, ROOT)
+    from lfm_public_b200.tools.libstamp import device_code_sha256
+    lib = os.path.join(ROOT, "lfm_public_b200", "liblfmgpu.so")
+    so = hashlib.sha256(open(lib, "rb").read()).hexdigest()
+    fat = device_code_sha256(lib)   # what bench.py compares: the device code (the file hash changes from build to build)
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     out = json.load(open(path)) if os.path.exists(path) else {}
     for name, rep in (("tile_stage", stage), ("tile_grad", grad)):
         b, d, u = traffic(rep, {"tile_stage": "k_stage_pipe", "tile_grad": "k_grad_pipe"}[name] if stage == grad else None)
         out.setdefault(name, {})[prec] = {"n": n, "numbering": numbering, "bytes_per_launch": b, "ncu_duration": d, "ncu_duration_unit": u,
-                                          "lib_sha256": so, "capture": os.path.basename(rep)}
+                                          "lib_sha256": so, "fatbin_sha256": fat, "capture": os.path.basename(rep)}
     json.dump(out, open(path, "w"), indent=1, sort_keys=True)
     print(json.dumps(out, indent=1))
 

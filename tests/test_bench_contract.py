@@ -45,3 +45,35 @@ def test_cuda_arm_line():
     x = d["extra"]
     assert "error" not in x, x
     assert x["f32"]["value"] > 0 and all(x["numbering"][k]["value"] > 0 for k in ("morton", "bricks", "lex"))
+
+
+def test_device_code_stamp(tmp_path):
+    """roofline.traffic is only reported for the kernels the committed ncu capture was taken from: the stamp is the SHA-256 of
+    the library's .nv_fatbin section (tools/libstamp.py) -- unchanged by what differs between two builds of the same sources
+    (nvcc leaves a temporary file name in the symbol strings), changed by any change of the device code."""
+    from lfm_public_b200.tools.libstamp import device_code_sha256
+    lib = os.path.join(common.ROOT, "lfm_public_b200", "liblfmgpu.so")
+    if not os.path.exists(lib):
+        pytest.skip("liblfmgpu.so not built")
+    stamp = device_code_sha256(lib)
+    raw = bytearray(open(lib, "rb").read())
+    # a byte of the symbol string table (behind every loaded section): same stamp
+    a = bytearray(raw)
+    i = a.rindex(b"fatbinData")
+    a[i - 8] ^= 1
+    pa = tmp_path / "a.so"
+    pa.write_bytes(bytes(a))
+    assert device_code_sha256(str(pa)) == stamp
+    # a byte in the middle of the fat binary: another stamp
+    import struct
+    e_shoff, = struct.unpack_from("<Q", raw, 0x28)
+    e_shentsize, e_shnum, _ = struct.unpack_from("<HHH", raw, 0x3A)
+    sizes = [struct.unpack_from("<IIQQQQ", raw, e_shoff + k * e_shentsize)[4:6] for k in range(e_shnum)]
+    off, size = max(sizes, key=lambda t: t[1])   # the fat binary is by far the largest section
+    b = bytearray(raw)
+    b[off + size // 2] ^= 1
+    pb = tmp_path / "b.so"
+    pb.write_bytes(bytes(b))
+    assert device_code_sha256(str(pb)) != stamp
+    tr = json.load(open(os.path.join(common.ROOT, "profiles", "ncu_traffic.json")))
+    assert all("fatbin_sha256" in v["f64"] for k, v in tr.items() if k.startswith("tile_"))
