@@ -11,7 +11,7 @@ import common
 pytestmark = pytest.mark.skipif(not common.have_ref(), reason="reference binary not built")
 
 
-@pytest.mark.parametrize("name", ["quad2d_m1_p4", "hex3d_m2_p4", "hex3d_m2_les_p4"])
+@pytest.mark.parametrize("name", ["quad2d_m1_p4", "hex3d_m2_p4", "hex3d_m2_les_p4", "hex3d_m2_pc8", "hex3d_ausm_p4"])
 @pytest.mark.parametrize("halo,comm", [(3, 1), (3, 2), (4, 1), (4, 2)])
 def test_one_sided_modes_equal_two_sided(name, halo, comm, tmp_path):
     fields = {}
@@ -26,3 +26,19 @@ def test_one_sided_modes_equal_two_sided(name, halo, comm, tmp_path):
         for k in ("rho", "U", "E", "p"):
             a, b = fields["two_sided"][r][k], fields["one_sided"][r][k]
             assert np.isfinite(a).all() and np.array_equal(a, b), f"{name} halo {halo} comm {comm} rank {r} field {k}: rel max {common.rel_max(a, b):.3e}"
+
+
+@pytest.mark.skipif(not common.have_ref(sp=True), reason="single-precision reference binary not built")
+@pytest.mark.parametrize("halo,comm", [(3, 2), (4, 1)])
+def test_one_sided_modes_equal_two_sided_fp32(halo, comm, tmp_path):
+    """The single-precision build moves float payloads through the same windows (MPI_CHAR gets of float buffers)."""
+    fields = {}
+    for tag, h in (("two_sided", 2), ("one_sided", halo)):
+        d = str(tmp_path / tag)
+        m, o = common.build_case("hex3d_m2_p4", d, haloCommType=h, commType=comm)
+        common.run_reference(d, o, sp=True, dump=False)
+        fields[tag] = common.read_reference_q(d, o, o["deltaT"] * common.N_STEPS, o["dimension"])
+        n_ranks = o["n_ranks"]
+    for r in range(n_ranks):
+        for k in ("rho", "U", "E", "p"):
+            assert np.array_equal(fields["two_sided"][r][k], fields["one_sided"][r][k]), f"fp32 halo {halo} comm {comm} rank {r} field {k}"
