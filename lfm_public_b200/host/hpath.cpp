@@ -4,8 +4,10 @@
 // prepared without OpenFOAM.  Result: order[new] = old with the boundary submesh first (a walk that always moves
 // to the nearest unwalked boundary cell), then the interior submesh (a walk that hugs the rim of what is left,
 // best of several starts and of two next-cell rules), cells that no walk reached ("dead ends") appended to
-// their part.  The plugin cannot run here (no OpenFOAM), so this file is pinned only by its invariants
-// (tests/test_renumber.py): a permutation, boundary submesh first, path adjacency.
+// their part.  PINNED against the plugin itself: oracle/_ref/hpath_plugin is hpathRenumber.C compiled unchanged against a
+// stand-in for the few OpenFOAM types it touches (oracle/shim/openfoam_stub/), and tests/test_hpath_vs_plugin.py requires
+// the two orders to be equal on the zoo's meshes, on larger shuffled meshes and on the reference's own example meshes
+// (525 000 quads, 1 959 342 triangle prisms); tests/test_renumber.py keeps the invariants.
 //
 // Decisions of the plugin that shape the numbering and are kept, quirks included:
 //   * `empty` patches do not count as boundary (hpathRenumber.C:137-146);
