@@ -548,7 +548,11 @@ def run_gpu_arm(args):
             from lfm_public_b200.tools.libstamp import device_code_sha256
             tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[dom]["f64" if s == 8 else "f32"]
             so = device_code_sha256(os.path.join(ROOT, "lfm_public_b200", "liblfmgpu.so"))
-            if tr["n"] == args.n and tr.get("numbering") == args.numbering and tr.get("fatbin_sha256") == so:
+            if abs(per_launch_cells - n_cells) > 0.5:
+                # (a rank with neighbours launches the kernel once per submesh: `achieved` is per average launch there, the capture
+                # is of a launch over the whole rank)
+                traffic_note = "the committed ncu capture is of a launch over the whole rank; this run launches per submesh: not reported"
+            elif tr["n"] == args.n and tr.get("numbering") == args.numbering and tr.get("fatbin_sha256") == so:
                 traffic = tr["bytes_per_launch"]
             else:
                 traffic_note = "the committed ncu capture is of another binary or workload: not reported"
