@@ -86,8 +86,8 @@ CASES = {
 N_STEPS = 6
 
 
-def build_case(name, case_dir, n_steps=N_STEPS, **override):
-    spec = CASES[name]
+def build_case(name, case_dir, n_steps=N_STEPS, spec=None, **override):
+    spec = spec or CASES[name]
     m = spec["mesh"]()
     opts = dict(spec["opts"])
     opts.update(override)

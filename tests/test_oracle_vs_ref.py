@@ -122,3 +122,42 @@ def test_oracle_on_the_reference_example_cases(name, tmp_path):
     mine = common.primitives_from_q(case.to_mesh_order(orc.download(0)), case.desc.c.gamma_m1)
     for k, want in fx["sha256"].items():
         assert hashlib.sha256(np.ascontiguousarray(mine[k], dtype=np.float64).tobytes()).hexdigest() == want, (name, k)
+
+
+# Larger than the zoo (whose meshes are a few hundred cells so that every test runs in a blink): the same pinning on meshes where
+# every rank has thousands of interior cells, several tiles' worth of halo and all three patch kinds towards a neighbour.
+MEDIUM = {
+    # 61 440 hexes, 2x2x2 ranks, z periodic: processor + processorCyclic patches, M2 + viscous + sponge (the bench workload's scheme)
+    "hex48x40x32_m2_pc8": dict(mesh=lambda: common.meshgen.hex_box(48, 40, 32, lengths=(2.0, 1.5, 1.0), z_cyclic=True), two_d=False, blocks=(2, 2, 2),
+                               opts=dict(solver=1, dimension=3, deltaT=1e-3, Ls=0.4, commType=2, mu=7.17948717948718e-05)),
+    # 30 720-cell O-grid cylinder in 4 ranks around the cylinder: wall + inlet/outlet + cyclic span, M1, packed payload
+    "ogrid3d_32x96x10_m1_p4": dict(mesh=lambda: common.meshgen.ogrid_cylinder(32, 96, 10, r_in=0.5, r_out=6.0, span=1.0, stretch=4.0), two_d=False,
+                                   blocks=(2, 2, 1), opts=dict(solver=0, dimension=3, deltaT=5e-4, Ls=2.0, commType=1, mu=7.17948717948718e-05)),
+    # 36 000 shuffled triangle prisms, 2D, M2, serial (the unstructured generator has no block decomposition)
+    "tri150x120_m2": dict(mesh=lambda: common.meshgen.tri_prism_box(150, 120, lengths=(2.0, 1.6), shuffle_seed=5), two_d=True, blocks=None,
+                          opts=dict(solver=1, dimension=2, deltaT=5e-4, Ls=0.5)),
+}
+
+
+@needs_ref
+@pytest.mark.parametrize("name", sorted(MEDIUM))
+def test_medium_meshes_match_reference_fp64(name, tmp_path):
+    case_dir = str(tmp_path / name)
+    m, o = common.build_case(name, case_dir, n_steps=3, spec=MEDIUM[name])
+    common.run_reference(case_dir, o)
+    cases = common.open_ranks(case_dir, o)
+    oracles = [oracle_lib.Oracle(c) for c in cases]
+    record = {}
+    oracle_lib.lockstep_run(oracles, cases, o["solver"], o["deltaT"], 3, record=record)
+    D = o["dimension"]
+    ref = common.read_reference_q(case_dir, o, o["deltaT"] * 3, D)
+    for r, (c, orc) in enumerate(zip(cases, oracles)):
+        mine = common.primitives_from_q(c.to_mesh_order(orc.download(0)), c.desc.c.gamma_m1)
+        assert len(ref[r]["rho"]) == c.desc.n_cells and ref[r]["rho"].std() > 0
+        for k in ("rho", "U", "E", "p"):
+            assert np.array_equal(mine[k], ref[r][k]), f"{name} rank {r} field {k}: rel max {common.rel_max(mine[k], ref[r][k]):.3e}"
+    for (src, dst), msgs in record.items():
+        refm = common.read_dump(case_dir, src, dst, np.float64)
+        assert len(refm) == len(msgs)
+        for i, ((tag, a), b) in enumerate(zip(refm, msgs)):
+            assert a.tobytes() == b.tobytes(), f"{name} {src}->{dst} message {i} differs"
